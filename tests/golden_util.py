@@ -1,0 +1,56 @@
+"""Load tests/golden/*.npz (made by tests/golden/make_golden.py from the unmodified reference)."""
+import os
+
+import numpy as np
+
+from tencent_recommendation_2025_b200.layout import FeatureLayout, DEFAULT_FEAT_TYPES
+from tencent_recommendation_2025_b200.synth import PackedCall
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TRAIN_CASES = ["baseline_h32", "o1_h64", "o1_h64_mm2", "baseline_l102_nomm"]
+
+
+class Golden:
+    def __init__(self, name):
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+        z = self.z
+        self.B, self.L, self.H = int(z["B"]), int(z["L"]), int(z["H"])
+        self.mm_ids = [str(x) for x in z["mm_ids"]]
+        stats = {str(k): int(v) for k, v in zip(z["stat_keys"], z["stat_vals"])}
+        ft = {k: list(v) for k, v in DEFAULT_FEAT_TYPES.items()}
+        ft["item_emb"] = self.mm_ids
+        self.feat_types, self.feat_statistics = ft, stats
+        self.item_num, self.user_num = int(z["item_num"]), int(z["user_num"])
+        self.layout = FeatureLayout(self.user_num, self.item_num, stats, ft, self.H)
+        self.n_steps = int(z["n_steps"]) if "n_steps" in z else 0
+        self.lr = float(z["lr"]) if "lr" in z else None
+        self.wd = float(z["wd"]) if "wd" in z else None
+
+    def params0(self):
+        return {k[len("param0/"):]: self.z[k] for k in self.z.files if k.startswith("param0/")}
+
+    def group(self, prefix):
+        return {k[len(prefix):]: self.z[k] for k in self.z.files if k.startswith(prefix)}
+
+    def call(self, step, c) -> PackedCall:
+        pre = f"s{step}/c{c}/"
+        z = self.z
+        mm = [z[pre + f"mm_x{j}"] for j in range(len(self.mm_ids))]
+        inc = (pre + "mask") in z.files
+        return PackedCall(self.B, self.L, inc, z[pre + "ids"], z[pre + "arr_off"], z[pre + "arr_val"], mm,
+                          seq=z[pre + "seq"], mask=z[pre + "mask"] if inc else None)
+
+    def calls(self, step):
+        return [self.call(step, c) for c in range(3)]
+
+    def outs(self, step):
+        return [self.z[f"s{step}/c{c}/out"] for c in range(3)]
+
+    def upstream(self, step):
+        return [self.z[f"s{step}/c{c}/upstream"] for c in range(3)]
+
+    def sweep_call(self) -> PackedCall:
+        z = self.z
+        mm = [z[f"mm_x{j}"] for j in range(len(self.mm_ids))]
+        return PackedCall(1, self.L, False, z["ids"], z["arr_off"], z["arr_val"], mm, seq=z["seq"], mask=None)
