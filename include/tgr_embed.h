@@ -1,0 +1,192 @@
+/* tgr_embed.h — C ABI of the B200 (sm_100a) sparse-feature embedding path for the TencentGR
+ * baseline models (Puiching-Memory/Tencent_Recommendation_2025).
+ *
+ * The reference has NO FFI / plugin interface: its boundary is the Python method
+ *     BaselineModel.feat2emb(seq, feature_array, mask=None, include_user=False)
+ * (model/BaseLine/model.py:226-310, model/BaseLineO1/model.py:327-416) plus what autograd and
+ * torch.optim.AdamW do underneath it (model/BaseLine/main.py:131,188-190). This header is the
+ * boundary the build introduces UNDER that method; each entry cites the reference lines whose
+ * work it replaces. Host code (tencent_recommendation_2025_b200/engine.py) binds it with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev / inside the structs is a DEVICE pointer
+ *     borrowed for the duration of the call (torch owns all memory; the library allocates nothing);
+ *   - every entry takes the CUDA stream as `void* stream` (cudaStream_t), is asynchronous, does no
+ *     host synchronisation and keeps no global mutable state (re-entrant across streams);
+ *   - return 0 on success, negative on error; tgr_last_error() gives the thread's last message;
+ *   - ids are int32, id 0 is the padding row of every table (nn.Embedding(padding_idx=0),
+ *     model.py:115-116,158-165); tables are row-major fp32 [rows, H], H % 4 == 0.
+ */
+#ifndef TGR_EMBED_H_
+#define TGR_EMBED_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGR_ABI_VERSION 1
+
+#define TGR_MAX_TABLES 64
+#define TGR_MAX_SLOTS 32
+#define TGR_MAX_ARRAYS 8
+#define TGR_MAX_CALLS 4
+
+/* slot kinds */
+#define TGR_KIND_SINGLE 0 /* one id per token: copy one table row            (model.py:242-247,275) */
+#define TGR_KIND_ARRAY 1  /* ragged id list: rows summed left to right       (model.py:277)         */
+#define TGR_KIND_MM 2     /* dense mm vector: projected by tgr_mm_proj_*     (model.py:281-299)     */
+
+#define TGR_SIDE_ITEM 0
+#define TGR_SIDE_USER 1
+
+#define TGR_DTYPE_F32 0
+#define TGR_DTYPE_BF16 1
+
+/* source code of one gradient contribution: call << 29 | slot << 24 | token */
+#define TGR_SRC_CALL_SHIFT 29
+#define TGR_SRC_SLOT_SHIFT 24
+#define TGR_SRC_TOKEN_MASK 0x00FFFFFFu
+
+/* One embedding table = one nn.Embedding(rows, H, padding_idx=0) (model.py:115-116,158-165).
+ * Global key of a row = key_base + id; key bases are cumulative row counts in table order. */
+typedef struct tgr_table {
+  float* weight;     /* [rows, H] */
+  float* exp_avg;    /* Adam m, [rows, H]; NULL unless a row update is requested */
+  float* exp_avg_sq; /* Adam v, [rows, H] */
+  float* grad;       /* dense [rows, H] gradient target for tgr_scatter_rows (parity mode), else NULL */
+  int64_t rows;
+  int64_t key_base;
+} tgr_table_t;
+
+/* One H-wide column block of a concat buffer (concat order: model.py:244-245,252-263,281-299). */
+typedef struct tgr_slot {
+  int32_t kind;  /* TGR_KIND_* */
+  int32_t side;  /* TGR_SIDE_* */
+  int32_t col;   /* first column (elements) in that side's concat buffer */
+  int32_t table; /* index into the table array (SINGLE/ARRAY) */
+  int32_t src;   /* SINGLE: column of ids; ARRAY: index into arr_*; MM: unused */
+} tgr_slot_t;
+
+/* One feat2emb call in packed form (replaces the 22/14 feat2tensor tensors of model.py:186-224,272). */
+typedef struct tgr_call {
+  int32_t T;       /* tokens = B*L */
+  int32_t n_slots; /* entries of slots[] */
+  int32_t n_single; /* columns of ids */
+  int32_t n_arrays;
+  tgr_slot_t slots[TGR_MAX_SLOTS];
+  const int32_t* ids;                     /* [T, n_single] token-major; already type-masked (model.py:240-243) */
+  const int32_t* arr_off[TGR_MAX_ARRAYS]; /* [T+1] CSR offsets into arr_val (absolute) */
+  const int32_t* arr_tok[TGR_MAX_ARRAYS]; /* [nnz_a] token of each value (COO row), used by the backward */
+  int32_t arr_begin[TGR_MAX_ARRAYS];      /* first value of array a inside arr_val */
+  int32_t arr_nnz[TGR_MAX_ARRAYS];
+  const int32_t* arr_val;                 /* concatenated values of all arrays, padding id 0 dropped */
+  void* item_cat;                         /* fwd: OUT concat [T, item_ld]; bwd: IN d(concat) */
+  void* user_cat;                         /* NULL when the call has no user side */
+  int64_t item_ld;                        /* row pitch in elements */
+  int64_t user_ld;
+  int32_t cat_dtype;                      /* TGR_DTYPE_* of item_cat / user_cat */
+  int32_t reserved;
+  int32_t* err_flag;                      /* optional device int32: set to 1 + slot index on an out-of-range id
+                                             (the reference raises IndexError / device-asserts); the offending
+                                             lookup reads row 0 instead of faulting. NULL = no report. */
+} tgr_call_t;
+
+/* AdamW hyper-parameters of the row update (model/BaseLine/main.py:131; torch/optim/adam.py:416-419,457,476,531-547).
+ * step counts from 1; bias corrections are formed on the host in double exactly as torch does. */
+typedef struct tgr_adam {
+  float lr, beta1, beta2, eps, weight_decay;
+  float step_size;       /* lr / (1 - beta1^step) */
+  float bc2_sqrt;        /* sqrt(1 - beta2^step) */
+  float grad_scale;      /* multiplied into the reduced gradient before the update (1/loss_scale; 1 otherwise) */
+  float decay;           /* 1 - lr*weight_decay, formed in double then rounded (param.mul_) */
+  float one_minus_beta1; /* float(1 - beta1) in double (lerp_ weight) */
+  float one_minus_beta2; /* float(1 - beta2) in double (addcmul_ value) */
+  float reserved;
+} tgr_adam_t;
+
+int tgr_abi_version(void);
+const char* tgr_last_error(void);
+
+/* ---- forward ---------------------------------------------------------------------------------
+ * Fused multi-table gather + array sum-pool + concat write: every SINGLE/ARRAY slot of the call in
+ * one launch, straight into item_cat/user_cat (fp32 or bf16 RNE). Replaces aten::embedding x(15|24),
+ * sum(2) x4 and cat x(1|2) of model.py:240-247,267-279,302,305 (SURVEY.md §2.2 K1,K3,K4,K6). */
+int tgr_fwd_gather_pool_concat(const tgr_table_t* tables, int n_tables, int H, const tgr_call_t* call, void* stream);
+
+/* mm projection forward: out[t, 0:H] = x[t, :] . W^T + b, written at `out` (already offset to the slot's
+ * column) with row pitch out_ld. Replaces emb_transform[k](x) + its cat copy (model.py:297,299,302). */
+int tgr_mm_proj_fwd(const void* x, int x_dtype, int64_t T, int mm_dim, const float* W, const float* bias, int H,
+                    void* out, int64_t out_ld, int out_dtype, void* stream);
+
+/* mm projection backward: dW[H, mm_dim] (+)= dY^T . x ; db[H] (+)= sum_t dY. dY is read in place from the
+ * concat gradient (pointer already offset to the slot's column). Deterministic split-T reduction.
+ * workspace: tgr_mm_proj_bwd_workspace_bytes(). (autograd of model.py:297) */
+size_t tgr_mm_proj_bwd_workspace_bytes(int64_t T, int mm_dim, int H);
+int tgr_mm_proj_bwd(const void* x, int x_dtype, int64_t T, int mm_dim, const void* dy, int64_t dy_ld, int dy_dtype,
+                    int H, float* dW, float* db, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- backward --------------------------------------------------------------------------------
+ * Replaces embedding_dense_backward x54 + dense AdamW over every table row (SURVEY.md §2.2 K8,K10).
+ * Pipeline: build_keys -> sort_pairs -> [dedup] -> segment_reduce(+adam) . All stages deterministic. */
+
+/* Upper bound of gradient contributions of `n_calls` calls (all id slots incl. padding + all array values). */
+int64_t tgr_bwd_max_entries(const tgr_call_t* calls, int n_calls);
+
+/* Emit (global key, source code) for every non-padding id, compacted, in (call, token, slot) order.
+ * n_valid_dev (int32, device) receives the count. keys/srcs must hold tgr_bwd_max_entries() items.
+ * workspace >= tgr_build_keys_workspace_bytes(max_entries). */
+size_t tgr_build_keys_workspace_bytes(int64_t max_entries);
+int tgr_bwd_build_keys(const tgr_table_t* tables, int n_tables, const tgr_call_t* calls, int n_calls,
+                       uint32_t* keys, uint32_t* srcs, int32_t* n_valid_dev, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* Stable LSD radix sort of (key, src) pairs on key bits [0, key_bits). n is the host-known entry count. */
+size_t tgr_sort_workspace_bytes(int64_t n);
+int tgr_sort_pairs(const uint32_t* keys_in, const uint32_t* srcs_in, uint32_t* keys_out, uint32_t* srcs_out, int64_t n,
+                   int key_bits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Run-length encode sorted keys: unique keys, segment offsets [U+1] (counts = diff), per-entry segment index
+ * (optional, [n]) and U to n_unique_dev. Bit-exact with torch.unique(sorted=True, return_inverse/return_counts). */
+size_t tgr_dedup_workspace_bytes(int64_t n);
+int tgr_dedup(const uint32_t* keys_sorted, int64_t n, uint32_t* uniq, int32_t* seg_off, int32_t* seg_of_entry,
+              int32_t* n_unique_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Segmented reduction of the concat-gradient rows over the sorted pairs; fixed tiling => bitwise reproducible.
+ *   mode 0: write the reduced row of the u-th unique key to grads_out[u, 0:H] (u from seg_of_entry, tgr_dedup)
+ *   mode 1: fused AdamW row update in place on tables[].weight/exp_avg/exp_avg_sq (no grads_out, no dedup)
+ * calls[].item_cat/user_cat are the concat GRADIENTS here. */
+size_t tgr_reduce_workspace_bytes(int64_t n, int H);
+int tgr_bwd_reduce(const tgr_table_t* tables, int n_tables, int H, const tgr_call_t* calls, int n_calls,
+                   const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n, int mode,
+                   const int32_t* seg_of_entry, float* grads_out, const tgr_adam_t* adam, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* AdamW row update from already-reduced rows: for u < *n_unique_dev: row(uniq[u]) <- adamw(row, grads[u]). */
+int tgr_adam_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
+                  const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam, void* stream);
+
+/* Parity mode: add reduced rows into dense per-table gradients tables[].grad (each key once => plain store-add). */
+int tgr_scatter_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
+                     const int32_t* n_unique_dev, int64_t max_unique, void* stream);
+
+/* ---- row-sharded multi-GPU helpers (no reference counterpart) ------------------
+ * owner = key mod W, local_row = key div W. Input keys sorted ascending & unique. Outputs: keys grouped by
+ * owner (ascending inside each bucket), bucket counts [W], and for each input position its slot in the
+ * bucketed order (perm). */
+size_t tgr_route_workspace_bytes(int64_t max_unique, int W);
+int tgr_route_bucket(const uint32_t* uniq, const int32_t* n_unique_dev, int64_t max_unique, int W,
+                     uint32_t* bucketed_local_rows, int32_t* perm, int32_t* counts_dev, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* Gather rows of a flat table by local row index: out[i, :] = table[rows[i], :] for i < *n_dev. */
+int tgr_gather_rows(const float* table, int H, const uint32_t* rows, const int32_t* n_dev, int64_t max_n, float* out,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGR_EMBED_H_ */

@@ -237,16 +237,24 @@ def accumulate(grads_in_autograd_order: Sequence[Dict[str, np.ndarray]]) -> Dict
 # ---------------------------------------------------------------------------------------------
 # AdamW (torch/optim/adam.py _single_tensor_adam, decoupled weight decay)
 # ---------------------------------------------------------------------------------------------
+def _fma32(a, b, c):
+    """float32 fma(a, b, c): the product of two float32 is exact in float64; one final rounding."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(F32)
+
+
 def adamw_dense(w, g, m, v, step: int, lr=1e-3, beta1=0.9, beta2=0.98, eps=1e-8, wd=1e-2):
-    """One dense AdamW step on one tensor; returns new (w, m, v). ``step`` counts from 1."""
-    w = (w * F32(1 - lr * wd)).astype(F32)                       # adam.py:416-419 (param.mul_)
-    m = (m + (g - m) * F32(1 - beta1)).astype(F32)               # adam.py:457  (lerp_)
-    v = (v * F32(beta2) + (g * g) * F32(1 - beta2)).astype(F32)  # adam.py:476  (mul_.addcmul_)
+    """One dense AdamW step on one tensor; returns new (w, m, v). ``step`` counts from 1.
+
+    Rounding order = torch 2.11 CPU kernels (probed): lerp_ and addcmul_ fuse their last multiply-add.
+    """
+    w = (w * F32(1 - lr * wd)).astype(F32)                             # adam.py:416-419 (param.mul_)
+    m = _fma32(F32(1 - beta1), (g - m).astype(F32), m)                 # adam.py:457  (lerp_)
+    v = _fma32((F32(1 - beta2) * g).astype(F32), g, (v * F32(beta2)).astype(F32))   # adam.py:476
     bc1 = 1 - beta1 ** step
     bc2 = 1 - beta2 ** step
     step_size = lr / bc1
-    denom = (np.sqrt(v) / F32(bc2 ** 0.5) + F32(eps)).astype(F32)   # adam.py:536-547
-    w = (w - F32(step_size) * (m / denom)).astype(F32)
+    denom = ((np.sqrt(v) / F32(bc2 ** 0.5)).astype(F32) + F32(eps)).astype(F32)     # adam.py:536-547
+    w = (w + ((F32(-step_size) * m).astype(F32) / denom).astype(F32)).astype(F32)
     return w, m, v
 
 

@@ -1,0 +1,125 @@
+"""ctypes binding of libtgr_embed.so (include/tgr_embed.h). Fails loudly when the library is missing —
+there is no CPU or PyTorch fallback for the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libtgr_embed.so")
+
+TGR_ABI_VERSION = 1
+MAX_TABLES, MAX_SLOTS, MAX_ARRAYS, MAX_CALLS = 64, 32, 8, 4
+KIND_SINGLE, KIND_ARRAY, KIND_MM = 0, 1, 2
+DTYPE_F32, DTYPE_BF16 = 0, 1
+
+i32p = C.POINTER(C.c_int32)
+u32p = C.POINTER(C.c_uint32)
+f32p = C.POINTER(C.c_float)
+
+
+class Table(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("grad", C.c_void_p),
+                ("rows", C.c_int64), ("key_base", C.c_int64)]
+
+
+class Slot(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("side", C.c_int32), ("col", C.c_int32), ("table", C.c_int32), ("src", C.c_int32)]
+
+
+class Call(C.Structure):
+    _fields_ = [("T", C.c_int32), ("n_slots", C.c_int32), ("n_single", C.c_int32), ("n_arrays", C.c_int32),
+                ("slots", Slot * MAX_SLOTS),
+                ("ids", C.c_void_p),
+                ("arr_off", C.c_void_p * MAX_ARRAYS), ("arr_tok", C.c_void_p * MAX_ARRAYS),
+                ("arr_begin", C.c_int32 * MAX_ARRAYS), ("arr_nnz", C.c_int32 * MAX_ARRAYS),
+                ("arr_val", C.c_void_p),
+                ("item_cat", C.c_void_p), ("user_cat", C.c_void_p),
+                ("item_ld", C.c_int64), ("user_ld", C.c_int64),
+                ("cat_dtype", C.c_int32), ("reserved", C.c_int32),
+                ("err_flag", C.c_void_p)]
+
+
+class Adam(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("step_size", C.c_float), ("bc2_sqrt", C.c_float),
+                ("grad_scale", C.c_float), ("decay", C.c_float), ("one_minus_beta1", C.c_float),
+                ("one_minus_beta2", C.c_float), ("reserved", C.c_float)]
+
+
+def make_adam(lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, step: int,
+              grad_scale: float = 1.0) -> "Adam":
+    """Scalars exactly as torch/optim/adam.py forms them (python doubles, rounded once to float)."""
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    return Adam(lr, beta1, beta2, eps, weight_decay, lr / bc1, bc2 ** 0.5, grad_scale, 1 - lr * weight_decay,
+                1 - beta1, 1 - beta2, 0.0)
+
+
+# name -> (restype, argtypes); every symbol include/tgr_embed.h declares
+SIGNATURES = {
+    "tgr_abi_version": (C.c_int, []),
+    "tgr_last_error": (C.c_char_p, []),
+    "tgr_fwd_gather_pool_concat": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Call), C.c_void_p]),
+    "tgr_mm_proj_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                  C.c_int64, C.c_int, C.c_void_p]),
+    "tgr_mm_proj_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "tgr_mm_proj_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tgr_bwd_max_entries": (C.c_int64, [C.POINTER(Call), C.c_int]),
+    "tgr_build_keys_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "tgr_bwd_build_keys": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(Call), C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tgr_sort_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "tgr_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                 C.c_size_t, C.c_void_p]),
+    "tgr_dedup_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "tgr_dedup": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.c_size_t, C.c_void_p]),
+    "tgr_reduce_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "tgr_bwd_reduce": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Call), C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Adam), C.c_void_p, C.c_size_t,
+                                 C.c_void_p]),
+    "tgr_adam_rows": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.POINTER(Adam), C.c_void_p]),
+    "tgr_scatter_rows": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p]),
+    "tgr_route_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "tgr_route_bucket": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tgr_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class TgrError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and type the C-ABI library. Raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise TgrError(f"{LIB_PATH} not found: build it with `python -m tencent_recommendation_2025_b200.build` "
+                           "(there is no CPU fallback for this path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if lib.tgr_abi_version() != TGR_ABI_VERSION:
+            raise TgrError(f"ABI mismatch: library {lib.tgr_abi_version()} vs binding {TGR_ABI_VERSION}")
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().tgr_last_error().decode("utf-8", "replace")
+        raise TgrError(f"{what or 'tgr call'} failed ({rc}): {msg}")

@@ -1,0 +1,792 @@
+// Backward of the sparse-feature embedding path: deterministic sparse gradient + fused AdamW row update.
+//
+// Replaces what autograd + the optimizer do under the reference's feat2emb:
+//   embedding_dense_backward x 54 per step (sort + segmented sum into DENSE zero-filled [rows, H] grads)
+//   + dense AdamW over EVERY row of every table (model/BaseLine/main.py:131,188-190)
+// with a pipeline that touches only the rows a step actually used:
+//
+//   build_keys   (key = table.key_base + id, src = call|slot|token) for every non-padding id of up to 4
+//                calls, compacted in (call, token, slot) order (count -> scan -> emit, no atomics)
+//   sort_pairs   stable LSD radix sort on the key bits only (stability keeps each row's contributions
+//                in ascending (call, token) order = embedding_dense_backward's per-row order, F16)
+//   dedup        run-length encode -> unique keys / segment offsets / per-entry segment index
+//   reduce       fixed-tile segmented sum of the concat-gradient rows the sources point at; short runs
+//                are summed sequentially in order, runs crossing tile borders are stitched from
+//                per-tile partials in a fixed order (bitwise reproducible, no float atomics);
+//                mode 1 applies the AdamW row update in the same pass (w, m, v read+written once)
+//
+// All kernels are HBM/L2-bound integer/byte movers: 128-bit row accesses, one LANES=H/4 thread
+// group per gradient row, grids sized by the (host-known) entry count.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "tgr_common.cuh"
+
+namespace tgr {
+
+// =================================================================================================
+// generic ordered compaction: count -> single-CTA scan -> emit           (1024 entries per block)
+// =================================================================================================
+constexpr int kScanBlock = 1024;
+
+template <class F>
+__global__ void __launch_bounds__(kScanBlock) flag_count_kernel(const __grid_constant__ F f, int64_t n, int32_t* __restrict__ block_count) {
+  const int64_t e = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  const int v = (e < n) && f.valid(e);
+  const int c = __syncthreads_count(v);
+  if (threadIdx.x == 0) block_count[blockIdx.x] = c;
+}
+
+// exclusive scan of block counts in place; total -> *total_out (and optional second copy)
+__global__ void __launch_bounds__(kScanBlock) block_scan_kernel(int32_t* __restrict__ block_count, int n_blocks,
+                                                                int32_t* __restrict__ total_out) {
+  __shared__ int32_t warp_sum[32];
+  __shared__ int32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < n_blocks; base += kScanBlock) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_blocks ? block_count[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_sum[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int incl = x + (wid ? warp_sum[wid - 1] : 0) + carry;
+    if (i < n_blocks) block_count[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == kScanBlock - 1) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+}
+
+// position of this thread's entry among the block's valid entries (exclusive), ordered by thread index
+__device__ __forceinline__ int block_rank(int v, int32_t* warp_cnt /*[32] shared*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned b = __ballot_sync(0xffffffffu, v);
+  const int r = __popc(b & ((1u << lane) - 1u));
+  if (lane == 0) warp_cnt[wid] = __popc(b);
+  __syncthreads();
+  if (wid == 0) {
+    int w = warp_cnt[lane];
+    const int orig = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    warp_cnt[lane] = w - orig;  // exclusive
+  }
+  __syncthreads();
+  return r + warp_cnt[wid];
+}
+
+template <class F>
+__global__ void __launch_bounds__(kScanBlock) flag_emit_kernel(const __grid_constant__ F f, int64_t n, const int32_t* __restrict__ block_off) {
+  __shared__ int32_t warp_cnt[32];
+  const int64_t e = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  const int v = (e < n) && f.valid(e);
+  const int r = block_rank(v, warp_cnt);
+  const int64_t pos = (int64_t)block_off[blockIdx.x] + r;
+  if (v) f.emit(e, pos);
+  if (e < n) f.every(e, pos + v - 1);  // index of the last valid entry at or before e
+}
+
+// =================================================================================================
+// build_keys
+// =================================================================================================
+constexpr int kMaxKeySegs = TGR_MAX_CALLS * (1 + TGR_MAX_ARRAYS);
+
+struct KeySeg {
+  const int32_t* vals;  // SINGLE: ids matrix; ARRAY: arr_val + arr_begin
+  const int32_t* toks;  // ARRAY: token of each value
+  int64_t start;        // first global entry
+  int64_t count;
+  int32_t call;
+  int32_t n_cols;       // SINGLE: n_single (>0); ARRAY: 0
+  int32_t slot;         // ARRAY: slot index in the call
+  uint32_t key_base;    // ARRAY
+  int32_t rows;         // ARRAY
+  int32_t pad;
+};
+
+struct KeyParams {
+  KeySeg seg[kMaxKeySegs];
+  uint32_t col_key_base[TGR_MAX_CALLS][TGR_MAX_SLOTS];  // SINGLE: by ids column
+  int32_t col_rows[TGR_MAX_CALLS][TGR_MAX_SLOTS];
+  uint8_t col_slot[TGR_MAX_CALLS][TGR_MAX_SLOTS];
+  int32_t n_seg;
+};
+
+struct KeyFunctor {
+  KeyParams kp;  // ~3 KB, lives in the kernel parameter (constant) bank
+  uint32_t* keys;
+  uint32_t* srcs;
+
+  __device__ __forceinline__ bool decode(int64_t e, uint32_t& key, uint32_t& src) const {
+    const KeyParams* p = &kp;
+    int s = 0;
+    const int ns = p->n_seg;
+    while (s + 1 < ns && e >= p->seg[s + 1].start) ++s;
+    const KeySeg& g = p->seg[s];
+    const int64_t i = e - g.start;
+    if (g.n_cols > 0) {
+      const int id = __ldg(g.vals + i);
+      const int t = (int)(i / g.n_cols);
+      const int c = (int)(i - (int64_t)t * g.n_cols);
+      if (id <= 0 || id >= p->col_rows[g.call][c]) return false;
+      key = p->col_key_base[g.call][c] + (uint32_t)id;
+      src = ((uint32_t)g.call << TGR_SRC_CALL_SHIFT) | ((uint32_t)p->col_slot[g.call][c] << TGR_SRC_SLOT_SHIFT) | (uint32_t)t;
+    } else {
+      const int id = __ldg(g.vals + i);
+      if (id <= 0 || id >= g.rows) return false;
+      key = g.key_base + (uint32_t)id;
+      src = ((uint32_t)g.call << TGR_SRC_CALL_SHIFT) | ((uint32_t)g.slot << TGR_SRC_SLOT_SHIFT) | (uint32_t)__ldg(g.toks + i);
+    }
+    return true;
+  }
+  __device__ __forceinline__ bool valid(int64_t e) const {
+    uint32_t k, s;
+    return decode(e, k, s);
+  }
+  __device__ __forceinline__ void emit(int64_t e, int64_t pos) const {
+    uint32_t k, s;
+    decode(e, k, s);
+    keys[pos] = k;
+    srcs[pos] = s;
+  }
+  __device__ __forceinline__ void every(int64_t, int64_t) const {}
+};
+
+// =================================================================================================
+// dedup (run-length encode of sorted keys)
+// =================================================================================================
+struct HeadFunctor {
+  const uint32_t* __restrict__ k;
+  uint32_t* uniq;
+  int32_t* seg_off;
+  int32_t* seg_of_entry;  // optional
+  __device__ __forceinline__ bool valid(int64_t e) const { return e == 0 || k[e] != k[e - 1]; }
+  __device__ __forceinline__ void emit(int64_t e, int64_t pos) const {
+    uniq[pos] = k[e];
+    seg_off[pos] = (int32_t)e;
+  }
+  __device__ __forceinline__ void every(int64_t e, int64_t seg) const {
+    if (seg_of_entry) seg_of_entry[e] = (int32_t)seg;
+  }
+};
+
+__global__ void dedup_finish_kernel(int32_t* seg_off, const int32_t* n_unique_dev, int64_t n) {
+  seg_off[*n_unique_dev] = (int32_t)n;
+}
+
+// =================================================================================================
+// reduce: fixed-tile segmented sum (+ fused AdamW)
+// =================================================================================================
+constexpr int kRedThreads = 256;
+constexpr int kC = 64;        // sorted entries per group tile
+constexpr int kRedUnroll = 4; // gradient rows in flight per thread
+
+struct RedParams {
+  const char* chunk_base[TGR_MAX_CALLS][TGR_MAX_SLOTS];  // d(concat) base of (call, slot), offset to the slot's column
+  int64_t ld_bytes[TGR_MAX_CALLS][TGR_MAX_SLOTS];
+  // tables (fused AdamW / key -> row)
+  float* w[TGR_MAX_TABLES];
+  float* m[TGR_MAX_TABLES];
+  float* v[TGR_MAX_TABLES];
+  uint32_t key_base[TGR_MAX_TABLES + 1];
+  int32_t n_tables;
+  const uint32_t* keys;
+  const uint32_t* srcs;
+  const int32_t* seg_of_entry;  // mode 0
+  float* grads_out;             // mode 0: [U, H]
+  float* cta_head;              // [n_cta, H]
+  float* cta_tail;              // [n_cta, H]
+  int64_t n;
+  int32_t H4;
+  int32_t mode;
+  tgr_adam_t adam;
+};
+
+__device__ __forceinline__ float adam_elem(float& w, float& m, float& v, float g, const tgr_adam_t& a) {
+  // torch/optim/adam.py _single_tensor_adam with decoupled weight decay, rounding for rounding as the CPU
+  // kernels evaluate it (probed against torch 2.11 CPU: lerp_ and addcmul_ fuse their last multiply-add):
+  //   param.mul_(1 - lr*wd)                                   w = w * decay
+  //   exp_avg.lerp_(grad, 1-beta1)                            m = fma(1-b1, g - m, m)
+  //   exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)    v = fma((1-b2)*g, g, v*b2)
+  //   denom = exp_avg_sq.sqrt() / bc2_sqrt + eps
+  //   param.addcdiv_(exp_avg, denom, value=-step_size)        w = w + (-step_size*m)/denom
+  w = __fmul_rn(w, a.decay);
+  m = __fmaf_rn(a.one_minus_beta1, __fsub_rn(g, m), m);
+  v = __fmaf_rn(__fmul_rn(a.one_minus_beta2, g), g, __fmul_rn(v, a.beta2));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), a.bc2_sqrt), a.eps);
+  w = __fadd_rn(w, __fdiv_rn(__fmul_rn(-a.step_size, m), denom));
+  return w;
+}
+
+__device__ __forceinline__ void adam_row4(float4* wp, float4* mp, float4* vp, float4 g, const tgr_adam_t& a) {
+  float4 w = *wp, m = *mp, v = *vp;
+  g.x *= a.grad_scale; g.y *= a.grad_scale; g.z *= a.grad_scale; g.w *= a.grad_scale;
+  adam_elem(w.x, m.x, v.x, g.x, a);
+  adam_elem(w.y, m.y, v.y, g.y, a);
+  adam_elem(w.z, m.z, v.z, g.z, a);
+  adam_elem(w.w, m.w, v.w, g.w, a);
+  *wp = w; *mp = m; *vp = v;
+}
+
+__device__ __forceinline__ int find_table(const uint32_t* key_base, int n_tables, uint32_t key) {
+  int lo = 0, hi = n_tables;  // key_base[lo] <= key < key_base[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (key >= key_base[mid]) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// final value of one unique row: either AdamW in place, or store into the compact gradient buffer
+template <int LANES, int NJ>
+__device__ __forceinline__ void finish_row(const RedParams& p, uint32_t key, int64_t entry, const float4 (&acc)[NJ], int lane) {
+  const int H4 = p.H4;
+  if (p.mode == 1) {
+    const int t = find_table(p.key_base, p.n_tables, key);
+    const size_t row = (size_t)(key - p.key_base[t]) * (size_t)(H4 * 4);
+    float4* wp = reinterpret_cast<float4*>(p.w[t] + row);
+    float4* mp = reinterpret_cast<float4*>(p.m[t] + row);
+    float4* vp = reinterpret_cast<float4*>(p.v[t] + row);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = lane + j * LANES;
+      if (c < H4) adam_row4(wp + c, mp + c, vp + c, acc[j], p.adam);
+    }
+  } else {
+    const int u = __ldg(p.seg_of_entry + entry);
+    float4* dst = reinterpret_cast<float4*>(p.grads_out + (size_t)u * (size_t)(H4 * 4));
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = lane + j * LANES;
+      if (c < H4) dst[c] = acc[j];
+    }
+  }
+}
+
+template <bool BF16>
+__device__ __forceinline__ float4 load_grad4(const RedParams& p, uint32_t src, int c) {
+  const int call = src >> TGR_SRC_CALL_SHIFT;
+  const int slot = (src >> TGR_SRC_SLOT_SHIFT) & 31;
+  const uint32_t tok = src & TGR_SRC_TOKEN_MASK;
+  const char* row = p.chunk_base[call][slot] + (size_t)tok * p.ld_bytes[call][slot];
+  if constexpr (BF16) return unpack_bf16x4(ld_stream_u2(reinterpret_cast<const uint2*>(row) + c));
+  else return ld_stream(reinterpret_cast<const float4*>(row) + c);
+}
+
+// One CTA = G groups x kC sorted entries. NJ = float4 columns per lane (1 for H <= 128).
+template <int LANES, int NJ, bool BF16>
+__global__ void __launch_bounds__(kRedThreads) reduce_tiles_kernel(const __grid_constant__ RedParams p) {
+  constexpr int G = kRedThreads / LANES;
+  constexpr int TILE = G * kC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem_raw);            // [TILE + 2]  (index 0 = entry before the tile)
+  uint32_t* s_srcs = s_keys + TILE + 2;                                // [TILE]
+  float4* s_head = reinterpret_cast<float4*>(s_srcs + TILE + 2);       // [G][H4]   (16 B aligned: (2*TILE+4)*4 bytes)
+  float4* s_tail = s_head + G * p.H4;                                  // [G][H4]
+  int32_t* s_flag = reinterpret_cast<int32_t*>(s_tail + G * p.H4);     // [G] bit0 has_head, bit1 head_through, bit2 has_tail
+  uint32_t* s_tkey = reinterpret_cast<uint32_t*>(s_flag + G);          // [G] key of the tail run
+
+  const int tid = threadIdx.x, lane = tid % LANES, grp = tid / LANES;
+  const int H4 = p.H4;
+  const int64_t n = p.n;
+  const int64_t cta_a = (int64_t)blockIdx.x * TILE;
+  const int64_t cta_b = min(n, cta_a + TILE);
+  const int cnt_cta = (int)(cta_b - cta_a);
+
+  for (int i = tid; i < cnt_cta + 2; i += kRedThreads) {
+    const int64_t e = cta_a - 1 + i;
+    s_keys[i] = (e >= 0 && e < n) ? __ldg(p.keys + e) : 0xFFFFFFFFu;  // 0xFFFFFFFF never equals a real key
+  }
+  for (int i = tid; i < cnt_cta; i += kRedThreads) s_srcs[i] = __ldg(p.srcs + cta_a + i);
+  if (tid < G) s_flag[tid] = 0;
+  __syncthreads();
+
+  const int ga = grp * kC;                       // local range of this group
+  const int gb = min(cnt_cta, ga + kC);
+  if (ga < gb) {
+    float4 acc[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t cur = s_keys[ga + 1];
+    const bool from_prev = (s_keys[ga] == cur);
+    int run_start = ga;
+    for (int e0 = ga; e0 < gb; e0 += kRedUnroll) {
+      float4 g[kRedUnroll][NJ];
+#pragma unroll
+      for (int u = 0; u < kRedUnroll; ++u) {
+        if (e0 + u < gb) {
+          const uint32_t src = s_srcs[e0 + u];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int c = lane + j * LANES;
+            if (c < H4) g[u][j] = load_grad4<BF16>(p, src, c);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRedUnroll; ++u) {
+        const int e = e0 + u;
+        if (e < gb) {
+          const uint32_t k = s_keys[e + 1];
+          if (k != cur) {
+            // the run [run_start, e) ended inside this tile
+            if (run_start == ga && from_prev) {
+#pragma unroll
+              for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) s_head[grp * H4 + c] = acc[j]; }
+              if (lane == 0) s_flag[grp] |= 1;
+            } else {
+              finish_row<LANES, NJ>(p, cur, cta_a + run_start, acc, lane);
+            }
+            cur = k;
+            run_start = e;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = f4_add(acc[j], g[u][j]); }
+        }
+      }
+    }
+    // last run reaches the end of the group tile
+    const bool to_next = (s_keys[gb + 1] == cur);   // s_keys[cnt_cta + 1] is the entry after the CTA tile (or sentinel)
+    if (run_start == ga && from_prev) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) s_head[grp * H4 + c] = acc[j]; }
+      if (lane == 0) s_flag[grp] |= to_next ? 3 : 1;
+    } else if (to_next) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) s_tail[grp * H4 + c] = acc[j]; }
+      if (lane == 0) { s_flag[grp] |= 4; s_tkey[grp] = cur; }
+    } else {
+      finish_row<LANES, NJ>(p, cur, cta_a + run_start, acc, lane);
+    }
+  }
+  __syncthreads();
+
+  // ---- stitch runs that cross group tiles, in fixed order ----
+  const int g_active = (cnt_cta + kC - 1) / kC;
+  if (grp < g_active) {
+    const int fl = s_flag[grp];
+    if (grp == 0 && (fl & 1)) {
+      // run entering the CTA from the previous one: partial for the cross-CTA fix-up
+      float4 acc[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = s_head[c]; }
+      if (fl & 2) {
+        for (int q = 1; q < g_active; ++q) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = f4_add(acc[j], s_head[q * H4 + c]); }
+          if (!(s_flag[q] & 2)) break;
+        }
+      }
+      float4* dst = reinterpret_cast<float4*>(p.cta_head + (size_t)blockIdx.x * (size_t)(H4 * 4));
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) dst[c] = acc[j]; }
+    }
+    if (fl & 4) {
+      float4 acc[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = s_tail[grp * H4 + c]; }
+      bool open = true;  // run still continues past what has been summed
+      int q = grp + 1;
+      for (; q < g_active; ++q) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = f4_add(acc[j], s_head[q * H4 + c]); }
+        if (!(s_flag[q] & 2)) { open = false; break; }
+      }
+      if (open) {  // continues into the next CTA tile
+        float4* dst = reinterpret_cast<float4*>(p.cta_tail + (size_t)blockIdx.x * (size_t)(H4 * 4));
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) dst[c] = acc[j]; }
+      } else {
+        finish_row<LANES, NJ>(p, s_tkey[grp], cta_a + min(cnt_cta, (grp + 1) * kC) - 1, acc, lane);
+      }
+    }
+  }
+}
+
+// cross-CTA fix-up: one group per CTA tile; the tile that holds the START of a run leaving it owns the run
+template <int LANES, int NJ>
+__global__ void __launch_bounds__(kRedThreads) reduce_fixup_kernel(const __grid_constant__ RedParams p, int n_cta) {
+  constexpr int G = kRedThreads / LANES;
+  constexpr int64_t TILE = (int64_t)G * kC;
+  const int lane = threadIdx.x % LANES, grp = threadIdx.x / LANES;
+  const int c0 = blockIdx.x * G + grp;
+  if (c0 >= n_cta) return;
+  const int64_t n = p.n;
+  const int H4 = p.H4;
+  const int64_t a = (int64_t)c0 * TILE, b = min(n, a + TILE);
+  if (b >= n) return;
+  const uint32_t K = __ldg(p.keys + b - 1);
+  if (__ldg(p.keys + b) != K) return;                                        // nothing leaves this tile
+  if (a > 0 && __ldg(p.keys + a) == K && __ldg(p.keys + a - 1) == K) return;  // "through" tile: an earlier tile owns it
+  float4 acc[NJ];
+  const float4* src = reinterpret_cast<const float4*>(p.cta_tail + (size_t)c0 * (size_t)(H4 * 4));
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = src[c]; }
+  for (int t = c0 + 1; t < n_cta; ++t) {
+    const float4* hs = reinterpret_cast<const float4*>(p.cta_head + (size_t)t * (size_t)(H4 * 4));
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = f4_add(acc[j], hs[c]); }
+    const int64_t te = min(n, (int64_t)(t + 1) * TILE);
+    const bool through = (__ldg(p.keys + te - 1) == K) && te < n && (__ldg(p.keys + te) == K);
+    if (!through) break;
+  }
+  finish_row<LANES, NJ>(p, K, b - 1, acc, lane);
+}
+
+// =================================================================================================
+// row-wise kernels over the compact unique list
+// =================================================================================================
+struct RowParams {
+  float* w[TGR_MAX_TABLES];
+  float* m[TGR_MAX_TABLES];
+  float* v[TGR_MAX_TABLES];
+  float* grad[TGR_MAX_TABLES];
+  uint32_t key_base[TGR_MAX_TABLES + 1];
+  int32_t n_tables;
+  int32_t H4;
+  tgr_adam_t adam;
+};
+
+template <int MODE>  // 0: adam, 1: scatter-add into dense grads
+__global__ void __launch_bounds__(256) rows_kernel(const __grid_constant__ RowParams p, const uint32_t* __restrict__ uniq,
+                                                   const float* __restrict__ grads, const int32_t* __restrict__ n_dev) {
+  const int n = *n_dev;
+  const int H4 = p.H4;
+  const int64_t total = (int64_t)n * H4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int u = (int)(i / H4), c = (int)(i - (int64_t)u * H4);
+    const uint32_t key = __ldg(uniq + u);
+    const int t = find_table(p.key_base, p.n_tables, key);
+    const size_t row = (size_t)(key - p.key_base[t]) * (size_t)(H4 * 4);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(grads) + i);
+    if (MODE == 0) {
+      adam_row4(reinterpret_cast<float4*>(p.w[t] + row) + c, reinterpret_cast<float4*>(p.m[t] + row) + c,
+                reinterpret_cast<float4*>(p.v[t] + row) + c, g, p.adam);
+    } else if (p.grad[t] != nullptr) {  // tables without a dense gradient target are skipped
+      float4* d = reinterpret_cast<float4*>(p.grad[t] + row) + c;
+      float4 o = *d;
+      *d = f4_add(o, g);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, int H4,
+                                                          const uint32_t* __restrict__ rows,
+                                                          const int32_t* __restrict__ n_dev, float* __restrict__ out) {
+  const int n = *n_dev;
+  const int64_t total = (int64_t)n * H4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int u = (int)(i / H4), c = (int)(i - (int64_t)u * H4);
+    const size_t r = __ldg(rows + u);
+    reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(table + r * (size_t)(H4 * 4)) + c);
+  }
+}
+
+// ---- helpers -------------------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+static int fill_row_params(RowParams& rp, const tgr_table_t* tables, int n_tables, int H) {
+  TGR_REQUIRE(tables && n_tables > 0 && n_tables <= TGR_MAX_TABLES, "bad table array");
+  TGR_REQUIRE(H > 0 && H % 4 == 0, "bad H=%d", H);
+  rp.n_tables = n_tables;
+  rp.H4 = H / 4;
+  for (int t = 0; t < n_tables; ++t) {
+    rp.w[t] = tables[t].weight;
+    rp.m[t] = tables[t].exp_avg;
+    rp.v[t] = tables[t].exp_avg_sq;
+    rp.grad[t] = tables[t].grad;
+    rp.key_base[t] = (uint32_t)tables[t].key_base;
+    if (t) TGR_REQUIRE(tables[t].key_base == tables[t - 1].key_base + tables[t - 1].rows, "key bases must be cumulative");
+  }
+  rp.key_base[n_tables] = (uint32_t)(tables[n_tables - 1].key_base + tables[n_tables - 1].rows);
+  return 0;
+}
+
+}  // namespace tgr
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace tgr;
+
+extern "C" int64_t tgr_bwd_max_entries(const tgr_call_t* calls, int n_calls) {
+  int64_t n = 0;
+  for (int c = 0; c < n_calls; ++c) {
+    n += (int64_t)calls[c].T * calls[c].n_single;
+    for (int a = 0; a < calls[c].n_arrays; ++a) n += calls[c].arr_nnz[a];
+  }
+  return n;
+}
+
+extern "C" size_t tgr_build_keys_workspace_bytes(int64_t max_entries) {
+  const size_t nb = (size_t)((max_entries + kScanBlock - 1) / kScanBlock) + 1;
+  return align_up(nb * sizeof(int32_t));
+}
+
+extern "C" int tgr_bwd_build_keys(const tgr_table_t* tables, int n_tables, const tgr_call_t* calls, int n_calls,
+                                  uint32_t* keys, uint32_t* srcs, int32_t* n_valid_dev, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  TGR_REQUIRE(tables && calls && keys && srcs && n_valid_dev && workspace, "null argument");
+  TGR_REQUIRE(n_calls > 0 && n_calls <= TGR_MAX_CALLS, "n_calls=%d out of range", n_calls);
+  TGR_REQUIRE(n_tables > 0 && n_tables <= TGR_MAX_TABLES, "n_tables=%d out of range", n_tables);
+  cudaStream_t st = (cudaStream_t)stream;
+  KeyFunctor f{};
+  KeyParams& kp = f.kp;
+  int64_t total = 0;
+  int ns = 0;
+  for (int c = 0; c < n_calls; ++c) {
+    const tgr_call_t& cl = calls[c];
+    TGR_REQUIRE(cl.T >= 0 && (uint32_t)cl.T <= TGR_SRC_TOKEN_MASK, "call %d: T=%d does not fit the 24-bit token field", c, cl.T);
+    TGR_REQUIRE(cl.n_slots <= TGR_MAX_SLOTS && cl.n_single <= TGR_MAX_SLOTS && cl.n_arrays <= TGR_MAX_ARRAYS, "call %d: too many slots", c);
+    for (int i = 0; i < cl.n_slots; ++i) {
+      const tgr_slot_t& s = cl.slots[i];
+      if (s.kind == TGR_KIND_MM) continue;
+      TGR_REQUIRE(s.table >= 0 && s.table < n_tables, "call %d slot %d: bad table", c, i);
+      const tgr_table_t& tb = tables[s.table];
+      TGR_REQUIRE(tb.key_base + tb.rows <= 0xFFFFFFFFll, "key space exceeds 32 bits");
+      if (s.kind == TGR_KIND_SINGLE) {
+        TGR_REQUIRE(s.src >= 0 && s.src < cl.n_single, "call %d slot %d: bad ids column", c, i);
+        kp.col_key_base[c][s.src] = (uint32_t)tb.key_base;
+        kp.col_rows[c][s.src] = (int32_t)tb.rows;
+        kp.col_slot[c][s.src] = (uint8_t)i;
+      }
+    }
+    if (cl.T > 0 && cl.n_single > 0) {
+      TGR_REQUIRE(cl.ids != nullptr, "call %d: ids is NULL", c);
+      KeySeg& g = kp.seg[ns++];
+      g.vals = cl.ids; g.toks = nullptr; g.start = total; g.count = (int64_t)cl.T * cl.n_single;
+      g.call = c; g.n_cols = cl.n_single; g.slot = 0; g.key_base = 0; g.rows = 0;
+      total += g.count;
+    }
+    for (int i = 0; i < cl.n_slots; ++i) {
+      const tgr_slot_t& s = cl.slots[i];
+      if (s.kind != TGR_KIND_ARRAY) continue;
+      TGR_REQUIRE(s.src >= 0 && s.src < cl.n_arrays, "call %d slot %d: bad array index", c, i);
+      const int a = s.src;
+      if (cl.arr_nnz[a] <= 0) continue;
+      TGR_REQUIRE(cl.arr_val && cl.arr_tok[a], "call %d array %d: NULL pointers", c, a);
+      KeySeg& g = kp.seg[ns++];
+      g.vals = cl.arr_val + cl.arr_begin[a]; g.toks = cl.arr_tok[a]; g.start = total; g.count = cl.arr_nnz[a];
+      g.call = c; g.n_cols = 0; g.slot = i; g.key_base = (uint32_t)tables[s.table].key_base; g.rows = (int32_t)tables[s.table].rows;
+      total += g.count;
+    }
+  }
+  kp.n_seg = ns;
+  TGR_REQUIRE(workspace_bytes >= tgr_build_keys_workspace_bytes(total), "workspace too small");
+  if (total == 0) {
+    cudaMemsetAsync(n_valid_dev, 0, sizeof(int32_t), st);
+    return check_launch("build_keys(empty)");
+  }
+  TGR_REQUIRE(total < (1ll << 31), "too many entries");
+  int32_t* block_cnt = (int32_t*)workspace;
+  const int nb = (int)((total + kScanBlock - 1) / kScanBlock);
+  f.keys = keys;
+  f.srcs = srcs;
+  flag_count_kernel<<<nb, kScanBlock, 0, st>>>(f, total, block_cnt);
+  block_scan_kernel<<<1, kScanBlock, 0, st>>>(block_cnt, nb, n_valid_dev);
+  flag_emit_kernel<<<nb, kScanBlock, 0, st>>>(f, total, block_cnt);
+  return check_launch("build_keys");
+}
+
+extern "C" size_t tgr_sort_workspace_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)(n > 0 ? n : 1), 0, 32, (cudaStream_t)0);
+  return align_up(bytes);
+}
+
+extern "C" int tgr_sort_pairs(const uint32_t* keys_in, const uint32_t* srcs_in, uint32_t* keys_out, uint32_t* srcs_out,
+                              int64_t n, int key_bits, void* workspace, size_t workspace_bytes, void* stream) {
+  TGR_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
+  TGR_REQUIRE(key_bits > 0 && key_bits <= 32, "key_bits=%d out of range", key_bits);
+  if (n == 0) return 0;
+  TGR_REQUIRE(keys_in && srcs_in && keys_out && srcs_out && workspace, "null argument");
+  size_t bytes = workspace_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(workspace, bytes, keys_in, keys_out, srcs_in, srcs_out, (int)n, 0,
+                                                  key_bits, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("sort_pairs: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return check_launch("sort_pairs");
+}
+
+extern "C" size_t tgr_dedup_workspace_bytes(int64_t n) {
+  return align_up((size_t)((n + kScanBlock - 1) / kScanBlock + 1) * sizeof(int32_t));
+}
+
+extern "C" int tgr_dedup(const uint32_t* keys_sorted, int64_t n, uint32_t* uniq, int32_t* seg_off, int32_t* seg_of_entry,
+                         int32_t* n_unique_dev, void* workspace, size_t workspace_bytes, void* stream) {
+  TGR_REQUIRE(uniq && seg_off && n_unique_dev && workspace, "null argument");
+  TGR_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
+  TGR_REQUIRE(workspace_bytes >= tgr_dedup_workspace_bytes(n), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    cudaMemsetAsync(n_unique_dev, 0, sizeof(int32_t), st);
+    cudaMemsetAsync(seg_off, 0, sizeof(int32_t), st);
+    return check_launch("dedup(empty)");
+  }
+  TGR_REQUIRE(keys_sorted, "null keys");
+  int32_t* block_cnt = (int32_t*)workspace;
+  const int nb = (int)((n + kScanBlock - 1) / kScanBlock);
+  HeadFunctor f{keys_sorted, uniq, seg_off, seg_of_entry};
+  flag_count_kernel<<<nb, kScanBlock, 0, st>>>(f, n, block_cnt);
+  block_scan_kernel<<<1, kScanBlock, 0, st>>>(block_cnt, nb, n_unique_dev);
+  flag_emit_kernel<<<nb, kScanBlock, 0, st>>>(f, n, block_cnt);
+  dedup_finish_kernel<<<1, 1, 0, st>>>(seg_off, n_unique_dev, n);
+  return check_launch("dedup");
+}
+
+namespace tgr {
+static int red_lanes(int H4) { return H4 <= 8 ? 8 : (H4 <= 16 ? 16 : 32); }
+static int red_tile(int H4) { return (kRedThreads / red_lanes(H4)) * kC; }
+}  // namespace tgr
+
+extern "C" size_t tgr_reduce_workspace_bytes(int64_t n, int H) {
+  const int H4 = H / 4;
+  const int64_t n_cta = (n + red_tile(H4) - 1) / red_tile(H4);
+  return 2 * align_up((size_t)(n_cta + 1) * H * sizeof(float));
+}
+
+template <int LANES, int NJ>
+static int launch_reduce(RedParams& p, bool bf16, int n_cta, cudaStream_t st) {
+  constexpr int G = kRedThreads / LANES;
+  constexpr int TILE = G * kC;
+  const size_t smem = (size_t)(2 * TILE + 4) * 4 + (size_t)2 * G * p.H4 * 16 + (size_t)2 * G * 4;
+  if (bf16) {
+    cudaFuncSetAttribute(reduce_tiles_kernel<LANES, NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reduce_tiles_kernel<LANES, NJ, true><<<n_cta, kRedThreads, smem, st>>>(p);
+  } else {
+    cudaFuncSetAttribute(reduce_tiles_kernel<LANES, NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reduce_tiles_kernel<LANES, NJ, false><<<n_cta, kRedThreads, smem, st>>>(p);
+  }
+  if (int rc = check_launch("reduce_tiles")) return rc;
+  if (n_cta > 1) {
+    reduce_fixup_kernel<LANES, NJ><<<(n_cta + G - 1) / G, kRedThreads, 0, st>>>(p, n_cta);
+    return check_launch("reduce_fixup");
+  }
+  return 0;
+}
+
+extern "C" int tgr_bwd_reduce(const tgr_table_t* tables, int n_tables, int H, const tgr_call_t* calls, int n_calls,
+                              const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n, int mode,
+                              const int32_t* seg_of_entry, float* grads_out, const tgr_adam_t* adam, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  TGR_REQUIRE(calls && n_calls > 0 && n_calls <= TGR_MAX_CALLS, "bad calls");
+  TGR_REQUIRE(H > 0 && H % 4 == 0 && H <= 512, "H=%d unsupported (multiple of 4, <= 512)", H);
+  TGR_REQUIRE(mode == 0 || mode == 1, "bad mode");
+  TGR_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
+  if (n == 0) return 0;
+  TGR_REQUIRE(keys_sorted && srcs_sorted && workspace, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  RedParams p{};
+  RowParams rp{};
+  if (int rc = fill_row_params(rp, tables, n_tables, H)) return rc;
+  for (int t = 0; t < n_tables; ++t) { p.w[t] = rp.w[t]; p.m[t] = rp.m[t]; p.v[t] = rp.v[t]; }
+  for (int t = 0; t <= n_tables; ++t) p.key_base[t] = rp.key_base[t];
+  p.n_tables = n_tables;
+  const int dtype = calls[0].cat_dtype;
+  for (int c = 0; c < n_calls; ++c) {
+    const tgr_call_t& cl = calls[c];
+    TGR_REQUIRE(cl.cat_dtype == dtype, "all calls must share the concat-gradient dtype");
+    const size_t esz = dtype == TGR_DTYPE_BF16 ? 2 : 4;
+    for (int i = 0; i < cl.n_slots; ++i) {
+      const tgr_slot_t& s = cl.slots[i];
+      if (s.kind == TGR_KIND_MM) continue;
+      const char* base = (const char*)(s.side == TGR_SIDE_ITEM ? cl.item_cat : cl.user_cat);
+      const int64_t ld = s.side == TGR_SIDE_ITEM ? cl.item_ld : cl.user_ld;
+      TGR_REQUIRE(base != nullptr, "call %d slot %d: concat gradient is NULL", c, i);
+      TGR_REQUIRE(s.col % 4 == 0 && ld % 4 == 0, "call %d slot %d: col/ld not 128-bit tileable", c, i);
+      p.chunk_base[c][i] = base + (size_t)s.col * esz;
+      p.ld_bytes[c][i] = ld * (int64_t)esz;
+    }
+  }
+  if (mode == 1) {
+    TGR_REQUIRE(adam != nullptr, "adam is NULL");
+    for (int t = 0; t < n_tables; ++t) TGR_REQUIRE(p.w[t] && p.m[t] && p.v[t], "table %d: weight/exp_avg/exp_avg_sq NULL", t);
+    p.adam = *adam;
+  }
+  p.keys = keys_sorted;
+  p.srcs = srcs_sorted;
+  p.n = n;
+  p.H4 = H / 4;
+  p.mode = mode;
+  const int tile = red_tile(p.H4);
+  const int n_cta = (int)((n + tile - 1) / tile);
+  TGR_REQUIRE(workspace_bytes >= tgr_reduce_workspace_bytes(n, H), "workspace too small");
+  const size_t part = align_up((size_t)(n_cta + 1) * H * sizeof(float));
+  p.cta_head = (float*)workspace;
+  p.cta_tail = (float*)((char*)workspace + part);
+  if (mode == 0) {
+    TGR_REQUIRE(seg_of_entry && grads_out, "mode 0 needs seg_of_entry / grads_out");
+    p.seg_of_entry = seg_of_entry;
+    p.grads_out = grads_out;
+  }
+  const bool bf16 = dtype == TGR_DTYPE_BF16;
+  const int H4 = p.H4;
+  if (H4 <= 8) return launch_reduce<8, 1>(p, bf16, n_cta, st);
+  if (H4 <= 16) return launch_reduce<16, 1>(p, bf16, n_cta, st);
+  if (H4 <= 32) return launch_reduce<32, 1>(p, bf16, n_cta, st);
+  if (H4 <= 64) return launch_reduce<32, 2>(p, bf16, n_cta, st);
+  return launch_reduce<32, 4>(p, bf16, n_cta, st);
+}
+
+extern "C" int tgr_adam_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
+                             const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam, void* stream) {
+  TGR_REQUIRE(uniq && grads && n_unique_dev && adam, "null argument");
+  RowParams rp{};
+  if (int rc = fill_row_params(rp, tables, n_tables, H)) return rc;
+  for (int t = 0; t < n_tables; ++t) TGR_REQUIRE(rp.w[t] && rp.m[t] && rp.v[t], "table %d: weight/exp_avg/exp_avg_sq NULL", t);
+  rp.adam = *adam;
+  if (max_unique <= 0) return 0;
+  int64_t blocks = (max_unique * rp.H4 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  rows_kernel<0><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rp, uniq, grads, n_unique_dev);
+  return check_launch("adam_rows");
+}
+
+extern "C" int tgr_scatter_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
+                                const int32_t* n_unique_dev, int64_t max_unique, void* stream) {
+  TGR_REQUIRE(uniq && grads && n_unique_dev, "null argument");
+  RowParams rp{};
+  if (int rc = fill_row_params(rp, tables, n_tables, H)) return rc;
+  if (max_unique <= 0) return 0;
+  int64_t blocks = (max_unique * rp.H4 + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  rows_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rp, uniq, grads, n_unique_dev);
+  return check_launch("scatter_rows");
+}
+
+extern "C" int tgr_gather_rows(const float* table, int H, const uint32_t* rows, const int32_t* n_dev, int64_t max_n,
+                               float* out, void* stream) {
+  TGR_REQUIRE(table && rows && n_dev && out, "null argument");
+  TGR_REQUIRE(H > 0 && H % 4 == 0, "bad H");
+  if (max_n <= 0) return 0;
+  int64_t blocks = (max_n * (H / 4) + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, H / 4, rows, n_dev, out);
+  return check_launch("gather_rows");
+}

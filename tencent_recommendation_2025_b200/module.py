@@ -1,0 +1,181 @@
+"""Drop-in for ``BaselineModel.feat2emb`` (+ backward + embedding-row update).
+
+Two ways in, same engine underneath:
+
+  * ``BaselineEmbedding`` — a standalone nn.Module with the reference's constructor signature
+    ``(user_num, item_num, feat_statistics, feat_types, args)`` and the hot path's attribute names
+    (``item_emb``, ``user_emb``, ``sparse_emb[fid]``, ``emb_transform[fid]``, ``itemdnn``, ``userdnn``;
+    model/BaseLine/model.py:104-167), so ``named_parameters()`` / ``state_dict()`` keys, the xavier /
+    row-0 init of main.py:95-111 and checkpoints interchange with the reference for those keys.
+  * ``install(model)`` — graft onto an existing reference ``BaselineModel``: its ``feat2emb`` is
+    replaced by the CUDA path operating on the model's OWN parameters; trunk, loss and training loop
+    stay untouched (model.py:324,376-377,425 keep calling ``self.feat2emb`` with the same arguments).
+
+``feat2emb(seq, feature_array, mask=None, include_user=False)`` keeps the reference signature and
+returns ``[B, L, H]`` on the module's device; ``feat2emb_packed`` takes a pre-tensorized
+``PackedBatch`` (the fast entry the benchmark times). itemdnn / userdnn + ReLU + add stay torch
+calls and consume the fused concat buffers.
+"""
+from __future__ import annotations
+
+import types
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .engine import EmbeddingEngine, GatherConcatFn
+from .layout import FeatureLayout
+from .packed import PackedBatch, pack_from_dicts, to_device
+
+
+def _concat_dtype() -> torch.dtype:
+    # Under bf16 autocast the reference's fp32 concat is rounded to bf16 by the autocast Linear that
+    # consumes it; writing bf16 directly feeds itemdnn bit-identical inputs.
+    if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        return torch.bfloat16
+    return torch.float32
+
+
+class _FeatEmbMixin:
+    """feat2emb family shared by the standalone module and by ``install``-ed reference models."""
+
+    _tgr_engine: EmbeddingEngine
+    _tgr_layout: FeatureLayout
+
+    # -- reference-compatible tensorizer (model.py:186-224), kept for callers that use it directly
+    def feat2tensor(self, seq_feature, k):
+        lay = self._tgr_layout
+        is_array = k in lay.item_array or k in lay.user_array
+        B = len(seq_feature)
+        if is_array:
+            max_a = max(max(len(tok[k]) for tok in row) for row in seq_feature)
+            max_l = max(len(row) for row in seq_feature)
+            out = np.zeros((B, max_l, max_a), dtype=np.int64)
+            for i, row in enumerate(seq_feature):
+                for j, tok in enumerate(row):
+                    v = tok[k][:max_a]
+                    out[i, j, :len(v)] = v
+        else:
+            max_l = max(len(row) for row in seq_feature)
+            out = np.zeros((B, max_l), dtype=np.int64)
+            for i, row in enumerate(seq_feature):
+                out[i] = [tok[k] for tok in row]
+        return torch.from_numpy(out).to(self.dev)
+
+    def pack(self, seq, feature_array, mask=None, include_user=False, mm_dtype=torch.float32) -> PackedBatch:
+        """Dict-form call -> device PackedBatch: one pass over the dicts, one pinned H2D copy."""
+        pc = pack_from_dicts(self._tgr_layout, seq, feature_array, mask, include_user)
+        return to_device(self._tgr_layout, pc, self._tgr_engine._device(), mm_dtype=mm_dtype)
+
+    @torch.compiler.disable
+    def feat2emb(self, seq, feature_array, mask=None, include_user=False):
+        """Same signature and result as model/BaseLine/model.py:226-310."""
+        return self.feat2emb_packed(self.pack(seq, feature_array, mask, include_user))
+
+    @torch.compiler.disable
+    def feat2emb_packed(self, pb: PackedBatch):
+        eng = self._tgr_engine
+        lay = self._tgr_layout
+        params = [t for t in eng.tables]
+        for k in lay.item_emb_feat:
+            params += [self.emb_transform[k].weight, self.emb_transform[k].bias]
+        item_cat, user_cat = GatherConcatFn.apply(eng, pb, _concat_dtype(), *params)
+        B, L = pb.B, pb.L
+        out = torch.relu(self.itemdnn(item_cat.view(B, L, -1)))            # model.py:303
+        if pb.include_user:
+            out = out + torch.relu(self.userdnn(user_cat.view(B, L, -1)))  # model.py:306-307
+        return out
+
+    def fused_step(self, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
+        return self._tgr_engine.fused_step(lr, betas, eps, weight_decay, grad_scale)
+
+    def check_padding_rows(self):
+        """Row 0 of every table must be all-zero (the reference keeps it so: main.py:106-111, padding_idx
+        gradient masking, AdamW fixed point). Array pooling drops padding ids on that basis."""
+        for p, t in zip(self._tgr_engine.tables, self._tgr_layout.tables):
+            if bool(torch.any(p.data[0] != 0)):
+                raise ValueError(f"{t.name}: padding row 0 is not zero")
+
+
+def _table_params(mod, layout: FeatureLayout) -> List[torch.nn.Parameter]:
+    out = []
+    for t in layout.tables:
+        if t.name in ("item_emb", "user_emb"):
+            out.append(getattr(mod, t.name).weight)
+        else:
+            out.append(mod.sparse_emb[t.name.split(".", 1)[1]].weight)
+    return out
+
+
+class BaselineEmbedding(_FeatEmbMixin, torch.nn.Module):
+    """The hot-path slice of the reference ``BaselineModel`` with the CUDA ``feat2emb``."""
+
+    def __init__(self, user_num, item_num, feat_statistics, feat_types, args, mode: str = "parity"):
+        super().__init__()
+        self.user_num, self.item_num = user_num, item_num
+        self.dev = args.device
+        H = args.hidden_units
+        lay = FeatureLayout(user_num, item_num, feat_statistics, feat_types, H)
+        self._tgr_layout = lay
+        # same declarations, same insertion order as model.py:115-116,158-167
+        self.item_emb = torch.nn.Embedding(item_num + 1, H, padding_idx=0)
+        self.user_emb = torch.nn.Embedding(user_num + 1, H, padding_idx=0)
+        self.sparse_emb = torch.nn.ModuleDict()
+        self.emb_transform = torch.nn.ModuleDict()
+        self.userdnn = torch.nn.Linear(lay.user_dim, H)
+        self.itemdnn = torch.nn.Linear(lay.item_dim, H)
+        for group in (lay.user_sparse, lay.item_sparse, lay.item_array, lay.user_array):
+            for k, vocab in group.items():
+                self.sparse_emb[k] = torch.nn.Embedding(vocab + 1, H, padding_idx=0)
+        for k, d in lay.item_emb_feat.items():
+            self.emb_transform[k] = torch.nn.Linear(d, H)
+        self._tgr_engine = EmbeddingEngine(lay, _table_params(self, lay), dict(self.emb_transform.items()), mode)
+
+    @property
+    def layout(self) -> FeatureLayout:
+        return self._tgr_layout
+
+    @property
+    def engine(self) -> EmbeddingEngine:
+        return self._tgr_engine
+
+    def dense_parameters(self):
+        """Parameters the outer (dense) optimizer should own in fused mode: everything but the tables."""
+        tabs = {id(p) for p in self._tgr_engine.tables}
+        return [p for p in self.parameters() if id(p) not in tabs]
+
+
+def install(model, optimizer: Optional[torch.optim.Optimizer] = None, mode: str = "parity"):
+    """Replace ``model.feat2emb`` of a reference-style ``BaselineModel`` with the CUDA path, in place.
+
+    The model keeps its own nn.Embedding / nn.Linear parameters (so init, checkpoints and, in parity
+    mode, the optimizer are untouched). In fused mode pass the optimizer: after every
+    ``optimizer.step()`` a post-hook applies the queued row updates with that optimizer's lr / betas /
+    eps / weight_decay; the tables receive no ``.grad`` so the dense optimizer skips them.
+    """
+    H = model.item_emb.embedding_dim
+    feat_types = {
+        "user_sparse": list(model.USER_SPARSE_FEAT), "item_sparse": list(model.ITEM_SPARSE_FEAT),
+        "user_array": list(model.USER_ARRAY_FEAT), "item_array": list(model.ITEM_ARRAY_FEAT),
+        "item_emb": list(model.ITEM_EMB_FEAT), "user_continual": list(model.USER_CONTINUAL_FEAT),
+        "item_continual": list(model.ITEM_CONTINUAL_FEAT),
+    }
+    stats: Dict[str, int] = {}
+    for d in (model.USER_SPARSE_FEAT, model.ITEM_SPARSE_FEAT, model.USER_ARRAY_FEAT, model.ITEM_ARRAY_FEAT):
+        stats.update(d)
+    lay = FeatureLayout(model.user_num, model.item_num, stats, feat_types, H)
+    model._tgr_layout = lay
+    model._tgr_engine = EmbeddingEngine(lay, _table_params(model, lay), dict(model.emb_transform.items()), mode)
+    for name in ("feat2tensor", "pack", "feat2emb", "feat2emb_packed", "fused_step", "check_padding_rows"):
+        setattr(model, name, types.MethodType(getattr(_FeatEmbMixin, name), model))
+    if mode == "fused":
+        if optimizer is None:
+            raise ValueError("fused mode needs the optimizer whose step() should trigger the row update")
+
+        def _post_step(opt, args, kwargs):
+            g = opt.param_groups[0]
+            model._tgr_engine.fused_step(g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"])
+
+        model._tgr_hook = optimizer.register_step_post_hook(_post_step)
+    return model

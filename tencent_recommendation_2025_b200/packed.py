@@ -1,0 +1,176 @@
+"""Packed batches: the kernel-facing replacement of the reference's per-feature ``feat2tensor`` tensors.
+
+The reference walks the B x L feature dicts once PER FEATURE (22 / 14 times per call) and issues one
+synchronous host->device copy per feature (model/BaseLine/model.py:186-224,272). Here one
+pass over the dicts fills ONE token-major int32 id matrix (+ CSR arrays, + dense mm inputs), staged in a
+single pinned buffer and uploaded with one async copy per dtype.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from itertools import chain
+from operator import itemgetter
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .layout import FeatureLayout
+from .synth import PackedCall
+
+
+def pack_from_dicts(layout: FeatureLayout, seq, feature_array, mask=None, include_user: bool = False) -> PackedCall:
+    """list[B] of indexable[L] of dict  ->  PackedCall (host).  Semantics of model.py:237-247 + feat2tensor:
+
+    * item/user id columns: ``(mask == 1) * seq`` / ``(mask == 2) * seq`` when include_user, else ``seq``;
+    * sparse features: ``item[k]`` for every token (KeyError if a dict lacks k, as the reference);
+      ragged sequences raise ValueError (model.py:222);
+    * array features: the token's list with padding ids (0) dropped — summing row 0 is a no-op because
+      row 0 is the all-zero padding row (nn.Embedding(padding_idx=0), main.py:106-111);
+    * mm features: ``item[k]`` if present else zeros (model.py:288-293).
+    """
+    call = layout.calls[include_user]
+    seq_np = seq.detach().cpu().numpy() if isinstance(seq, torch.Tensor) else np.asarray(seq)
+    if seq_np.ndim != 2:
+        raise ValueError("seq must be [B, L]")
+    B, L = seq_np.shape
+    if len(feature_array) != B:
+        raise ValueError(f"feature_array has {len(feature_array)} sequences, seq has {B}")
+    for row in feature_array:
+        if len(row) != L:
+            # the reference's numpy row assignment fails on ragged input (model.py:217-222)
+            raise ValueError("setting an array element with a sequence: ragged feature sequences")
+    T = B * L
+    flat = seq_np.reshape(-1).astype(np.int64)
+    ids = np.zeros((T, call.n_single), np.int32)
+    names = layout.single_slot_names(include_user)
+    if include_user:
+        if mask is None:
+            raise ValueError("include_user=True needs the token-type mask")
+        m = (mask.detach().cpu().numpy() if isinstance(mask, torch.Tensor) else np.asarray(mask)).reshape(-1)
+        ids[:, names.index("item_id")] = np.where(m == 1, flat, 0)
+        ids[:, names.index("user_id")] = np.where(m == 2, flat, 0)
+    else:
+        ids[:, names.index("item_id")] = flat
+    feat_cols = [(c, k) for c, k in enumerate(names) if k not in ("item_id", "user_id")]
+    tokens = list(chain.from_iterable(feature_array))
+    if feat_cols:
+        keys = [k for _, k in feat_cols]
+        if len(keys) == 1:
+            vals = np.fromiter((tok[keys[0]] for tok in tokens), dtype=np.int64, count=T).reshape(T, 1)
+        else:
+            vals = np.array(list(map(itemgetter(*keys), tokens)), dtype=np.int64).reshape(T, len(keys))
+        ids[:, [c for c, _ in feat_cols]] = vals
+    arr_names = layout.array_slot_names(include_user)
+    arr_off = np.zeros((len(arr_names), T + 1), np.int32)
+    arr_vals: List[np.ndarray] = []
+    base = 0
+    for j, k in enumerate(arr_names):
+        lists = [tok[k] for tok in tokens]
+        lens = np.fromiter((len(v) for v in lists), dtype=np.int64, count=T)
+        flatv = np.fromiter(chain.from_iterable(lists), dtype=np.int64, count=int(lens.sum()))
+        keep = flatv != 0
+        owner = np.repeat(np.arange(T), lens)[keep]
+        cnt = np.bincount(owner, minlength=T)
+        arr_off[j, 0] = base
+        arr_off[j, 1:] = base + np.cumsum(cnt)
+        arr_vals.append(flatv[keep].astype(np.int32))
+        base = int(arr_off[j, -1])
+    arr_val = np.concatenate(arr_vals) if arr_vals else np.zeros((0,), np.int32)
+    mm_x = []
+    for k, d in layout.item_emb_feat.items():
+        x = np.zeros((T, d), np.float32)
+        for t, tok in enumerate(tokens):
+            v = tok.get(k) if isinstance(tok, dict) else (tok[k] if k in tok else None)
+            if v is not None:
+                x[t] = v
+        mm_x.append(x)
+    return PackedCall(B, L, include_user, ids, arr_off, arr_val, mm_x,
+                      seq=seq_np.astype(np.int32), mask=None if mask is None else np.asarray(m).reshape(B, L).astype(np.int32))
+
+
+@dataclass
+class PackedBatch:
+    """Device-resident packed call. ``n_valid`` (non-padding ids) is known on the host at pack time and sizes
+    the backward's sort without a device->host sync."""
+
+    B: int
+    L: int
+    include_user: bool
+    ids: torch.Tensor                 # int32 [T, n_single]
+    arr_off: torch.Tensor             # int32 [n_array, T+1]
+    arr_val: torch.Tensor             # int32 [nnz]
+    arr_tok: torch.Tensor             # int32 [nnz] token of each array value
+    arr_begin: List[int]
+    arr_nnz: List[int]
+    mm_x: List[torch.Tensor]          # [T, mm_dim] float32 / bfloat16
+    n_valid: int
+    h2d_bytes: int = 0
+
+    @property
+    def T(self) -> int:
+        return self.B * self.L
+
+
+def _arr_tok(pc: PackedCall) -> np.ndarray:
+    toks = []
+    for j in range(pc.arr_off.shape[0]):
+        lens = np.diff(pc.arr_off[j].astype(np.int64))
+        toks.append(np.repeat(np.arange(pc.T, dtype=np.int32), lens))
+    return np.concatenate(toks).astype(np.int32) if toks else np.zeros((0,), np.int32)
+
+
+def count_valid(layout: FeatureLayout, pc: PackedCall) -> int:
+    """Non-padding, in-range ids of a call == entries tgr_bwd_build_keys will emit."""
+    call = layout.calls[pc.include_user]
+    n = 0
+    for s in call.slots:
+        rows = layout.tables[s.table].rows if s.table >= 0 else 0
+        if s.kind == 0:
+            col = pc.ids[:, s.src]
+            n += int(np.count_nonzero((col > 0) & (col < rows)))
+        elif s.kind == 1:
+            lo, hi = int(pc.arr_off[s.src, 0]), int(pc.arr_off[s.src, -1])
+            v = pc.arr_val[lo:hi]
+            n += int(np.count_nonzero((v > 0) & (v < rows)))
+    return n
+
+
+def to_device(layout: FeatureLayout, pc: PackedCall, device, mm_dtype: torch.dtype = torch.float32,
+              pin: bool = True, non_blocking: bool = True) -> PackedBatch:
+    """One pinned staging buffer + one async H2D copy for all integer data (and one per mm feature)."""
+    T = pc.T
+    arr_tok = _arr_tok(pc)
+    n_arr = pc.arr_off.shape[0]
+    parts = [pc.ids.reshape(-1), pc.arr_off.reshape(-1), pc.arr_val, arr_tok]
+    sizes = [p.size for p in parts]
+    # 16-byte align every part (ids needs it for the 128-bit id-block loads)
+    offs, tot = [], 0
+    for s in sizes:
+        offs.append(tot)
+        tot += (s + 3) // 4 * 4
+    stage = torch.empty(max(tot, 4), dtype=torch.int32, pin_memory=pin and torch.cuda.is_available())
+    st_np = stage.numpy()
+    for p, o, s in zip(parts, offs, sizes):
+        st_np[o:o + s] = p
+    dev = stage.to(device, non_blocking=non_blocking)
+    ids = dev[offs[0]:offs[0] + sizes[0]].view(T, pc.ids.shape[1])
+    arr_off = dev[offs[1]:offs[1] + sizes[1]].view(n_arr, T + 1)
+    arr_val = dev[offs[2]:offs[2] + sizes[2]]
+    arr_tok_d = dev[offs[3]:offs[3] + sizes[3]]
+    mm = []
+    h2d = tot * 4
+    for x in pc.mm_x:
+        xt = torch.from_numpy(np.ascontiguousarray(x))
+        if mm_dtype != torch.float32:
+            xt = xt.to(mm_dtype)
+        if pin and torch.cuda.is_available():
+            xt = xt.pin_memory()
+        mm.append(xt.to(device, non_blocking=non_blocking))
+        h2d += xt.numel() * xt.element_size()
+    begins = [int(pc.arr_off[j, 0]) for j in range(n_arr)]
+    nnz = [int(pc.arr_off[j, -1] - pc.arr_off[j, 0]) for j in range(n_arr)]
+    pb = PackedBatch(pc.B, pc.L, pc.include_user, ids, arr_off, arr_val, arr_tok_d, begins, nnz, mm,
+                     count_valid(layout, pc), h2d)
+    pb._stage = stage  # keep the pinned buffer alive until the copy has certainly run
+    return pb

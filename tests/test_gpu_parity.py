@@ -1,0 +1,417 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the CPU oracle and the reference-made golden
+fixtures. Bars (BASELINE.json north_star): bit-exact for ids / keys / dedup / routing and for pure row
+copies; 1e-5 relative (fp32) for pooled embeddings, projections, gradients and updated rows; 1e-2 (bf16).
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Golden, TRAIN_CASES
+from oracle import feat2emb_numpy as onp
+from tencent_recommendation_2025_b200.synth import SynthConfig, SynthWorld, packed_to_dicts
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _close(a, b, rtol=RTOL, what=""):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if b.size == 0:
+        return
+    scale = max(np.abs(b).max(), 1e-30)
+    err = np.abs(a - b).max()
+    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rtol {rtol})"
+
+
+def make_module(g: Golden, mode="parity"):
+    from tencent_recommendation_2025_b200.module import BaselineEmbedding
+    args = types.SimpleNamespace(device="cuda", hidden_units=g.H)
+    m = BaselineEmbedding(g.user_num, g.item_num, g.feat_statistics, g.feat_types, args, mode).to("cuda")
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in g.params0().items()})
+    return m
+
+
+def dev_batch(m, pc, mm_dtype=torch.float32):
+    from tencent_recommendation_2025_b200.packed import to_device
+    return to_device(m.layout, pc, "cuda", mm_dtype=mm_dtype)
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_forward_concat_and_output(name):
+    g = Golden(name)
+    m = make_module(g)
+    lay = g.layout
+    params = g.params0()
+    H = g.H
+    for c, pc in enumerate(g.calls(0)):
+        pb = dev_batch(m, pc)
+        item_cat, user_cat = m.engine.forward(pb)
+        _, cache = onp.feat2emb_forward(params, lay, pc.seq, onp.tensors_from_packed(lay, pc), pc.mask, pc.include_user)
+        ref = {0: cache["item_cat"].reshape(pc.T, -1), 1: cache.get("user_cat", np.zeros((pc.T, 0))).reshape(pc.T, -1)}
+        got = {0: item_cat.cpu().numpy(), 1: user_cat.cpu().numpy() if user_cat is not None else None}
+        for s in lay.calls[pc.include_user].slots:
+            a = got[s.side][:, s.col:s.col + H]
+            b = ref[s.side][:, s.col:s.col + H]
+            if s.kind == 2:
+                _close(a, b, what=f"{name} c{c} mm slot {s.name}")
+            else:
+                # row copies and left-to-right pooled sums are bit-exact
+                assert np.array_equal(a, b), f"{name} c{c} slot {s.name} not bit-exact"
+        out = m.feat2emb_packed(pb)
+        assert out.shape == (pc.B, pc.L, H)
+        _close(out, g.outs(0)[c], what=f"{name} out c{c}")
+
+
+@pytest.mark.parametrize("name", ["baseline_h32", "o1_h64_mm2"])
+def test_dict_signature_matches_reference(name):
+    """feat2emb(seq, feature_array, mask, include_user) with the reference's list-of-dict inputs."""
+    g = Golden(name)
+    m = make_module(g)
+    for c, pc in enumerate(g.calls(0)):
+        dicts = packed_to_dicts(g.layout, pc)
+        seq = torch.from_numpy(pc.seq)
+        mask = torch.from_numpy(pc.mask) if pc.include_user else None
+        out = m.feat2emb(seq, dicts, mask=mask, include_user=pc.include_user)
+        _close(out, g.outs(0)[c], what=f"{name} dict call {c}")
+
+
+def test_item_sweep_call_shape():
+    """save_item_emb's int64 [1, n] call with [object-array of dicts] (model.py:418-425)."""
+    g = Golden("item_sweep")
+    m = make_module(g)
+    pc = g.sweep_call()
+    dicts = packed_to_dicts(g.layout, pc)
+    with torch.no_grad():
+        out = m.feat2emb(torch.from_numpy(g.z["seq"]).cuda(), dicts, include_user=False).squeeze(0)
+    _close(out, g.z["out"][0], what="item sweep")
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_backward_parity_mode_dense_grads(name):
+    g = Golden(name)
+    m = make_module(g, "parity")
+    outs = [m.feat2emb_packed(dev_batch(m, pc)) for pc in g.calls(0)]
+    loss = sum((o * torch.from_numpy(r).cuda()).sum() for o, r in zip(outs, g.upstream(0)))
+    loss.backward()
+    ref = g.group("s0/grad/")
+    named = dict(m.named_parameters())
+    for k, v in ref.items():
+        p = named[k]
+        if v.size == 0:
+            assert p.grad is None or not bool(p.grad.any())
+            continue
+        assert p.grad is not None, k
+        _close(p.grad, v, what=f"{name} grad {k}")
+        if k.split(".")[0] in ("item_emb", "user_emb", "sparse_emb"):
+            assert not bool(p.grad[0].any()), "padding row must get exactly zero grad"
+
+
+@pytest.mark.parametrize("name", ["baseline_h32", "o1_h64"])
+def test_fused_row_update_matches_reference_adamw(name):
+    """Step 1 from zero state: the fused sparse AdamW == the reference's dense AdamW on every touched row
+    (SURVEY.md §7 H1); untouched rows are left alone (dense AdamW would scale them by 1 - lr*wd)."""
+    g = Golden(name)
+    m = make_module(g, "fused")
+    dense_opt = torch.optim.AdamW(m.dense_parameters(), lr=g.lr, betas=(0.9, 0.98), weight_decay=g.wd)
+    outs = [m.feat2emb_packed(dev_batch(m, pc)) for pc in g.calls(0)]
+    loss = sum((o * torch.from_numpy(r).cuda()).sum() for o, r in zip(outs, g.upstream(0)))
+    loss.backward()
+    for p in m.engine.tables:
+        assert p.grad is None
+    dense_opt.step()
+    n = m.fused_step(lr=g.lr, betas=(0.9, 0.98), eps=1e-8, weight_decay=g.wd)
+    assert n == sum(pb_n for pb_n in [dev_batch(m, pc).n_valid for pc in g.calls(0)])
+    ref_g, ref_p, p0 = g.group("s0/grad/"), g.group("s0/param/"), g.params0()
+    named = dict(m.named_parameters())
+    last = g.n_steps - 1
+    for k, p in named.items():
+        got = p.detach().cpu().numpy()
+        if k.split(".")[0] in ("item_emb", "user_emb", "sparse_emb"):
+            touched = np.nonzero(np.any(ref_g[k] != 0, axis=1))[0]
+            untouched = np.setdiff1d(np.arange(got.shape[0]), touched)
+            _close(got[touched], ref_p[k][touched], rtol=2e-6, what=f"{name} updated rows {k}")
+            assert np.array_equal(got[untouched], p0[k][untouched]), f"{k}: untouched rows must not move"
+            assert not got[0].any()
+            if last == 0:
+                i = [t.name + ".weight" for t in g.layout.tables].index(k)
+                _close(m.engine.exp_avg[i][touched], g.z[f"s0/exp_avg/{k}"][touched], rtol=2e-6, what=f"exp_avg {k}")
+                _close(m.engine.exp_avg_sq[i][touched], g.z[f"s0/exp_avg_sq/{k}"][touched], rtol=2e-6, what=f"exp_avg_sq {k}")
+        else:
+            # GPU AdamW step 1 moves every element by ~lr*sign(g): elements with |g| ~ eps differ between
+            # CPU and GPU library kernels, so the bar here is the gradient's, not a bit-level one
+            _close(got, ref_p[k], rtol=2e-4, what=f"{name} dense param {k}")
+
+
+def test_multi_step_parity_mode_tracks_reference():
+    """Parity mode + the reference's own dense AdamW over two steps (different batches)."""
+    g = Golden("baseline_h32")
+    m = make_module(g, "parity")
+    opt = torch.optim.AdamW(m.parameters(), lr=g.lr, betas=(0.9, 0.98), weight_decay=g.wd)
+    named = dict(m.named_parameters())
+    for step in range(g.n_steps):
+        opt.zero_grad(set_to_none=True)
+        outs = [m.feat2emb_packed(dev_batch(m, pc)) for pc in g.calls(step)]
+        for c, o in enumerate(outs):
+            _close(o, g.outs(step)[c], rtol=5e-5, what=f"step {step} out c{c}")
+        loss = sum((o * torch.from_numpy(r).cuda()).sum() for o, r in zip(outs, g.upstream(step)))
+        loss.backward()
+        opt.step()
+        ref_p = g.group(f"s{step}/param/")
+        for k, p in named.items():
+            _close(p, ref_p[k], rtol=3e-4, what=f"step {step} param {k}")
+
+
+def _run_keys(m, calls_np):
+    """build_keys + sort + dedup through the C ABI -> numpy (keys, srcs, uniq, seg_off)."""
+    eng = m.engine
+    pbs = [dev_batch(m, pc) for pc in calls_np]
+    lay = m.layout
+    calls = []
+    for pb in pbs:
+        cl = lay.calls[pb.include_user]
+        di = torch.zeros((pb.T, cl.item_dim), device="cuda")
+        du = torch.zeros((pb.T, cl.user_dim), device="cuda") if pb.include_user else None
+        calls.append((pb, di, du))
+    structs, keys, srcs, n, calls = eng._sorted_pairs(calls)
+    torch.cuda.synchronize()
+    buf = eng._ws["pairs"]
+    q = max(n, 1) * 4
+    raw = buf[: 4 * q].cpu().numpy().view(np.uint32)
+    keys_in, srcs_in, keys_out, srcs_out = (raw[i * max(n, 1): i * max(n, 1) + n] for i in range(4))
+    return keys_in.copy(), srcs_in.copy(), keys_out.copy(), srcs_out.copy(), n, calls
+
+
+@pytest.mark.parametrize("name", ["baseline_h32", "o1_h64", "baseline_l102_nomm"])
+def test_keys_sort_dedup_bit_exact(name):
+    g = Golden(name)
+    m = make_module(g)
+    calls_np = g.calls(0)
+    k_in, s_in, k_out, s_out, n, calls = _run_keys(m, calls_np)
+    rk, rs = onp.build_keys(g.layout, calls_np)
+    # the CUDA path enumerates (call, token, slot); the oracle (call, slot, token): same multiset, and
+    # after a STABLE sort by key the order inside a key is identical (one slot per table per call)
+    assert n == rk.size
+    order, uniq, seg, counts = onp.sort_dedup(rk)
+    assert np.array_equal(np.sort(k_in), np.sort(rk))
+    assert np.array_equal(k_out, rk[order])
+    assert np.array_equal(s_out, rs[order])
+    got_uniq, seg_off, n_unique, rows, n2 = m.engine.dedup_reduce(calls)
+    U = int(n_unique.item())
+    assert U == uniq.size
+    assert np.array_equal(got_uniq[:U].cpu().numpy().view(np.uint32), uniq)
+    assert np.array_equal(seg_off[:U + 1].cpu().numpy(), seg)
+    tu, tc = torch.unique(torch.from_numpy(rk.astype(np.int64)), sorted=True, return_counts=True)
+    assert np.array_equal(np.diff(seg_off[:U + 1].cpu().numpy()), tc.numpy())
+
+
+def test_segment_reduce_vs_fp64_truth_and_determinism():
+    cfg = SynthConfig(B=64, L=101, H=64, item_num=3000, user_num=500, alpha=1.2, mm_ids=("81",))
+    w = SynthWorld(cfg, 5)
+    st = w.make_step(0)
+    from tencent_recommendation_2025_b200.module import BaselineEmbedding
+    args = types.SimpleNamespace(device="cuda", hidden_units=cfg.H)
+    m = BaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), args, "parity").cuda()
+    lay = m.layout
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    calls, d_cats = [], []
+    for pc in st.calls:
+        pb = dev_batch(m, pc)
+        cl = lay.calls[pc.include_user]
+        di = torch.randn((pc.T, cl.item_dim), generator=gen)
+        du = torch.randn((pc.T, cl.user_dim), generator=gen) if pc.include_user else None
+        d_cats.append((di.numpy(), None if du is None else du.numpy()))
+        calls.append((pb, di.cuda(), None if du is None else du.cuda()))
+    uniq, seg_off, n_unique, rows, n = m.engine.dedup_reduce(list(calls))
+    U = int(n_unique.item())
+    ref_uniq, ref_rows = onp.segment_reduce_fp64(lay, st.calls, d_cats)
+    assert np.array_equal(uniq[:U].cpu().numpy().view(np.uint32), ref_uniq)
+    got = rows[:U].cpu().numpy().astype(np.float64)
+    # judged against fp64 truth, relative to each row's term magnitude (long Zipf segments: SURVEY.md F16/F17)
+    counts = np.diff(seg_off[:U + 1].cpu().numpy())
+    assert counts.max() > 500, "config should contain heavy segments"
+    scale = np.maximum(np.abs(ref_rows).max(axis=1, keepdims=True), np.sqrt(counts)[:, None])
+    assert (np.abs(got - ref_rows) / scale).max() < 1e-5
+    uniq2, _, n_unique2, rows2, _ = m.engine.dedup_reduce(list(calls))
+    assert torch.equal(rows[:U], rows2[:U]) and torch.equal(uniq[:U], uniq2[:U])
+
+
+def test_fused_step_deterministic_and_equals_unfused_rows():
+    """fused reduce+AdamW == dedup_reduce + adam_rows (two code paths, same arithmetic), bitwise; run twice."""
+    from tencent_recommendation_2025_b200._lib import make_adam, check
+    import ctypes as C
+    g = Golden("baseline_h32")
+    res = []
+    for variant in ("fused", "fused", "rows"):
+        m = make_module(g, "fused")
+        eng = m.engine
+        calls = []
+        gen = torch.Generator().manual_seed(11)
+        for pc in g.calls(0):
+            pb = dev_batch(m, pc)
+            cl = g.layout.calls[pc.include_user]
+            di = torch.randn((pc.T, cl.item_dim), generator=gen).cuda()
+            du = torch.randn((pc.T, cl.user_dim), generator=gen).cuda() if pc.include_user else None
+            calls.append((pb, di, du))
+        if variant == "fused":
+            for c in calls:
+                eng.queue(*c)
+            eng.fused_step(lr=1e-3, weight_decay=1e-2)
+        else:
+            eng.ensure_state()
+            uniq, seg_off, n_unique, rows, n = eng.dedup_reduce(list(calls))
+            adam = make_adam(1e-3, 0.9, 0.98, 1e-8, 1e-2, 1)
+            tabs = eng._table_array(state=True)
+            check(eng.lib.tgr_adam_rows(tabs, len(eng.tables), g.H, uniq.data_ptr(), rows.data_ptr(), n_unique.data_ptr(), n,
+                                        C.byref(adam), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        res.append([p.detach().clone() for p in eng.tables] + [t.clone() for t in eng.exp_avg] + [t.clone() for t in eng.exp_avg_sq])
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b), "fused step must be bitwise reproducible"
+    for a, b in zip(res[0], res[2]):
+        assert torch.equal(a, b), "fused and unfused row updates must agree bitwise"
+
+
+def test_bf16_concat_is_rne_of_fp32():
+    g = Golden("o1_h64")
+    m = make_module(g)
+    pc = g.calls(0)[0]
+    pb = dev_batch(m, pc)
+    f32_item, f32_user = m.engine.forward(pb, torch.float32)
+    bf_item, bf_user = m.engine.forward(pb, torch.bfloat16)
+    H = g.H
+    for s in g.layout.calls[True].slots:
+        a = (bf_item if s.side == 0 else bf_user)[:, s.col:s.col + H]
+        b = (f32_item if s.side == 0 else f32_user)[:, s.col:s.col + H].to(torch.bfloat16)
+        assert torch.equal(a, b), f"slot {s.name}: bf16 concat must be the RNE rounding of the fp32 value"
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m.feat2emb_packed(pb)
+    _close(out.float(), g.outs(0)[0], rtol=1e-2, what="bf16 autocast output")
+
+
+def test_bf16_backward_within_1e2():
+    g = Golden("o1_h64")
+    m = make_module(g, "parity")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        outs = [m.feat2emb_packed(dev_batch(m, pc)) for pc in g.calls(0)]
+    loss = sum((o.float() * torch.from_numpy(r).cuda()).sum() for o, r in zip(outs, g.upstream(0)))
+    loss.backward()
+    ref = g.group("s0/grad/")
+    for k, p in m.named_parameters():
+        if ref[k].size:
+            _close(p.grad, ref[k], rtol=2e-2, what=f"bf16 grad {k}")
+
+
+@pytest.mark.parametrize("H", [32, 64, 128, 48, 256])
+def test_hidden_sizes_and_edge_ids(H):
+    """H in {32,64,128} (templated widths), 48 (partial lanes), 256 (two 128-bit columns per lane);
+    ids 0 and max id; empty arrays; an all-padding sequence."""
+    stats = {k: 9 for k in ["103", "104", "105", "109", "100", "117", "111", "118", "101", "102", "119", "120", "114",
+                            "112", "121", "115", "122", "116", "106", "107", "108", "110"]}
+    cfg = SynthConfig(B=3, L=7, H=H, item_num=50, user_num=9, mm_ids=("81",) if H <= 128 else (), min_len=2,
+                      feat_statistics=stats)
+    w = SynthWorld(cfg, 9)
+    st = w.make_step(0)
+    pc = st.calls[0]
+    pc.ids[0, :] = 0                     # fully padded token
+    pc.ids[1, 0] = cfg.item_num          # max item id
+    pc.ids[2, 1:15] = 9                  # max feature ids
+    from tencent_recommendation_2025_b200.module import BaselineEmbedding
+    args = types.SimpleNamespace(device="cuda", hidden_units=H)
+    torch.manual_seed(0)
+    m = BaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), args, "parity").cuda()
+    params = {k: v.detach().cpu().numpy() for k, v in m.named_parameters()}
+    upstream = [torch.from_numpy(r).cuda() for r in st.upstream]
+    outs, grads = [], []
+    for c, p in enumerate(st.calls):
+        out = m.feat2emb_packed(dev_batch(m, p))
+        ref, cache = onp.feat2emb_forward(params, m.layout, p.seq, onp.tensors_from_packed(m.layout, p), p.mask, p.include_user)
+        if c == 0:
+            # seq was edited above: rebuild the oracle's id view from the packed ids
+            cache = None
+        else:
+            _close(out, ref, what=f"H={H} out c{c}")
+            grads.append(onp.feat2emb_backward(params, m.layout, cache, st.upstream[c]))
+        outs.append(out)
+    loss = sum((o * r).sum() for o, r in zip(outs[1:], upstream[1:]))
+    loss.backward()
+    tot = onp.accumulate(list(reversed(grads)))
+    for k, p in m.named_parameters():
+        if k in tot and p.grad is not None:
+            _close(p.grad, tot[k], what=f"H={H} grad {k}")
+    # call 0 with the edited ids: slots are pure row copies -> check against torch indexing
+    item_cat, user_cat = m.engine.forward(dev_batch(m, pc))
+    ids = torch.from_numpy(pc.ids.astype(np.int64)).cuda()
+    for s in m.layout.calls[True].slots:
+        if s.kind == 0:
+            wt = m.engine.tables[s.table].data
+            got = (item_cat if s.side == 0 else user_cat)[:, s.col:s.col + H]
+            assert torch.equal(got, wt[ids[:, s.src]])
+
+
+def test_out_of_range_id_raises_index_error():
+    g = Golden("baseline_h32")
+    m = make_module(g)
+    m.engine.check_ids = True
+    pc = g.calls(0)[1]
+    pc.ids[3, 0] = g.item_num + 1
+    with pytest.raises(IndexError):
+        m.engine.forward(dev_batch(m, pc))
+
+
+def test_ragged_and_missing_inputs_raise():
+    g = Golden("baseline_h32")
+    m = make_module(g)
+    pc = g.calls(0)[1]
+    dicts = packed_to_dicts(g.layout, pc)
+    dicts[0] = dicts[0][:-1]
+    with pytest.raises(ValueError):
+        m.feat2emb(torch.from_numpy(pc.seq), dicts, include_user=False)
+    dicts = packed_to_dicts(g.layout, pc)
+    del dicts[1][2]["100"]
+    with pytest.raises(KeyError):
+        m.feat2emb(torch.from_numpy(pc.seq), dicts, include_user=False)
+
+
+def test_cpu_tables_fail_loudly():
+    from tencent_recommendation_2025_b200.module import BaselineEmbedding
+    from tencent_recommendation_2025_b200._lib import TgrError
+    g = Golden("baseline_h32")
+    args = types.SimpleNamespace(device="cpu", hidden_units=g.H)
+    m = BaselineEmbedding(g.user_num, g.item_num, g.feat_statistics, g.feat_types, args)
+    from tencent_recommendation_2025_b200.packed import to_device
+    pb = to_device(m.layout, g.calls(0)[1], "cpu", pin=False)
+    with pytest.raises(TgrError):
+        m.feat2emb_packed(pb)
+
+
+@pytest.mark.parametrize("W", [1, 2, 4, 8])
+def test_route_bucket_bit_exact(W):
+    import ctypes as C
+    from tencent_recommendation_2025_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(W)
+    keys = np.unique(rng.integers(1, 200000, size=50000)).astype(np.uint32)
+    n = keys.size
+    d_keys = torch.from_numpy(keys.view(np.int32)).cuda()
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    cap = n + 777
+    d_keys_pad = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    d_keys_pad[:n] = d_keys
+    rows = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    perm = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    counts = torch.zeros(W, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.tgr_route_workspace_bytes(cap, W), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.tgr_route_bucket(d_keys_pad.data_ptr(), n_dev.data_ptr(), cap, W, rows.data_ptr(), perm.data_ptr(),
+                                    counts.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    owner, local, cnt, order = onp.route(keys, W)
+    assert np.array_equal(counts.cpu().numpy(), cnt)
+    assert np.array_equal(rows[:n].cpu().numpy().view(np.uint32), local[order].astype(np.uint32))
+    inv = np.empty(n, np.int64)
+    inv[order] = np.arange(n)
+    assert np.array_equal(perm[:n].cpu().numpy(), inv)
