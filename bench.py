@@ -1,0 +1,390 @@
+"""bench.py — embedding fwd+bwd rows/sec of the TencentGR sparse-feature path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c3|c5|c1]
+
+One "step" = one training step's worth of the hot path on one synthetic batch:
+  3 x feat2emb forward (seq with users, pos, neg: model.py:324,376-377)  — fused gather/pool/concat kernels,
+      mm projection, then the reference's own itemdnn/userdnn torch calls
+  + backward from injected upstream gradients            — torch Linear backward, mm dW/db,
+      key build, radix sort, fixed-tile segmented reduction
+  + fused sparse AdamW row update of every touched table row.
+"row" = one non-padding table-row lookup in a forward call. `value` = rows/s with inputs resident in HBM;
+`e2e` = the same step driven from HOST packed buffers (pinned H2D inside the timed region, loss read back).
+`roofline` describes the dominant kernel, timed live with CUDA events on the launching stream.
+`--impl reference` times the CPU oracle port (the reference's torch op sequence + dense AdamW, all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from tencent_recommendation_2025_b200 import synth  # noqa: E402
+
+METRIC = "embedding fwd+bwd rows/sec at 1/2/4/8 B200; % of HBM roofline"
+UNIT = "rows/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def get_config(name: str, B: int):
+    if name == "c1":
+        return synth.config_c1()
+    if name == "c2":
+        return synth.config_c2(B)
+    if name == "c3":
+        return synth.config_c3(B)
+    if name == "c4":
+        return synth.config_c4(B)
+    if name == "c5":
+        return synth.config_c5(B)
+    raise ValueError(name)
+
+
+WORKLOADS = {
+    "c1": "C1 BaseLine tiny batch (B=128, L=101, H=32, 100k items)",
+    "c2": "C2 BaseLine feat2emb fwd+bwd, full feature mix (B=1024/GPU, L=101, H=64, 5M-row item table, mm '81')",
+    "c3": "C3 BaseLineO1 + frozen mm features '81'+'82' (1024-d) projection",
+    "c4": "C4 row-sharded 50M-row item/user tables",
+    "c5": "C5 high-skew Zipf 1.2, 50M-row tables",
+}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def init_module(cfg: synth.SynthConfig, device, mode="fused"):
+    from tencent_recommendation_2025_b200.module import BaselineEmbedding
+    args = types.SimpleNamespace(device=str(device), hidden_units=cfg.H)
+    with torch.device(device):
+        m = BaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), args, mode=mode)
+    g = torch.Generator(device=device).manual_seed(0)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() >= 2:
+                p.normal_(0.0, 0.05, generator=g)
+            else:
+                p.normal_(0.0, 0.1, generator=g)
+        for p in m.engine.tables:
+            p[0].zero_()
+    return m
+
+
+def algorithmic_bytes(lay, calls, uniq_per_call, uniq_step, cat_esz=4, x_esz=4):
+    """SURVEY.md §8(d), counted compulsory from the actual batch. Returns (fwd_bytes, bwd_bytes, detail)."""
+    H = lay.H
+    fwd = bwd = 0
+    for pc, U in zip(calls, uniq_per_call):
+        cl = lay.calls[pc.include_user]
+        S = pc.ids.size + pc.arr_val.size + pc.arr_off.size
+        D = cl.item_dim + cl.user_dim
+        X = sum(lay.item_emb_feat.values())
+        fwd += 4 * S + U * H * 4 + pc.T * D * cat_esz + pc.T * X * x_esz
+        bwd += 4 * S + pc.T * D * cat_esz + pc.T * X * x_esz
+    bwd += uniq_step * 6 * H * 4
+    return fwd, bwd
+
+
+def unique_counts(lay, calls):
+    from oracle import feat2emb_numpy as onp  # checker-side accounting only (exact U), never the timed path
+    per = []
+    allk = []
+    for pc in calls:
+        k, _ = onp.build_keys(lay, [pc])
+        per.append(int(np.unique(k).size))
+        allk.append(k)
+    return per, int(np.unique(np.concatenate(allk)).size)
+
+
+def run_gpu(args):
+    from tencent_recommendation_2025_b200.packed import to_device
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    if world > 1:
+        from bench_sharded import run_sharded  # row-sharded tables + all-to-all
+        return run_sharded(args, rank, world, local_rank)
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    hbm_peak, peak_src = load_peaks()
+    cfg = get_config(args.config, args.batch)
+    worldgen = synth.SynthWorld(cfg, 0)
+    lay = worldgen.layout
+    m = init_module(cfg, dev, "fused")
+    dense_opt = torch.optim.AdamW(m.dense_parameters(), lr=1e-3, betas=(0.9, 0.98))
+    eng = m.engine
+    n_batches = max(1, min(args.batches, args.steps + args.warmup))
+    steps_np = [worldgen.make_step(s) for s in range(n_batches)]
+    dev_steps = []
+    for st in steps_np:
+        pbs = [to_device(lay, pc, dev) for pc in st.calls]
+        ups = [torch.from_numpy(r).to(dev) for r in st.upstream]
+        dev_steps.append((pbs, ups))
+    torch.cuda.synchronize()
+    hyper = dict(lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
+
+    def one_step(pbs, ups):
+        dense_opt.zero_grad(set_to_none=True)
+        outs = [m.feat2emb_packed(pb) for pb in pbs]
+        torch.autograd.backward(outs, ups)
+        dense_opt.step()
+        m.fused_step(**hyper)
+        return outs
+
+    # ---- device-resident timing (value) -------------------------------------------------------
+    for i in range(args.warmup):
+        one_step(*dev_steps[i % n_batches])
+    torch.cuda.synchronize()
+    eng.timing = {}
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    rows = 0
+    for i in range(args.steps):
+        k = (args.warmup + i) % n_batches
+        one_step(*dev_steps[k])
+        rows += steps_np[k].n_lookups()
+    ev1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launches - l0
+    kern_ms = eng.timing_summary()
+    eng.timing = None
+    value = rows / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    per_u, step_u = [], []
+    alg_f = alg_b = 0
+    used = [(args.warmup + i) % n_batches for i in range(args.steps)]
+    stats = {}
+    for k in sorted(set(used)):
+        pu, su = unique_counts(lay, steps_np[k].calls)
+        f, b = algorithmic_bytes(lay, steps_np[k].calls, pu, su)
+        stats[k] = (pu, su, f, b)
+    H = lay.H
+    kernel_bytes = {"fwd_gather_pool_concat": 0.0, "bwd_reduce_adam": 0.0}
+    for k in used:
+        pu, su, f, b = stats[k]
+        alg_f += f
+        alg_b += b
+        st = steps_np[k]
+        for pc, U in zip(st.calls, pu):
+            cl = lay.calls[pc.include_user]
+            d_tab = cl.item_dim + cl.user_dim - H * cl.n_mm       # columns the gather kernel writes
+            kernel_bytes["fwd_gather_pool_concat"] += 4 * (pc.ids.size + pc.arr_val.size + pc.arr_off.size) + U * H * 4 + pc.T * d_tab * 4
+        n_valid = sum(pb.n_valid for pb in dev_steps[k][0])
+        # reduce+AdamW: sorted (key, src) pairs + one gradient row per non-padding lookup + w,m,v read+write per unique row
+        kernel_bytes["bwd_reduce_adam"] += 8 * n_valid + n_valid * H * 4 + su * 6 * H * 4
+    dom = max(kernel_bytes, key=lambda n: kern_ms.get(n, (0.0, 0))[0])
+    dom_ms, dom_launches = kern_ms.get(dom, (0.0, 0))
+    achieved = kernel_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "kernel_ms_per_step": round(dom_ms / args.steps, 4), "launches": dom_launches,
+                "kernels_ms_per_step": {n: round(v[0] / args.steps, 4) for n, v in kern_ms.items()},
+                "step_algorithmic_GB": round((alg_f + alg_b) / args.steps / 1e9, 3),
+                "step_frac_of_hbm_peak": round((alg_f + alg_b) / (ms * 1e-3) / 1e9 / hbm_peak, 4)}
+
+    # ---- end to end from host buffers (e2e) ----------------------------------------------------
+    e2e_steps = max(3, min(args.steps, 10))
+    torch.cuda.synchronize()
+    h2d = d2h = 0
+    t_e2e = 0.0
+    rows_e2e = 0
+    for i in range(e2e_steps + 1):
+        k = i % n_batches
+        st = steps_np[k]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pbs = [to_device(lay, pc, dev) for pc in st.calls]          # pinned staging + async H2D
+        outs = one_step(pbs, dev_steps[k][1])
+        loss_host = float(sum(o.sum() for o in outs).item())        # D2H read of the step's result
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i == 0:
+            continue  # warm-up of the host path
+        t_e2e += dt
+        rows_e2e += st.n_lookups()
+        h2d += sum(pb.h2d_bytes for pb in pbs)
+        d2h += 4
+    e2e = {"value": rows_e2e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps,
+           "d2h_bytes_per_step": d2h // e2e_steps, "ms_per_step": round(t_e2e / e2e_steps * 1e3, 3),
+           "entry": "BaselineEmbedding.feat2emb_packed from host PackedCall buffers (pinned H2D in the timed region)"}
+
+    # ---- CPU baseline (bounded sample, rank 0, N=1) ---------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_reference(cfg, steps=2, warmup=1, batch=args.cpu_batch)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.config], "batch_per_gpu": cfg.B, "seq_len": cfg.L, "hidden": cfg.H,
+                       "item_rows": cfg.item_num + 1, "user_rows": cfg.user_num + 1, "zipf_alpha": cfg.alpha,
+                       "mm_features": list(cfg.mm_ids), "row_update": "fused sparse AdamW (lazy rows)",
+                       "rows_per_step": rows // args.steps, "tokens_per_step": 3 * cfg.B * cfg.L,
+                       "l2": "per-step working set (concat buffers ~1.3 GB + 6 GB of tables/state) >> 126 MB L2; "
+                             f"{n_batches} distinct batches cycled"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(cfg: synth.SynthConfig, steps: int, warmup: int, batch: int):
+    """The reference's CPU path (oracle port: same torch ops feat2emb issues + dense AdamW on the hot-path
+    parameters, main.py:131) on the host cores, on a bounded sample of the workload."""
+    import dataclasses
+    from oracle import feat2emb_numpy as onp
+    from oracle.feat2emb_torch import TorchOracle, tensors_to_torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    scfg = dataclasses.replace(cfg, B=min(batch, cfg.B))
+    world = synth.SynthWorld(scfg, 0)
+    lay = world.layout
+    orc = TorchOracle(lay)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for p in orc.parameters():
+            p.normal_(0.0, 0.05, generator=g)
+        for p in orc.table_params():
+            p[0].zero_()
+    opt = torch.optim.AdamW(orc.parameters(), lr=1e-3, betas=(0.9, 0.98))
+    times, rows = [], 0
+    for i in range(warmup + steps):
+        st = world.make_step(i)
+        inputs = []
+        for pc in st.calls:
+            t = tensors_to_torch(onp.tensors_from_packed(lay, pc))
+            seq = torch.from_numpy(pc.seq.astype(np.int64))
+            mask = torch.from_numpy(pc.mask.astype(np.int64)) if pc.include_user else None
+            inputs.append((seq, t, mask, pc.include_user))
+        ups = [torch.from_numpy(r) for r in st.upstream]
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        outs = [orc.feat2emb(*inp) for inp in inputs]
+        torch.autograd.backward(outs, ups)
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            rows += st.n_lookups()
+    return {"value": rows / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+            "ms_per_step": round(sum(times) / len(times) * 1e3, 1),
+            "sample": f"{steps} steps of B={scfg.B} (of {cfg.B}) sequences, same tables/feature mix; feat2tensor outputs "
+                      "pre-built (no Python dict walk); dense AdamW over all hot-path parameters as the reference does"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = get_config(args.config, args.batch)
+    total = args.steps + args.warmup
+    batch = args.cpu_batch if total <= 12 else max(64, args.cpu_batch // 4)
+    cpu = cpu_reference(cfg, steps=args.steps, warmup=args.warmup, batch=batch)
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.config], "seq_len": cfg.L, "hidden": cfg.H,
+                       "item_rows": cfg.item_num + 1, "user_rows": cfg.user_num + 1, "zipf_alpha": cfg.alpha,
+                       "mm_features": list(cfg.mm_ids)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=1024, help="sequences per GPU")
+    ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches to cycle")
+    ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -67,6 +67,27 @@ class EmbeddingEngine:
         self.launches = 0          # kernels launched by this engine (bench's gpu_launches)
         self.check_ids = _DEBUG
         self._err: Optional[torch.Tensor] = None
+        self.timing: Optional[Dict[str, list]] = None   # set to {} to time every C-ABI call with CUDA events
+
+    # ------------------------------------------------------------------ per-kernel timing (bench / profiling)
+    def _t0(self):
+        if self.timing is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _t1(self, name: str, e0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.timing.setdefault(name, []).append((e0, e1))
+
+    def timing_summary(self) -> Dict[str, Tuple[float, int]]:
+        """{call name: (total ms, launches)} over everything recorded since ``timing`` was set."""
+        torch.cuda.synchronize()
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in (self.timing or {}).items()}
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, name: str, nbytes: int, device) -> torch.Tensor:
@@ -147,8 +168,10 @@ class EmbeddingEngine:
         user_cat = torch.empty((T, cl.user_dim), dtype=out_dtype, device=dev) if pb.include_user else None
         tabs = self._table_array()
         call = self._call_struct(pb, item_cat, user_cat)
+        e0 = self._t0()
         check(self.lib.tgr_fwd_gather_pool_concat(tabs, len(self.tables), lay.H, C.byref(call), _stream()),
               "tgr_fwd_gather_pool_concat")
+        self._t1("fwd_gather_pool_concat", e0)
         self.launches += 1
         esz = item_cat.element_size()
         for s in cl.slots:
@@ -161,9 +184,11 @@ class EmbeddingEngine:
             w, b = lin.weight.data, lin.bias.data if lin.bias is not None else None
             if w.dtype != torch.float32 or not w.is_contiguous():
                 raise TypeError("emb_transform weight must be contiguous float32")
+            e0 = self._t0()
             check(self.lib.tgr_mm_proj_fwd(x.data_ptr(), _dtype_code(x.dtype), T, s.mm_dim, w.data_ptr(), _ptr(b), lay.H,
                                            item_cat.data_ptr() + s.col * esz, item_cat.stride(0),
                                            _dtype_code(item_cat.dtype), _stream()), "tgr_mm_proj_fwd")
+            self._t1("mm_proj_fwd", e0)
             self.launches += 1
         if self.check_ids:
             bad = int(self._err.item())
@@ -186,10 +211,12 @@ class EmbeddingEngine:
             db = torch.empty((lay.H,), dtype=torch.float32, device=d_item.device)
             nbytes = self.lib.tgr_mm_proj_bwd_workspace_bytes(pb.T, s.mm_dim, lay.H)
             ws = self._buf("mm_bwd", nbytes, d_item.device)
+            e0 = self._t0()
             check(self.lib.tgr_mm_proj_bwd(x.data_ptr(), _dtype_code(x.dtype), pb.T, s.mm_dim,
                                            d_item.data_ptr() + s.col * esz, d_item.stride(0), _dtype_code(d_item.dtype),
                                            lay.H, dW.data_ptr(), db.data_ptr(), 0, ws.data_ptr(), ws.numel(), _stream()),
                   "tgr_mm_proj_bwd")
+            self._t1("mm_proj_bwd", e0)
             self.launches += 2
             out[s.name] = (dW, db)
         return out
@@ -222,18 +249,19 @@ class EmbeddingEngine:
         ws_bytes = max(self.lib.tgr_build_keys_workspace_bytes(n_max), self.lib.tgr_sort_workspace_bytes(n))
         ws = self._buf("keys_ws", ws_bytes, dev)
         tabs = self._table_array()
-        # emit writes at most n_valid(device) <= n entries only if the host count is right; guard the buffer size
-        if n < n_max and _DEBUG:
-            pass
+        e0 = self._t0()
         check(self.lib.tgr_bwd_build_keys(tabs, len(self.tables), structs, n_calls, keys_a, srcs_a, cnt.data_ptr(),
                                           ws.data_ptr(), ws.numel(), _stream()), "tgr_bwd_build_keys")
+        self._t1("bwd_build_keys", e0)
         self.launches += 3
         if _DEBUG:
             got = int(cnt.view(torch.int32)[0].item())
             if got != n:
                 raise _lib.TgrError(f"PackedBatch.n_valid mismatch: host {n}, device {got}")
+        e0 = self._t0()
         check(self.lib.tgr_sort_pairs(keys_a, srcs_a, keys_b, srcs_b, n, self.layout.key_bits, ws.data_ptr(), ws.numel(),
                                       _stream()), "tgr_sort_pairs")
+        self._t1("sort_pairs", e0)
         self.launches += 5
         return structs, keys_b, srcs_b, n, calls
 
@@ -300,8 +328,10 @@ class EmbeddingEngine:
             rws = self._buf("reduce_ws", self.lib.tgr_reduce_workspace_bytes(n, H), dev)
             tabs = self._table_array(state=True)
             adam = make_adam(lr, betas[0], betas[1], eps, weight_decay, self.step, grad_scale)
+            e0 = self._t0()
             check(self.lib.tgr_bwd_reduce(tabs, len(self.tables), H, structs, len(group), keys, srcs, n, 1, None, None,
                                           C.byref(adam), rws.data_ptr(), rws.numel(), _stream()), "tgr_bwd_reduce")
+            self._t1("bwd_reduce_adam", e0)
             self.launches += 2
             total += n
         return total
