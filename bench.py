@@ -83,12 +83,19 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:   # nvidia-smi takes a moment to emit its first sample
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples from here on belong to the timed region."""
+        self.first = len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -104,7 +111,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        timed = self.lines[getattr(self, "first", 0):]
+        # a timed region shorter than a couple of sampling periods falls back to warm-up + timed samples (same load)
+        for ln in (timed if len(timed) >= 3 else self.lines[1:]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -178,6 +187,9 @@ def run_gpu(args):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # itemdnn/userdnn stay the caller's torch Linear calls; the reference's launcher runs them with TF32
+    # (run.sh:8 --use_tf32 -> main.py:66-68). Tables, concat buffers, gradients and the row update stay fp32.
+    torch.backends.cuda.matmul.allow_tf32 = args.dnn_matmul == "tf32"
     hbm_peak, peak_src = load_peaks()
     cfg = get_config(args.config, args.batch)
     worldgen = synth.SynthWorld(cfg, 0)
@@ -204,12 +216,13 @@ def run_gpu(args):
         return outs
 
     # ---- device-resident timing (value) -------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for i in range(args.warmup):
         one_step(*dev_steps[i % n_batches])
     torch.cuda.synchronize()
     eng.timing = {}
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark()
     l0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -298,6 +311,7 @@ def run_gpu(args):
             "config": {"workload": WORKLOADS[args.config], "batch_per_gpu": cfg.B, "seq_len": cfg.L, "hidden": cfg.H,
                        "item_rows": cfg.item_num + 1, "user_rows": cfg.user_num + 1, "zipf_alpha": cfg.alpha,
                        "mm_features": list(cfg.mm_ids), "row_update": "fused sparse AdamW (lazy rows)",
+                       "dnn_matmul": f"torch F.linear (caller side, unchanged), {args.dnn_matmul} as reference run.sh --use_tf32",
                        "rows_per_step": rows // args.steps, "tokens_per_step": 3 * cfg.B * cfg.L,
                        "l2": "per-step working set (concat buffers ~1.3 GB + 6 GB of tables/state) >> 126 MB L2; "
                              f"{n_batches} distinct batches cycled"},
@@ -380,6 +394,8 @@ def main():
     ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches to cycle")
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dnn-matmul", default="tf32", choices=["tf32", "fp32"],
+                    help="precision of the caller-side torch itemdnn/userdnn matmuls (reference launcher: tf32)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

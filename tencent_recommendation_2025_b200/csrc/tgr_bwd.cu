@@ -144,11 +144,11 @@ struct KeyFunctor {
     const int ns = p->n_seg;
     while (s + 1 < ns && e >= p->seg[s + 1].start) ++s;
     const KeySeg& g = p->seg[s];
-    const int64_t i = e - g.start;
+    const uint32_t i = (uint32_t)(e - g.start);   // a segment holds < 2^31 entries: 32-bit index math
     if (g.n_cols > 0) {
       const int id = __ldg(g.vals + i);
-      const int t = (int)(i / g.n_cols);
-      const int c = (int)(i - (int64_t)t * g.n_cols);
+      const uint32_t t = i / (uint32_t)g.n_cols;
+      const int c = (int)(i - t * (uint32_t)g.n_cols);
       if (id <= 0 || id >= p->col_rows[g.call][c]) return false;
       key = p->col_key_base[g.call][c] + (uint32_t)id;
       src = ((uint32_t)g.call << TGR_SRC_CALL_SHIFT) | ((uint32_t)p->col_slot[g.call][c] << TGR_SRC_SLOT_SHIFT) | (uint32_t)t;

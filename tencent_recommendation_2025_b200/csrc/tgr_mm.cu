@@ -199,20 +199,24 @@ __global__ void __launch_bounds__(kMmThreads) mm_proj_bwd_partial_kernel(const v
   if (blockIdx.y == 0 && tid < H) ws_db[(size_t)chunk * H + tid] = dbacc;
 }
 
-__global__ void mm_proj_bwd_reduce_kernel(const float* __restrict__ ws_dw, const float* __restrict__ ws_db,
-                                          int n_chunks, int H, int K, float* __restrict__ dW, float* __restrict__ db,
-                                          int accumulate) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output element: lanes stride the chunk partials, then a fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(256) mm_proj_bwd_reduce_kernel(const float* __restrict__ ws_dw,
+                                                                 const float* __restrict__ ws_db, int n_chunks, int H,
+                                                                 int K, float* __restrict__ dW, float* __restrict__ db,
+                                                                 int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nW = (int64_t)H * K;
-  if (i < nW) {
-    float s = 0.f;
-    for (int c = 0; c < n_chunks; ++c) s += ws_dw[(size_t)c * nW + i];  // fixed order
-    dW[i] = accumulate ? dW[i] + s : s;
-  } else if (i < nW + H) {
-    const int h = (int)(i - nW);
-    float s = 0.f;
-    for (int c = 0; c < n_chunks; ++c) s += ws_db[(size_t)c * H + h];
-    if (db) db[h] = accumulate ? db[h] + s : s;
+  if (i >= nW + H) return;
+  const float* src = i < nW ? ws_dw + i : ws_db + (i - nW);
+  const int64_t stride = i < nW ? nW : H;
+  float s = 0.f;
+  for (int c = lane; c < n_chunks; c += 32) s += src[(size_t)c * stride];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    if (i < nW) dW[i] = accumulate ? dW[i] + s : s;
+    else if (db) db[i - nW] = accumulate ? db[i - nW] + s : s;
   }
 }
 
@@ -285,6 +289,6 @@ extern "C" int tgr_mm_proj_bwd(const void* x, int x_dtype, int64_t T, int mm_dim
     if (int rc = check_launch("mm_proj_bwd_partial")) return rc;
   }
   const int64_t total = (int64_t)H * mm_dim + H;
-  mm_proj_bwd_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws_dw, ws_db, T > 0 ? n : 0, H, mm_dim, dW, db, accumulate);
+  mm_proj_bwd_reduce_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, st>>>(ws_dw, ws_db, T > 0 ? n : 0, H, mm_dim, dW, db, accumulate);
   return check_launch("mm_proj_bwd_reduce");
 }

@@ -136,9 +136,44 @@ def count_valid(layout: FeatureLayout, pc: PackedCall) -> int:
     return n
 
 
+class _PinnedPool:
+    """Reusable pinned staging buffers. cudaHostAlloc costs milliseconds, so buffers are recycled; a buffer is
+    handed out again only after the event recorded behind its last H2D copy has completed."""
+
+    def __init__(self):
+        self.free = {}   # (dtype, bucket) -> list of (tensor, event)
+
+    @staticmethod
+    def _bucket(n: int) -> int:
+        b = 1024
+        while b < n:
+            b *= 2
+        return b
+
+    def get(self, n: int, dtype: torch.dtype) -> torch.Tensor:
+        key = (dtype, self._bucket(max(n, 1)))
+        lst = self.free.setdefault(key, [])
+        for i, (t, ev) in enumerate(lst):
+            if ev is None or ev.query():
+                lst.pop(i)
+                return t
+        return torch.empty(key[1], dtype=dtype, pin_memory=True)
+
+    def put(self, t: torch.Tensor, dtype: torch.dtype):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.free.setdefault((dtype, t.numel()), []).append((t, ev))
+
+
+_POOL = _PinnedPool()
+
+
 def to_device(layout: FeatureLayout, pc: PackedCall, device, mm_dtype: torch.dtype = torch.float32,
               pin: bool = True, non_blocking: bool = True) -> PackedBatch:
     """One pinned staging buffer + one async H2D copy for all integer data (and one per mm feature)."""
+    use_pool = pin and torch.cuda.is_available() and torch.device(device).type == "cuda"
+    if pc.n_valid is None:
+        pc.n_valid = count_valid(layout, pc)   # host-known entry count of the backward (cached on the call)
     T = pc.T
     arr_tok = _arr_tok(pc)
     n_arr = pc.arr_off.shape[0]
@@ -149,11 +184,14 @@ def to_device(layout: FeatureLayout, pc: PackedCall, device, mm_dtype: torch.dty
     for s in sizes:
         offs.append(tot)
         tot += (s + 3) // 4 * 4
-    stage = torch.empty(max(tot, 4), dtype=torch.int32, pin_memory=pin and torch.cuda.is_available())
+    n_int = max(tot, 4)
+    stage = _POOL.get(n_int, torch.int32) if use_pool else torch.empty(n_int, dtype=torch.int32)
     st_np = stage.numpy()
     for p, o, s in zip(parts, offs, sizes):
         st_np[o:o + s] = p
-    dev = stage.to(device, non_blocking=non_blocking)
+    dev = stage[:n_int].to(device, non_blocking=non_blocking)
+    if use_pool:
+        _POOL.put(stage, torch.int32)
     ids = dev[offs[0]:offs[0] + sizes[0]].view(T, pc.ids.shape[1])
     arr_off = dev[offs[1]:offs[1] + sizes[1]].view(n_arr, T + 1)
     arr_val = dev[offs[2]:offs[2] + sizes[2]]
@@ -161,16 +199,19 @@ def to_device(layout: FeatureLayout, pc: PackedCall, device, mm_dtype: torch.dty
     mm = []
     h2d = tot * 4
     for x in pc.mm_x:
-        xt = torch.from_numpy(np.ascontiguousarray(x))
-        if mm_dtype != torch.float32:
-            xt = xt.to(mm_dtype)
-        if pin and torch.cuda.is_available():
-            xt = xt.pin_memory()
-        mm.append(xt.to(device, non_blocking=non_blocking))
-        h2d += xt.numel() * xt.element_size()
+        n = x.size
+        if use_pool:
+            st = _POOL.get(n, mm_dtype)
+            view = st[:n].view(x.shape)
+            view.copy_(torch.from_numpy(np.ascontiguousarray(x)))     # converts to mm_dtype on the host
+            mm.append(view.to(device, non_blocking=non_blocking))
+            _POOL.put(st, mm_dtype)
+        else:
+            xt = torch.from_numpy(np.ascontiguousarray(x)).to(mm_dtype)
+            mm.append(xt.to(device, non_blocking=non_blocking))
+        h2d += n * torch.empty((), dtype=mm_dtype).element_size()
     begins = [int(pc.arr_off[j, 0]) for j in range(n_arr)]
     nnz = [int(pc.arr_off[j, -1] - pc.arr_off[j, 0]) for j in range(n_arr)]
     pb = PackedBatch(pc.B, pc.L, pc.include_user, ids, arr_off, arr_val, arr_tok_d, begins, nnz, mm,
-                     count_valid(layout, pc), h2d)
-    pb._stage = stage  # keep the pinned buffer alive until the copy has certainly run
+                     pc.n_valid, h2d)
     return pb

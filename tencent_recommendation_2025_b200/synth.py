@@ -114,6 +114,7 @@ class PackedCall:
     mm_x: List[np.ndarray]               # float32 [T, mm_dim] per mm feature, zeros where the item has none
     seq: Optional[np.ndarray] = None     # int32 [B, L] raw ids (what the reference call receives)
     mask: Optional[np.ndarray] = None    # int32 [B, L] token types (include_user calls)
+    n_valid: Optional[int] = None        # non-padding in-range ids (cached by packed.to_device)
 
     @property
     def T(self) -> int:

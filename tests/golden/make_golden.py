@@ -156,12 +156,49 @@ def make_item_sweep(name, cfg: SynthConfig, seed, n):
     print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def make_bf16_case(name, base_name):
+    """Same inputs/weights as ``base_name`` (read back from its fixture), reference run under
+    ``torch.autocast('cpu', dtype=torch.bfloat16)`` — the bf16 oracle of SURVEY.md F15 / §4."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import Golden
+    g = Golden(base_name)
+    Model = load_ref(str(g.z["variant"]))
+    args = types.SimpleNamespace(device="cpu", norm_first=False, maxlen=g.L - 1, hidden_units=g.H,
+                                 num_blocks=1, num_heads=1, dropout_rate=0.0)
+    model = Model(g.user_num, g.item_num, g.feat_statistics, g.feat_types, args)
+    hp = hot_params(model)
+    for n, p in hp.items():
+        p.data.copy_(torch.from_numpy(g.z[f"param0/{n}"]))
+    outs = []
+    calls = g.calls(0)
+    for c, pc in enumerate(calls):
+        dicts = packed_to_dicts(g.layout, pc)
+        seq = torch.from_numpy(pc.seq)
+        mask = torch.from_numpy(pc.mask) if pc.include_user else None
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            outs.append(model.feat2emb(seq, dicts, mask=mask, include_user=pc.include_user))
+    loss = sum((o.float() * torch.from_numpy(r)).sum() for o, r in zip(outs, g.upstream(0)))
+    loss.backward()
+    blob = {"base": base_name}
+    for c, o in enumerate(outs):
+        blob[f"out{c}"] = o.detach().float().numpy()
+    for n, p in hp.items():
+        if p.grad is not None:
+            blob[f"grad/{n}"] = p.grad.float().numpy().copy()
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **blob)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 SMALL_STATS = {"103": 3, "104": 8, "105": 15, "109": 30,
                "100": 5, "117": 12, "111": 30, "118": 50, "101": 90, "102": 6, "119": 11, "120": 25,
                "114": 40, "112": 80, "121": 4, "115": 15, "122": 28, "116": 45,
                "106": 20, "107": 35, "108": 60, "110": 10}
 
 if __name__ == "__main__":
+    if "--bf16-only" in sys.argv:
+        make_bf16_case("o1_h64_bf16", "o1_h64")
+        sys.exit(0)
     # BaseLine: H=32, mm '81', duplicate-heavy ids (alpha 1.2 on a small table)
     make_case("baseline_h32", "BaseLine",
               SynthConfig(B=6, L=12, H=32, item_num=150, user_num=20, alpha=1.2, mm_ids=("81",), min_len=3,
@@ -180,3 +217,4 @@ if __name__ == "__main__":
                           feat_statistics=SMALL_STATS), seed=3, lr=1e-3, wd=1e-2, n_steps=1, store_state=False)
     make_item_sweep("item_sweep", SynthConfig(B=1, L=37, H=32, item_num=300, user_num=10, mm_ids=("81",),
                                               feat_statistics=SMALL_STATS), seed=4, n=37)
+    make_bf16_case("o1_h64_bf16", "o1_h64")

@@ -29,6 +29,16 @@ def _close(a, b, rtol=RTOL, what=""):
     assert err <= rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rtol {rtol})"
 
 
+def _close_fro(a, b, rtol, what=""):
+    """Relative Frobenius error — the bar used for bf16, where single elements carry 2^-9 rounding noise."""
+    a = a.detach().float().cpu().numpy().astype(np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    den = max(np.linalg.norm(b), 1e-30)
+    err = np.linalg.norm(a - b) / den
+    assert err <= rtol, f"{what}: relative Frobenius error {err:.3e} > {rtol}"
+
+
 def make_module(g: Golden, mode="parity"):
     from tencent_recommendation_2025_b200.module import BaselineEmbedding
     args = types.SimpleNamespace(device="cuda", hidden_units=g.H)
@@ -291,20 +301,28 @@ def test_bf16_concat_is_rne_of_fp32():
         assert torch.equal(a, b), f"slot {s.name}: bf16 concat must be the RNE rounding of the fp32 value"
     with torch.autocast("cuda", dtype=torch.bfloat16):
         out = m.feat2emb_packed(pb)
-    _close(out.float(), g.outs(0)[0], rtol=1e-2, what="bf16 autocast output")
+    _close_fro(out, g.outs(0)[0], 1e-2, what="bf16 autocast output")
 
 
 def test_bf16_backward_within_1e2():
+    """bf16 bar (1e-2): oracle = the unmodified reference under torch.autocast(bfloat16),
+    fixture o1_h64_bf16.npz. Relative Frobenius error per tensor; the reference's own bf16-vs-fp32 gap on
+    these tensors is ~1e-2, so comparing against the fp32 fixture would only measure bf16 itself."""
+    import os
+    from golden_util import GOLDEN_DIR
     g = Golden("o1_h64")
+    ref = np.load(os.path.join(GOLDEN_DIR, "o1_h64_bf16.npz"))
     m = make_module(g, "parity")
     with torch.autocast("cuda", dtype=torch.bfloat16):
         outs = [m.feat2emb_packed(dev_batch(m, pc)) for pc in g.calls(0)]
+    for c, o in enumerate(outs):
+        _close_fro(o, ref[f"out{c}"], 1e-2, what=f"bf16 out c{c}")
     loss = sum((o.float() * torch.from_numpy(r).cuda()).sum() for o, r in zip(outs, g.upstream(0)))
     loss.backward()
-    ref = g.group("s0/grad/")
     for k, p in m.named_parameters():
-        if ref[k].size:
-            _close(p.grad, ref[k], rtol=2e-2, what=f"bf16 grad {k}")
+        key = f"grad/{k}"
+        if key in ref.files:
+            _close_fro(p.grad, ref[key], 1e-2, what=f"bf16 grad {k}")
 
 
 @pytest.mark.parametrize("H", [32, 64, 128, 48, 256])
