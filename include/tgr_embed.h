@@ -182,6 +182,16 @@ int tgr_route_bucket(const uint32_t* uniq, const int32_t* n_unique_dev, int64_t 
                      uint32_t* bucketed_local_rows, int32_t* perm, int32_t* counts_dev, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Replace every id of an [n / n_cols, n_cols] id matrix by 1 + perm[index of its global key in uniq] (0 for
+ * padding): turns the packed ids into row numbers of the buffer the all-to-all returned, so the same fused
+ * gather kernel runs on it. col_key_base / col_rows are HOST arrays [n_cols]. */
+int tgr_remap_ids(const int32_t* ids, int64_t n, int n_cols, const uint32_t* col_key_base, const int32_t* col_rows,
+                  const uint32_t* uniq, const int32_t* n_unique_dev, const int32_t* perm, int32_t* out, void* stream);
+
+/* out[perm[u], :] = in[u, :] for u < *n_dev (inverse = 0), or out[u, :] = in[perm[u], :] (inverse = 1). */
+int tgr_permute_rows(const float* in, int H, const int32_t* perm, const int32_t* n_dev, int64_t max_n, int inverse,
+                     float* out, void* stream);
+
 /* Gather rows of a flat table by local row index: out[i, :] = table[rows[i], :] for i < *n_dev. */
 int tgr_gather_rows(const float* table, int H, const uint32_t* rows, const int32_t* n_dev, int64_t max_n, float* out,
                     void* stream);

@@ -296,8 +296,9 @@ def build_keys(layout, packed_calls) -> Tuple[np.ndarray, np.ndarray]:
             keys.append(layout.tables[s.table].key_base + ids[keep])
             srcs.append((c << 29) | (si << 24) | toks[keep])
     if not keys:
-        return np.zeros(0, np.uint32), np.zeros(0, np.uint32)
-    return np.concatenate(keys).astype(np.uint32), np.concatenate(srcs).astype(np.uint32)
+        return np.zeros(0, np.uint32), np.zeros(0, np.int64)
+    # sources stay int64 here so the oracle also handles more than 8 calls (the C ABI packs 3 call bits)
+    return np.concatenate(keys).astype(np.uint32), np.concatenate(srcs).astype(np.int64)
 
 
 def sort_dedup(keys: np.ndarray):

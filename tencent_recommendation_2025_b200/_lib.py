@@ -88,6 +88,9 @@ SIGNATURES = {
     "tgr_route_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "tgr_route_bucket": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tgr_remap_ids": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, u32p, i32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
+    "tgr_permute_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "tgr_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 

@@ -134,3 +134,77 @@ extern "C" int tgr_route_bucket(const uint32_t* uniq, const int32_t* n_unique_de
   route_emit_kernel<<<nb, kRouteBlock, 0, st>>>(uniq, n_unique_dev, W, nb, cnt, bucketed_local_rows, perm);
   return check_launch("route_bucket");
 }
+
+// ---- id remap / row permutation for the sharded exchange ------------------------------------------------
+namespace tgr {
+
+struct RemapCols {
+  uint32_t key_base[TGR_MAX_SLOTS];
+  int32_t rows[TGR_MAX_SLOTS];
+};
+
+// out[i] = 1 + perm[index of (key_base[col] + ids[i]) in uniq]   (0 for padding / out-of-range ids)
+__global__ void __launch_bounds__(256) remap_ids_kernel(const int32_t* __restrict__ ids, int64_t n, int n_cols,
+                                                        const __grid_constant__ RemapCols cols,
+                                                        const uint32_t* __restrict__ uniq,
+                                                        const int32_t* __restrict__ n_unique_dev,
+                                                        const int32_t* __restrict__ perm, int32_t* __restrict__ out) {
+  const int U = *n_unique_dev;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % n_cols);
+    const int id = __ldg(ids + i);
+    int r = 0;
+    if (id > 0 && id < cols.rows[c]) {
+      const uint32_t key = cols.key_base[c] + (uint32_t)id;
+      int lo = 0, hi = U;  // first index with uniq[idx] >= key
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(uniq + mid) < key) lo = mid + 1; else hi = mid;
+      }
+      if (lo < U && __ldg(uniq + lo) == key) r = 1 + __ldg(perm + lo);
+    }
+    out[i] = r;
+  }
+}
+
+// out[perm[u], :] = in[u, :]  (u < *n_dev)   or, inverse = 1:  out[u, :] = in[perm[u], :]
+__global__ void __launch_bounds__(256) permute_rows_kernel(const float* __restrict__ in, int H4,
+                                                           const int32_t* __restrict__ perm,
+                                                           const int32_t* __restrict__ n_dev, int inverse,
+                                                           float* __restrict__ out) {
+  const int n = *n_dev;
+  const int64_t total = (int64_t)n * H4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int u = (int)(i / H4), c = (int)(i - (int64_t)u * H4);
+    const int64_t p = __ldg(perm + u);
+    if (inverse) reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(in) + p * H4 + c);
+    else reinterpret_cast<float4*>(out)[p * H4 + c] = __ldg(reinterpret_cast<const float4*>(in) + i);
+  }
+}
+
+}  // namespace tgr
+
+extern "C" int tgr_remap_ids(const int32_t* ids, int64_t n, int n_cols, const uint32_t* col_key_base,
+                             const int32_t* col_rows, const uint32_t* uniq, const int32_t* n_unique_dev,
+                             const int32_t* perm, int32_t* out, void* stream) {
+  TGR_REQUIRE(n >= 0 && n_cols > 0 && n_cols <= TGR_MAX_SLOTS, "bad n / n_cols");
+  if (n == 0) return 0;
+  TGR_REQUIRE(ids && col_key_base && col_rows && uniq && n_unique_dev && perm && out, "null argument");
+  RemapCols cols{};
+  for (int c = 0; c < n_cols; ++c) { cols.key_base[c] = col_key_base[c]; cols.rows[c] = col_rows[c]; }
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  remap_ids_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ids, n, n_cols, cols, uniq, n_unique_dev, perm, out);
+  return check_launch("remap_ids");
+}
+
+extern "C" int tgr_permute_rows(const float* in, int H, const int32_t* perm, const int32_t* n_dev, int64_t max_n,
+                                int inverse, float* out, void* stream) {
+  TGR_REQUIRE(in && perm && n_dev && out, "null argument");
+  TGR_REQUIRE(H > 0 && H % 4 == 0, "bad H");
+  if (max_n <= 0) return 0;
+  int64_t blocks = (max_n * (H / 4) + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  permute_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, H / 4, perm, n_dev, inverse, out);
+  return check_launch("permute_rows");
+}

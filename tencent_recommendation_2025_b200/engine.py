@@ -15,6 +15,7 @@ from . import _lib
 from ._lib import Adam, Call, Table, check, make_adam
 from .layout import FeatureLayout, KIND_MM
 from .packed import PackedBatch
+from ._structs import StructCache
 
 _DEBUG = os.environ.get("TGR_DEBUG", "0") not in ("", "0")
 
@@ -68,6 +69,8 @@ class EmbeddingEngine:
         self.check_ids = _DEBUG
         self._err: Optional[torch.Tensor] = None
         self.timing: Optional[Dict[str, list]] = None   # set to {} to time every C-ABI call with CUDA events
+        self._structs = StructCache(layout)
+        self._validated = False
 
     # ------------------------------------------------------------------ per-kernel timing (bench / profiling)
     def _t0(self):
@@ -112,49 +115,26 @@ class EmbeddingEngine:
 
     # ------------------------------------------------------------------ C structs
     def _table_array(self, state: bool = False, grads: Optional[List[Optional[torch.Tensor]]] = None):
-        arr = (Table * len(self.tables))()
-        for i, (p, t) in enumerate(zip(self.tables, self.layout.tables)):
-            w = p.data
-            if w.dtype != torch.float32 or not w.is_contiguous():
-                raise TypeError(f"table {t.name} must be contiguous float32")
-            arr[i].weight = w.data_ptr()
-            arr[i].exp_avg = self.exp_avg[i].data_ptr() if state else None
-            arr[i].exp_avg_sq = self.exp_avg_sq[i].data_ptr() if state else None
-            arr[i].grad = grads[i].data_ptr() if grads is not None and grads[i] is not None else None
-            arr[i].rows = t.rows
-            arr[i].key_base = t.key_base
-        return arr
+        ws = [p.data for p in self.tables]
+        if not self._validated:
+            for w, t in zip(ws, self.layout.tables):
+                if w.dtype != torch.float32 or not w.is_contiguous():
+                    raise TypeError(f"table {t.name} must be contiguous float32")
+            self._validated = True
+        if state:
+            return self._structs.tables(ws, self.exp_avg, self.exp_avg_sq, grads)
+        return self._structs.tables(ws, None, None, grads)
 
-    def _call_struct(self, pb: PackedBatch, item_cat: torch.Tensor, user_cat: Optional[torch.Tensor]) -> Call:
+    def _call_struct(self, pb: PackedBatch, item_cat: torch.Tensor, user_cat: Optional[torch.Tensor], out=None) -> Call:
         cl = self.layout.calls[pb.include_user]
-        c = Call()
-        c.T = pb.T
-        c.n_slots = len(cl.slots)
-        c.n_single = cl.n_single
-        c.n_arrays = cl.n_array
-        for i, s in enumerate(cl.slots):
-            c.slots[i].kind, c.slots[i].side, c.slots[i].col = s.kind, s.side, s.col
-            c.slots[i].table, c.slots[i].src = s.table, s.src
         if pb.ids.dtype != torch.int32 or not pb.ids.is_contiguous() or tuple(pb.ids.shape) != (pb.T, cl.n_single):
             raise TypeError("PackedBatch.ids must be contiguous int32 [T, n_single]")
-        c.ids = pb.ids.data_ptr()
-        for a in range(cl.n_array):
-            c.arr_off[a] = pb.arr_off[a].data_ptr()
-            c.arr_tok[a] = pb.arr_tok.data_ptr() + 4 * pb.arr_begin[a]
-            c.arr_begin[a] = pb.arr_begin[a]
-            c.arr_nnz[a] = pb.arr_nnz[a]
-        c.arr_val = pb.arr_val.data_ptr() if pb.arr_val.numel() else None
-        c.item_cat = item_cat.data_ptr()
-        c.item_ld = item_cat.stride(0)
-        c.user_cat = user_cat.data_ptr() if user_cat is not None else None
-        c.user_ld = user_cat.stride(0) if user_cat is not None else 0
-        c.cat_dtype = _dtype_code(item_cat.dtype)
-        c.err_flag = None
+        err = None
         if self.check_ids:
             if self._err is None or self._err.device != item_cat.device:
                 self._err = torch.zeros(1, dtype=torch.int32, device=item_cat.device)
-            c.err_flag = self._err.data_ptr()
-        return c
+            err = self._err.data_ptr()
+        return self._structs.call(pb, item_cat, user_cat, _dtype_code(item_cat.dtype), err, out)
 
     # ------------------------------------------------------------------ forward
     def forward(self, pb: PackedBatch, out_dtype: torch.dtype = torch.float32):
@@ -234,7 +214,7 @@ class EmbeddingEngine:
             if du is not None and not du.is_contiguous():
                 du = du.contiguous()
             calls[i] = (pb, di, du)
-            structs[i] = self._call_struct(pb, di, du)
+            self._call_struct(pb, di, du, out=structs[i])
         n = sum(pb.n_valid for pb, _, _ in calls)
         n_max = int(self.lib.tgr_bwd_max_entries(structs, n_calls))
         if n > n_max:

@@ -1,0 +1,465 @@
+"""Row-sharded embedding tables across W GPUs of one box; the reference is single-GPU.
+
+Partition: global key = table.key_base + id over the flat mega-table; owner = key mod W,
+local_row = key div W. Each rank keeps its slice of the flat table (+ AdamW m, v) and a data-parallel
+share of the batch. One exchange each way per call, always on DEDUPLICATED keys:
+
+  forward : local unique keys -> bucket by owner -> all-to-all counts, then local-row ids (4 B each)
+            -> owner gathers rows -> all-to-all rows back -> ids remapped to the received buffer ->
+            the same fused gather/pool/concat kernel writes the concat buffers.
+  backward: per-unique-key gradients reduced locally first -> all-to-all (local row, grad row) to the
+            owner -> owner stable-sorts by row (source-rank order inside a row) -> fixed-order
+            segmented sum + fused AdamW row update on its slice.
+
+The per-rank logic is written as generators that *yield* collective requests, so the same code runs
+(a) under torch.distributed (NCCL on GPUs, gloo in the CPU tests) and (b) with W emulated ranks inside
+one process (``run_emulated``) — how the 1-GPU test box checks the W>1 routing bit-exactly.
+Local compute is behind ``ShardOps``; the product implementation is ``CudaShardOps`` (C-ABI kernels).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Generator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Call, check, make_adam
+from .engine import EmbeddingEngine, _dtype_code, _stream
+from .layout import FeatureLayout, KIND_ARRAY, KIND_MM, KIND_SINGLE
+from .packed import PackedBatch
+
+
+# ----------------------------------------------------------------------------------------------------
+# key <-> (owner, local row) and table <-> shard layout  (pure index arithmetic, shared by every backend)
+# ----------------------------------------------------------------------------------------------------
+def shard_rows(total_rows: int, W: int) -> int:
+    return (total_rows + W - 1) // W
+
+
+def shard_of_tables(tables: Sequence[torch.Tensor], rank: int, W: int) -> torch.Tensor:
+    """Slice of the flat mega-table owned by ``rank``: rows with global key % W == rank, at key // W."""
+    flat = torch.cat([t.detach() for t in tables], dim=0)
+    n = shard_rows(flat.shape[0], W)
+    out = torch.zeros((n, flat.shape[1]), dtype=flat.dtype, device=flat.device)
+    part = flat[rank::W]
+    out[: part.shape[0]] = part
+    return out
+
+
+def tables_from_shards(layout: FeatureLayout, shards: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """Inverse of shard_of_tables over all ranks -> per-table tensors in layout order (checkpoint keys)."""
+    W = len(shards)
+    H = shards[0].shape[1]
+    flat = torch.zeros((layout.total_rows, H), dtype=shards[0].dtype, device=shards[0].device)
+    for r, s in enumerate(shards):
+        n = len(range(r, layout.total_rows, W))
+        flat[r::W] = s[:n]
+    return [flat[t.key_base:t.key_base + t.rows].clone() for t in layout.tables]
+
+
+# ----------------------------------------------------------------------------------------------------
+# local compute (product = CUDA kernels through the C ABI)
+# ----------------------------------------------------------------------------------------------------
+class CudaShardOps:
+    """Per-rank device work of the sharded path; every method is a handful of C-ABI kernel launches."""
+
+    def __init__(self, layout: FeatureLayout, local_table: torch.Tensor, mm: Dict[str, torch.nn.Linear], W: int):
+        self.lib = _lib.load()
+        self.layout = layout
+        self.W = W
+        self.local = local_table
+        self.exp_avg = torch.zeros_like(local_table)
+        self.exp_avg_sq = torch.zeros_like(local_table)
+        dev = local_table.device
+        # a helper engine over a dummy table set only provides key building / sorting / reduction plumbing
+        self._dummy = [torch.nn.Parameter(torch.empty((0, layout.H), device=dev), requires_grad=False) for _ in layout.tables]
+        self.mm = mm
+        self._ws: Dict[str, torch.Tensor] = {}
+        self.launches = 0
+        self.step = 0
+        self._eng = _KeyEngine(layout, dev)
+
+    def _buf(self, name, nbytes, dev):
+        b = self._ws.get(name)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(int(nbytes * 1.25), 256), dtype=torch.uint8, device=dev)
+            self._ws[name] = b
+        return b
+
+    # -- forward -------------------------------------------------------------------------------------
+    def unique_keys(self, pbs: List[PackedBatch]):
+        """Sorted unique global keys of the calls' non-padding ids -> (uniq int32[cap], n_unique int32[1], cap)."""
+        dev = self.local.device
+        n = sum(pb.n_valid for pb in pbs)
+        keys, srcs = self._eng.sorted_pairs(pbs, None)
+        cap = max(n, 1)
+        uniq = torch.empty(cap, dtype=torch.int32, device=dev)
+        seg_off = torch.empty(cap + 1, dtype=torch.int32, device=dev)
+        n_unique = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = self._buf("dedup", self.lib.tgr_dedup_workspace_bytes(n), dev)
+        check(self.lib.tgr_dedup(keys, n, uniq.data_ptr(), seg_off.data_ptr(), None, n_unique.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), _stream()), "tgr_dedup")
+        self.launches += 12
+        return uniq, n_unique, cap
+
+    def route(self, uniq, n_unique, cap):
+        dev = uniq.device
+        rows = torch.empty(cap, dtype=torch.int32, device=dev)
+        perm = torch.empty(cap, dtype=torch.int32, device=dev)
+        counts = torch.zeros(self.W, dtype=torch.int32, device=dev)
+        ws = self._buf("route", self.lib.tgr_route_workspace_bytes(cap, self.W), dev)
+        check(self.lib.tgr_route_bucket(uniq.data_ptr(), n_unique.data_ptr(), cap, self.W, rows.data_ptr(), perm.data_ptr(),
+                                        counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "tgr_route_bucket")
+        self.launches += 3
+        return rows, perm, counts
+
+    def gather(self, rows: torch.Tensor, n: int) -> torch.Tensor:
+        dev = self.local.device
+        out = torch.empty((n, self.layout.H), dtype=torch.float32, device=dev)
+        if n:
+            n_dev = torch.tensor([n], dtype=torch.int32, device=dev)
+            check(self.lib.tgr_gather_rows(self.local.data_ptr(), self.layout.H, rows.data_ptr(), n_dev.data_ptr(), n,
+                                           out.data_ptr(), _stream()), "tgr_gather_rows")
+            self.launches += 1
+        return out
+
+    def forward_from_rows(self, pb: PackedBatch, uniq, n_unique, perm, rows_buf: torch.Tensor, out_dtype):
+        """rows_buf [U+1, H] (row 0 zero) holds this call's unique rows in bucketed order; remap ids, then run
+        the fused gather/pool/concat kernel on it as if it were one table."""
+        lay = self.layout
+        dev = rows_buf.device
+        cl = lay.calls[pb.include_user]
+        n_rows = rows_buf.shape[0]
+        names = [s for s in cl.slots if s.kind == KIND_SINGLE]
+        kb = (C.c_uint32 * _lib.MAX_SLOTS)()
+        rw = (C.c_int32 * _lib.MAX_SLOTS)()
+        for s in names:
+            kb[s.src] = lay.tables[s.table].key_base
+            rw[s.src] = lay.tables[s.table].rows
+        ids_r = torch.empty_like(pb.ids)
+        check(self.lib.tgr_remap_ids(pb.ids.data_ptr(), pb.ids.numel(), cl.n_single, kb, rw, uniq.data_ptr(),
+                                     n_unique.data_ptr(), perm.data_ptr(), ids_r.data_ptr(), _stream()), "tgr_remap_ids")
+        arr_r = torch.empty_like(pb.arr_val)
+        for s in cl.slots:
+            if s.kind != KIND_ARRAY or pb.arr_nnz[s.src] == 0:
+                continue
+            kb1 = (C.c_uint32 * 1)(lay.tables[s.table].key_base)
+            rw1 = (C.c_int32 * 1)(lay.tables[s.table].rows)
+            off = 4 * pb.arr_begin[s.src]
+            check(self.lib.tgr_remap_ids(pb.arr_val.data_ptr() + off, pb.arr_nnz[s.src], 1, kb1, rw1, uniq.data_ptr(),
+                                         n_unique.data_ptr(), perm.data_ptr(), arr_r.data_ptr() + off, _stream()),
+                  "tgr_remap_ids(array)")
+            self.launches += 1
+        pb_r = PackedBatch(pb.B, pb.L, pb.include_user, ids_r, pb.arr_off, arr_r, pb.arr_tok, pb.arr_begin, pb.arr_nnz,
+                           pb.mm_x, pb.n_valid)
+        T = pb.T
+        item_cat = torch.empty((T, cl.item_dim), dtype=out_dtype, device=dev)
+        user_cat = torch.empty((T, cl.user_dim), dtype=out_dtype, device=dev) if pb.include_user else None
+        tabs = (_lib.Table * len(lay.tables))()
+        base = 0
+        for i in range(len(lay.tables)):
+            tabs[i].weight = rows_buf.data_ptr()
+            tabs[i].rows = n_rows
+            tabs[i].key_base = base
+            base += n_rows
+        call = self._eng.structs.call(pb_r, item_cat, user_cat, _dtype_code(out_dtype), None)
+        e0 = self._eng._t0()
+        check(self.lib.tgr_fwd_gather_pool_concat(tabs, len(lay.tables), lay.H, C.byref(call), _stream()),
+              "tgr_fwd_gather_pool_concat")
+        self._eng._t1("fwd_gather_pool_concat", e0)
+        self.launches += 2
+        esz = item_cat.element_size()
+        for s in cl.slots:
+            if s.kind != KIND_MM:
+                continue
+            lin = self.mm[s.name]
+            x = pb.mm_x[s.src]
+            check(self.lib.tgr_mm_proj_fwd(x.data_ptr(), _dtype_code(x.dtype), T, s.mm_dim, lin.weight.data.data_ptr(),
+                                           lin.bias.data.data_ptr(), lay.H, item_cat.data_ptr() + s.col * esz,
+                                           item_cat.stride(0), _dtype_code(out_dtype), _stream()), "tgr_mm_proj_fwd")
+            self.launches += 1
+        return item_cat, user_cat
+
+    # -- backward ------------------------------------------------------------------------------------
+    def reduce(self, calls):
+        """Per-unique-key gradient rows of the queued calls -> (uniq, n_unique, grads [cap, H], cap)."""
+        uniq, seg_off, n_unique, grads, n = self._eng.dedup_reduce(calls)
+        self.launches += 14
+        return uniq, n_unique, grads, max(n, 1)
+
+    def permute(self, grads, perm, n_unique, cap):
+        out = torch.empty_like(grads)
+        check(self.lib.tgr_permute_rows(grads.data_ptr(), self.layout.H, perm.data_ptr(), n_unique.data_ptr(), cap, 0,
+                                        out.data_ptr(), _stream()), "tgr_permute_rows")
+        self.launches += 1
+        return out
+
+    def mm_backward(self, pb, d_item):
+        return self._eng.mm_backward_with(self.mm, pb, d_item)
+
+    def apply(self, recv_rows: torch.Tensor, recv_grads: torch.Tensor, R: int, hyper: dict):
+        """Owner side: contributions arrive ordered by (source rank, key); a stable sort by local row keeps the
+        source-rank order inside each row, then the fixed-tile reduction + AdamW updates the slice in place."""
+        self.step += 1
+        if R == 0:
+            return
+        dev = self.local.device
+        H = self.layout.H
+        if R > (1 << 24):
+            raise ValueError("more than 2^24 received contributions in one step")
+        pos = torch.arange(R, dtype=torch.int32, device=dev)
+        keys_out = torch.empty(R, dtype=torch.int32, device=dev)
+        pos_out = torch.empty(R, dtype=torch.int32, device=dev)
+        ws = self._buf("sort", self.lib.tgr_sort_workspace_bytes(R), dev)
+        bits = max(1, int(self.local.shape[0] - 1).bit_length())
+        check(self.lib.tgr_sort_pairs(recv_rows.data_ptr(), pos.data_ptr(), keys_out.data_ptr(), pos_out.data_ptr(), R, bits,
+                                      ws.data_ptr(), ws.numel(), _stream()), "tgr_sort_pairs")
+        tab = (_lib.Table * 1)()
+        tab[0].weight = self.local.data_ptr()
+        tab[0].exp_avg = self.exp_avg.data_ptr()
+        tab[0].exp_avg_sq = self.exp_avg_sq.data_ptr()
+        tab[0].rows = self.local.shape[0]
+        tab[0].key_base = 0
+        call = Call()
+        call.T = R
+        call.n_slots = 1
+        call.n_single = 1
+        call.slots[0].kind, call.slots[0].side, call.slots[0].col, call.slots[0].table, call.slots[0].src = 0, 0, 0, 0, 0
+        call.item_cat = recv_grads.data_ptr()
+        call.item_ld = H
+        call.cat_dtype = _lib.DTYPE_F32
+        adam = make_adam(hyper["lr"], hyper["betas"][0], hyper["betas"][1], hyper["eps"], hyper["weight_decay"], self.step,
+                         hyper.get("grad_scale", 1.0))
+        rws = self._buf("reduce", self.lib.tgr_reduce_workspace_bytes(R, H), dev)
+        check(self.lib.tgr_bwd_reduce(tab, 1, H, C.byref(call), 1, keys_out.data_ptr(), pos_out.data_ptr(), R, 1, None, None,
+                                      C.byref(adam), rws.data_ptr(), rws.numel(), _stream()), "tgr_bwd_reduce")
+        self.launches += 7
+
+
+class _KeyEngine(EmbeddingEngine):
+    """EmbeddingEngine plumbing (key build / sort / dedup / reduce) without owning real tables: the global
+    key space comes from the layout, table pointers are never dereferenced by those kernels."""
+
+    def __init__(self, layout: FeatureLayout, device):
+        self.lib = _lib.load()
+        self.layout = layout
+        self.tables = [torch.nn.Parameter(torch.zeros((1, layout.H), device=device), requires_grad=False)
+                       for _ in layout.tables]
+        self.mm = {}
+        self.mode = "fused"
+        self.step = 0
+        self.exp_avg = [None] * len(self.tables)
+        self.exp_avg_sq = [None] * len(self.tables)
+        self.pending = []
+        self._ws = {}
+        self.launches = 0
+        self.check_ids = False
+        self._err = None
+        self.timing = None
+        from ._structs import StructCache
+        self._structs = StructCache(layout)
+        self.structs = self._structs
+        self._validated = True
+        self._dev = torch.device(device)
+
+    def _device(self):
+        return self._dev
+
+    def sorted_pairs(self, pbs: List[PackedBatch], dcats):
+        """(keys, srcs) device pointers of the stably sorted pairs of the calls' non-padding ids."""
+        calls = []
+        for i, pb in enumerate(pbs):
+            cl = self.layout.calls[pb.include_user]
+            if dcats is None:
+                # forward: no gradient buffers yet; the key builder never touches them
+                di = torch.empty((0, cl.item_dim), device=self._dev)
+                du = torch.empty((0, max(cl.user_dim, 1)), device=self._dev) if pb.include_user else None
+            else:
+                di, du = dcats[i]
+            calls.append((pb, di, du))
+        structs, keys, srcs, n, calls = self._sorted_pairs(calls)
+        return keys, srcs
+
+    def mm_backward_with(self, mm, pb, d_item):
+        self.mm = mm
+        return self.mm_backward(pb, d_item)
+
+
+# ----------------------------------------------------------------------------------------------------
+# per-rank state + generator orchestration
+# ----------------------------------------------------------------------------------------------------
+class ShardedRank:
+    """One rank of the row-sharded path. ``ops`` does the local compute (CudaShardOps in product)."""
+
+    def __init__(self, layout: FeatureLayout, ops, rank: int, W: int):
+        self.layout, self.ops, self.rank, self.W = layout, ops, rank, W
+        self.pending: list = []
+
+    # Each generator yields ("a2a_equal", tensor[W]) or ("a2a_v", tensor, send_splits, recv_splits) and is sent
+    # back the received tensor. Host split sizes come from ONE device->host read per exchange.
+    def forward_gen(self, pb: PackedBatch, out_dtype=torch.float32) -> Generator:
+        ops, W = self.ops, self.W
+        uniq, n_unique, cap = ops.unique_keys([pb])
+        rows_b, perm, counts = ops.route(uniq, n_unique, cap)
+        recv_counts_t = yield ("a2a_equal", counts)
+        both = torch.stack([counts, recv_counts_t]).cpu()          # the exchange's only host sync
+        send_counts, recv_counts = both[0].tolist(), both[1].tolist()
+        U, R = sum(send_counts), sum(recv_counts)
+        recv_rows = yield ("a2a_v", rows_b[:U], send_counts, recv_counts)
+        served = ops.gather(recv_rows, R)
+        back = yield ("a2a_v", served, recv_counts, send_counts)
+        rows_buf = torch.cat([torch.zeros((1, self.layout.H), dtype=back.dtype, device=back.device), back], dim=0)
+        self.last_fwd = {"U": U, "R": R, "send_counts": send_counts, "recv_counts": recv_counts}
+        return ops.forward_from_rows(pb, uniq, n_unique, perm, rows_buf, out_dtype)
+
+    def queue(self, pb, d_item, d_user):
+        self.pending.append((pb, d_item, d_user))
+
+    def step_gen(self, hyper: dict) -> Generator:
+        ops = self.ops
+        pend, self.pending = self.pending, []
+        H = self.layout.H
+        if pend:
+            uniq, n_unique, grads, cap = ops.reduce(pend)
+            rows_b, perm, counts = ops.route(uniq, n_unique, cap)
+            gb = ops.permute(grads, perm, n_unique, cap)
+        else:   # a rank without work still takes part in the collectives
+            dev = ops.local.device
+            counts = torch.zeros(self.W, dtype=torch.int32, device=dev)
+            rows_b = torch.zeros(1, dtype=torch.int32, device=dev)
+            gb = torch.zeros((1, H), device=dev)
+        recv_counts_t = yield ("a2a_equal", counts)
+        both = torch.stack([counts, recv_counts_t]).cpu()
+        send_counts, recv_counts = both[0].tolist(), both[1].tolist()
+        U, R = sum(send_counts), sum(recv_counts)
+        recv_rows = yield ("a2a_v", rows_b[:U], send_counts, recv_counts)
+        recv_grads = yield ("a2a_v", gb[:U], send_counts, recv_counts)
+        ops.apply(recv_rows, recv_grads, R, hyper)
+        self.last_step = {"U": U, "R": R, "send_counts": send_counts, "recv_counts": recv_counts}
+        return U
+
+
+def run_distributed(gen: Generator, group=None):
+    """Drive one rank's generator with torch.distributed collectives (NCCL on GPUs, gloo on CPU)."""
+    import torch.distributed as dist
+    try:
+        req = next(gen)
+        while True:
+            if req[0] == "a2a_equal":
+                out = torch.empty_like(req[1])
+                dist.all_to_all_single(out, req[1].contiguous(), group=group)
+            else:
+                _, t, ss, rs = req
+                t = t.contiguous()
+                out = torch.empty((sum(rs),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                dist.all_to_all_single(out, t, output_split_sizes=rs, input_split_sizes=ss, group=group)
+            req = gen.send(out)
+    except StopIteration as e:
+        return e.value
+
+
+def run_emulated(gens: List[Generator]):
+    """Drive W ranks' generators in lockstep inside one process, doing the all-to-alls by slicing."""
+    W = len(gens)
+    reqs = [next(g) for g in gens]
+    results = [None] * W
+    live = [True] * W
+    while any(live):
+        kind = reqs[0][0]
+        assert all(r[0] == kind for r in reqs), "ranks diverged"
+        outs = []
+        if kind == "a2a_equal":
+            for r in range(W):
+                outs.append(torch.stack([reqs[s][1][r] for s in range(W)]))
+        else:
+            for r in range(W):
+                parts = []
+                for s in range(W):
+                    _, t, ss, rs = reqs[s]
+                    o = sum(ss[:r])
+                    parts.append(t[o:o + ss[r]])
+                    assert ss[r] == reqs[r][3][s], "split sizes disagree"
+                outs.append(torch.cat(parts, dim=0))
+        for r in range(W):
+            try:
+                reqs[r] = gens[r].send(outs[r])
+            except StopIteration as e:
+                results[r] = e.value
+                live[r] = False
+        assert all(live) or not any(live), "ranks finished at different points"
+    return results
+
+
+# ----------------------------------------------------------------------------------------------------
+# nn.Module face of one rank
+# ----------------------------------------------------------------------------------------------------
+class ShardedGatherConcatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, pb, out_dtype, *params):
+        item_cat, user_cat = mod._run(mod.rank_state.forward_gen(pb, out_dtype))
+        ctx.mod, ctx.pb = mod, pb
+        ctx.n_params = len(params)
+        if user_cat is None:
+            user_cat = item_cat.new_empty(0)
+            ctx.mark_non_differentiable(user_cat)
+        return item_cat, user_cat
+
+    @staticmethod
+    def backward(ctx, d_item, d_user):
+        mod, pb = ctx.mod, ctx.pb
+        d_item = d_item.contiguous()
+        d_user = d_user.contiguous() if pb.include_user else None
+        mod.rank_state.queue(pb, d_item, d_user)
+        grads = [None] * ctx.n_params
+        names = list(mod.layout.item_emb_feat)
+        if names and any(ctx.needs_input_grad[3:]):
+            mg = mod.ops.mm_backward(pb, d_item)
+            for j, k in enumerate(names):
+                grads[2 * j], grads[2 * j + 1] = mg[k]
+        return (None, None, None, *grads)
+
+
+class ShardedBaselineEmbedding(torch.nn.Module):
+    """Row-sharded variant of ``BaselineEmbedding``: this rank's slice of the flat table lives in
+    ``local_table``; emb_transform / itemdnn / userdnn are replicated (their gradients are the caller's
+    to all-reduce, as in any data-parallel run). Row updates are always fused (``fused_step``)."""
+
+    def __init__(self, user_num, item_num, feat_statistics, feat_types, args, rank: int, world_size: int, group=None):
+        super().__init__()
+        H = args.hidden_units
+        lay = FeatureLayout(user_num, item_num, feat_statistics, feat_types, H)
+        self.layout = lay
+        self.rank, self.W, self.group = rank, world_size, group
+        self.dev = args.device
+        n_local = shard_rows(lay.total_rows, world_size)
+        self.local_table = torch.nn.Parameter(torch.zeros((n_local, H), device=args.device), requires_grad=False)
+        self.emb_transform = torch.nn.ModuleDict({k: torch.nn.Linear(d, H) for k, d in lay.item_emb_feat.items()})
+        self.userdnn = torch.nn.Linear(lay.user_dim, H)
+        self.itemdnn = torch.nn.Linear(lay.item_dim, H)
+        self.to(args.device)
+        self.ops = CudaShardOps(lay, self.local_table.data, dict(self.emb_transform.items()), world_size)
+        self.rank_state = ShardedRank(lay, self.ops, rank, world_size)
+        self._run = lambda gen: run_distributed(gen, self.group)
+
+    def load_full_tables(self, tables: Sequence[torch.Tensor]):
+        """Take this rank's slice out of full per-table tensors (layout order) — e.g. a reference checkpoint."""
+        with torch.no_grad():
+            self.local_table.copy_(shard_of_tables([t.to(self.local_table.device) for t in tables], self.rank, self.W))
+
+    def feat2emb_packed(self, pb: PackedBatch):
+        from .module import _concat_dtype
+        params = []
+        for k in self.layout.item_emb_feat:
+            params += [self.emb_transform[k].weight, self.emb_transform[k].bias]
+        item_cat, user_cat = ShardedGatherConcatFn.apply(self, pb, _concat_dtype(), *params)
+        B, L = pb.B, pb.L
+        out = torch.relu(self.itemdnn(item_cat.view(B, L, -1)))
+        if pb.include_user:
+            out = out + torch.relu(self.userdnn(user_cat.view(B, L, -1)))
+        return out
+
+    def fused_step(self, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
+        hyper = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale)
+        return self._run(self.rank_state.step_gen(hyper))
