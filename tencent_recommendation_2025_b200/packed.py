@@ -136,6 +136,68 @@ def count_valid(layout: FeatureLayout, pc: PackedCall) -> int:
     return n
 
 
+@dataclass
+class HostPacked:
+    """A packed call staged ONCE in pinned host memory (what a pin_memory DataLoader hands over):
+    ``upload`` is then nothing but 1 + n_mm async H2D copies."""
+
+    B: int
+    L: int
+    include_user: bool
+    ints: torch.Tensor                # pinned int32: [ids | arr_off | arr_val | arr_tok], each part 16 B aligned
+    offs: List[int]
+    sizes: List[int]
+    n_single: int
+    n_arr: int
+    arr_begin: List[int]
+    arr_nnz: List[int]
+    mm_x: List[torch.Tensor]          # pinned [T, mm_dim]
+    n_valid: int
+
+    @property
+    def T(self) -> int:
+        return self.B * self.L
+
+    @property
+    def nbytes(self) -> int:
+        return self.ints.numel() * 4 + sum(x.numel() * x.element_size() for x in self.mm_x)
+
+    def upload(self, device, non_blocking: bool = True) -> "PackedBatch":
+        dev = self.ints.to(device, non_blocking=non_blocking)
+        o, s, T = self.offs, self.sizes, self.T
+        ids = dev[o[0]:o[0] + s[0]].view(T, self.n_single)
+        arr_off = dev[o[1]:o[1] + s[1]].view(self.n_arr, T + 1)
+        mm = [x.to(device, non_blocking=non_blocking) for x in self.mm_x]
+        return PackedBatch(self.B, self.L, self.include_user, ids, arr_off, dev[o[2]:o[2] + s[2]], dev[o[3]:o[3] + s[3]],
+                           self.arr_begin, self.arr_nnz, mm, self.n_valid, self.nbytes)
+
+
+def stage_pinned(layout: FeatureLayout, pc: PackedCall, mm_dtype: torch.dtype = torch.float32) -> HostPacked:
+    pin = torch.cuda.is_available()
+    if pc.n_valid is None:
+        pc.n_valid = count_valid(layout, pc)
+    arr_tok = _arr_tok(pc)
+    n_arr = pc.arr_off.shape[0]
+    parts = [pc.ids.reshape(-1), pc.arr_off.reshape(-1), pc.arr_val, arr_tok]
+    sizes = [p.size for p in parts]
+    offs, tot = [], 0
+    for sz in sizes:
+        offs.append(tot)
+        tot += (sz + 3) // 4 * 4
+    ints = torch.empty(max(tot, 4), dtype=torch.int32, pin_memory=pin)
+    v = ints.numpy()
+    for p, o, sz in zip(parts, offs, sizes):
+        v[o:o + sz] = p
+    mm = []
+    for x in pc.mm_x:
+        t = torch.empty(x.shape, dtype=mm_dtype, pin_memory=pin)
+        t.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+        mm.append(t)
+    begins = [int(pc.arr_off[j, 0]) for j in range(n_arr)]
+    nnz = [int(pc.arr_off[j, -1] - pc.arr_off[j, 0]) for j in range(n_arr)]
+    return HostPacked(pc.B, pc.L, pc.include_user, ints, offs, sizes, pc.ids.shape[1], n_arr, begins, nnz, mm, pc.n_valid)
+
+
 class _PinnedPool:
     """Reusable pinned staging buffers. cudaHostAlloc costs milliseconds, so buffers are recycled; a buffer is
     handed out again only after the event recorded behind its last H2D copy has completed."""
