@@ -399,6 +399,7 @@ def main():
     ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches to cycle")
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="sharded path: per-call exchange instead of step prefetch")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks (debug)")
     ap.add_argument("--no-kernel-timing", action="store_true", help="no per-kernel CUDA events (debug)")
     ap.add_argument("--clock-period-ms", type=int, default=20)

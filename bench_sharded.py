@@ -52,6 +52,8 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
 
     def one_step(pbs, ups):
         dense_opt.zero_grad(set_to_none=True)
+        if not args.no_prefetch:
+            m.prefetch(pbs)                      # one dedup + one exchange for the step's three calls
         outs = [m.feat2emb_packed(pb) for pb in pbs]
         torch.autograd.backward(outs, ups)
         flat = torch.cat([p.grad.reshape(-1) for p in dense])      # replicated dense params: plain data-parallel all-reduce

@@ -182,6 +182,67 @@ class CudaShardOps:
             self.launches += 1
         return item_cat, user_cat
 
+    # -- step-level prefetch: one sort/dedup shared by the forward exchange and the backward reduction ----
+    def prepare(self, pbs: List[PackedBatch]):
+        """Sorted (key, src) pairs + dedup of ALL calls of a step; buffers are owned by the returned dict."""
+        dev = self.local.device
+        n = sum(pb.n_valid for pb in pbs)
+        keys, srcs = self._eng.sorted_pairs(pbs, None)
+        pairs = self._eng._ws.pop("pairs")          # keep this step's pairs alive until its backward
+        cap = max(n, 1)
+        uniq = torch.empty(cap, dtype=torch.int32, device=dev)
+        seg_off = torch.empty(cap + 1, dtype=torch.int32, device=dev)
+        seg_of = torch.empty(cap, dtype=torch.int32, device=dev)
+        n_unique = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = self._buf("dedup", self.lib.tgr_dedup_workspace_bytes(n), dev)
+        check(self.lib.tgr_dedup(keys, n, uniq.data_ptr(), seg_off.data_ptr(), seg_of.data_ptr(), n_unique.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), _stream()), "tgr_dedup")
+        self.launches += 12
+        return {"pairs": pairs, "keys": keys, "srcs": srcs, "n": n, "uniq": uniq, "seg_of": seg_of,
+                "n_unique": n_unique, "cap": cap}
+
+    def reduce_cached(self, pf, calls):
+        """Per-unique-key gradient rows from the step's cached sorted pairs (no second sort)."""
+        dev = self.local.device
+        H = self.layout.H
+        n = pf["n"]
+        structs = (Call * len(calls))()
+        for i, (pb, di, du) in enumerate(calls):
+            self._eng._call_struct(pb, di, du, out=structs[i])
+        grads = torch.empty((pf["cap"], H), dtype=torch.float32, device=dev)
+        if n:
+            rws = self._buf("reduce", self.lib.tgr_reduce_workspace_bytes(n, H), dev)
+            tabs = self._eng._table_array()
+            check(self.lib.tgr_bwd_reduce(tabs, len(self.layout.tables), H, structs, len(calls), pf["keys"], pf["srcs"], n, 0,
+                                          pf["seg_of"].data_ptr(), grads.data_ptr(), None, rws.data_ptr(), rws.numel(),
+                                          _stream()), "tgr_bwd_reduce")
+            self.launches += 2
+        return grads
+
+    def prepare_owner(self, recv_rows: torch.Tensor, R: int):
+        """Owner side, done during the forward: stable sort of the requested local rows (source-rank order kept)."""
+        if R == 0:
+            return None
+        if R > (1 << 24):
+            raise ValueError("more than 2^24 received contributions in one step")
+        dev = self.local.device
+        pos = torch.arange(R, dtype=torch.int32, device=dev)
+        keys_out = torch.empty(R, dtype=torch.int32, device=dev)
+        pos_out = torch.empty(R, dtype=torch.int32, device=dev)
+        ws = self._buf("sort", self.lib.tgr_sort_workspace_bytes(R), dev)
+        bits = max(1, int(self.local.shape[0] - 1).bit_length())
+        check(self.lib.tgr_sort_pairs(recv_rows.data_ptr(), pos.data_ptr(), keys_out.data_ptr(), pos_out.data_ptr(), R, bits,
+                                      ws.data_ptr(), ws.numel(), _stream()), "tgr_sort_pairs")
+        self.launches += 5
+        return keys_out, pos_out
+
+    def apply_cached(self, owner_state, recv_grads: torch.Tensor, R: int, hyper: dict):
+        self.step += 1
+        if R == 0:
+            return
+        keys_out, pos_out = owner_state
+        self._apply_sorted(keys_out, pos_out, recv_grads, R, hyper)
+
     # -- backward ------------------------------------------------------------------------------------
     def reduce(self, calls):
         """Per-unique-key gradient rows of the queued calls -> (uniq, n_unique, grads [cap, H], cap)."""
@@ -216,6 +277,12 @@ class CudaShardOps:
         bits = max(1, int(self.local.shape[0] - 1).bit_length())
         check(self.lib.tgr_sort_pairs(recv_rows.data_ptr(), pos.data_ptr(), keys_out.data_ptr(), pos_out.data_ptr(), R, bits,
                                       ws.data_ptr(), ws.numel(), _stream()), "tgr_sort_pairs")
+        self._apply_sorted(keys_out, pos_out, recv_grads, R, hyper)
+        self.launches += 5
+
+    def _apply_sorted(self, keys_out, pos_out, recv_grads, R, hyper):
+        dev = self.local.device
+        H = self.layout.H
         tab = (_lib.Table * 1)()
         tab[0].weight = self.local.data_ptr()
         tab[0].exp_avg = self.exp_avg.data_ptr()
@@ -235,7 +302,7 @@ class CudaShardOps:
         rws = self._buf("reduce", self.lib.tgr_reduce_workspace_bytes(R, H), dev)
         check(self.lib.tgr_bwd_reduce(tab, 1, H, C.byref(call), 1, keys_out.data_ptr(), pos_out.data_ptr(), R, 1, None, None,
                                       C.byref(adam), rws.data_ptr(), rws.numel(), _stream()), "tgr_bwd_reduce")
-        self.launches += 7
+        self.launches += 2
 
 
 class _KeyEngine(EmbeddingEngine):
@@ -299,8 +366,32 @@ class ShardedRank:
 
     # Each generator yields ("a2a_equal", tensor[W]) or ("a2a_v", tensor, send_splits, recv_splits) and is sent
     # back the received tensor. Host split sizes come from ONE device->host read per exchange.
+    def prefetch_gen(self, pbs: List[PackedBatch]) -> Generator:
+        """Step-level fast path: ONE sort/dedup and ONE exchange for all calls of the step. Later
+        ``forward_gen`` calls on these batches are local, and ``step_gen`` sends gradient rows only (the owner
+        already knows which rows each source asked for, in which order) — no ids, no counts, no host sync."""
+        ops = self.ops
+        pf = ops.prepare(list(pbs))
+        rows_b, perm, counts = ops.route(pf["uniq"], pf["n_unique"], pf["cap"])
+        recv_counts_t = yield ("a2a_equal", counts)
+        both = torch.stack([counts, recv_counts_t]).cpu()
+        send_counts, recv_counts = both[0].tolist(), both[1].tolist()
+        U, R = sum(send_counts), sum(recv_counts)
+        recv_rows = yield ("a2a_v", rows_b[:U], send_counts, recv_counts)
+        served = ops.gather(recv_rows, R)
+        owner_state = ops.prepare_owner(recv_rows, R)
+        back = yield ("a2a_v", served, recv_counts, send_counts)
+        rows_buf = torch.cat([torch.zeros((1, self.layout.H), dtype=back.dtype, device=back.device), back], dim=0)
+        self.pf = {"pbs": list(pbs), "pf": pf, "perm": perm, "rows_buf": rows_buf, "send_counts": send_counts,
+                   "recv_counts": recv_counts, "U": U, "R": R, "owner": owner_state}
+        self.last_fwd = {"U": U, "R": R, "send_counts": send_counts, "recv_counts": recv_counts}
+        return U
+
     def forward_gen(self, pb: PackedBatch, out_dtype=torch.float32) -> Generator:
         ops, W = self.ops, self.W
+        st = getattr(self, "pf", None)
+        if st is not None and any(pb is q for q in st["pbs"]):
+            return ops.forward_from_rows(pb, st["pf"]["uniq"], st["pf"]["n_unique"], st["perm"], st["rows_buf"], out_dtype)
         uniq, n_unique, cap = ops.unique_keys([pb])
         rows_b, perm, counts = ops.route(uniq, n_unique, cap)
         recv_counts_t = yield ("a2a_equal", counts)
@@ -321,6 +412,19 @@ class ShardedRank:
         ops = self.ops
         pend, self.pending = self.pending, []
         H = self.layout.H
+        st = getattr(self, "pf", None)
+        if st is not None:
+            self.pf = None
+            by_id = {id(pb): (pb, di, du) for pb, di, du in pend}
+            if len(by_id) != len(st["pbs"]) or any(id(pb) not in by_id for pb in st["pbs"]):
+                raise RuntimeError("fused_step after prefetch needs the gradient of every prefetched call")
+            calls = [by_id[id(pb)] for pb in st["pbs"]]            # source codes carry the prefetch call order
+            grads = ops.reduce_cached(st["pf"], calls)
+            gb = ops.permute(grads, st["perm"], st["pf"]["n_unique"], st["pf"]["cap"])
+            recv_grads = yield ("a2a_v", gb[:st["U"]], st["send_counts"], st["recv_counts"])
+            ops.apply_cached(st["owner"], recv_grads, st["R"], hyper)
+            self.last_step = {"U": st["U"], "R": st["R"], "send_counts": st["send_counts"], "recv_counts": st["recv_counts"]}
+            return st["U"]
         if pend:
             uniq, n_unique, grads, cap = ops.reduce(pend)
             rows_b, perm, counts = ops.route(uniq, n_unique, cap)
@@ -363,9 +467,16 @@ def run_distributed(gen: Generator, group=None):
 def run_emulated(gens: List[Generator]):
     """Drive W ranks' generators in lockstep inside one process, doing the all-to-alls by slicing."""
     W = len(gens)
-    reqs = [next(g) for g in gens]
     results = [None] * W
     live = [True] * W
+    reqs = [None] * W
+    for r, g in enumerate(gens):
+        try:
+            reqs[r] = next(g)
+        except StopIteration as e:          # purely local work (e.g. forward after a prefetch)
+            results[r] = e.value
+            live[r] = False
+    assert all(live) or not any(live), "ranks finished at different points"
     while any(live):
         kind = reqs[0][0]
         assert all(r[0] == kind for r in reqs), "ranks diverged"
@@ -459,6 +570,10 @@ class ShardedBaselineEmbedding(torch.nn.Module):
         if pb.include_user:
             out = out + torch.relu(self.userdnn(user_cat.view(B, L, -1)))
         return out
+
+    def prefetch(self, pbs: Sequence[PackedBatch]):
+        """Optional step-level fast path: exchange the unique rows of ALL the step's calls at once."""
+        return self._run(self.rank_state.prefetch_gen(list(pbs)))
 
     def fused_step(self, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
         hyper = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale)

@@ -114,3 +114,27 @@ class NumpyShardOps:
         w = self.local.numpy()
         onp.adamw_rows(w, self.m, self.v, uniq, red, self.step, lr=hyper["lr"], beta1=hyper["betas"][0],
                        beta2=hyper["betas"][1], eps=hyper["eps"], wd=hyper["weight_decay"])
+
+    # ---- step-level prefetch protocol (mirrors CudaShardOps.prepare / reduce_cached / prepare_owner / apply_cached)
+    def prepare(self, pbs):
+        pcs = [_pc(pb) for pb in pbs]
+        keys, srcs = onp.build_keys(self.layout, pcs)
+        uniq = np.unique(keys).astype(np.uint32)
+        cap = max(keys.size, 1)
+        out = np.zeros(cap, np.int32)
+        out[:uniq.size] = uniq.view(np.int32)
+        return {"pcs": pcs, "n": keys.size, "uniq": torch.from_numpy(out),
+                "n_unique": torch.tensor([uniq.size], dtype=torch.int32), "cap": cap}
+
+    def reduce_cached(self, pf, calls):
+        d = [(di.numpy(), None if du is None else du.numpy()) for _, di, du in calls]
+        uniq, rows = onp.segment_reduce_fp64(self.layout, pf["pcs"], d)
+        g = np.zeros((pf["cap"], self.layout.H), np.float32)
+        g[:uniq.size] = rows.astype(np.float32)
+        return torch.from_numpy(g)
+
+    def prepare_owner(self, recv_rows, R):
+        return recv_rows.clone()
+
+    def apply_cached(self, owner_state, recv_grads, R, hyper):
+        self.apply(owner_state, recv_grads, R, hyper)

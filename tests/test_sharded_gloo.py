@@ -55,11 +55,13 @@ def dcats(lay, st, seed):
     return out
 
 
-def rank_job(rank, W, lay, world, tables, mm, run):
+def rank_job(rank, W, lay, world, tables, mm, run, prefetch=False):
     ops = NumpyShardOps(lay, shard_of_tables(tables, rank, W), mm, W)
     rk = ShardedRank(lay, ops, rank, W)
     st = world.make_step(rank)
     pbs = [to_device(lay, pc, "cpu", pin=False) for pc in st.calls]
+    if prefetch:
+        run(rk.prefetch_gen(pbs))
     outs = [run(rk.forward_gen(pb)) for pb in pbs]
     facts = [dict(rk.last_fwd)]
     for pb, (di, du) in zip(pbs, dcats(lay, st, 50 + rank)):
@@ -69,24 +71,26 @@ def rank_job(rank, W, lay, world, tables, mm, run):
     return outs, ops.local, facts
 
 
-def _worker(rank, W, port, tmp):
+def _worker(rank, W, port, tmp, prefetch=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=W)
     torch.set_num_threads(1)
     cfg, world, lay, tables, mm = make_world()
-    outs, local, facts = rank_job(rank, W, lay, world, tables, mm, lambda g: run_distributed(g))
+    outs, local, facts = rank_job(rank, W, lay, world, tables, mm, lambda g: run_distributed(g), prefetch)
     torch.save({"outs": outs, "local": local, "facts": facts}, os.path.join(tmp, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_world_size_2_gloo_matches_single_rank():
+@pytest.mark.parametrize("prefetch", [False, True])
+def test_world_size_2_gloo_matches_single_rank(prefetch):
+    """prefetch=True: the step-level protocol (one exchange for all calls; backward sends gradient rows only)."""
     W = 2
-    port = 29500 + (os.getpid() % 400)
+    port = 29500 + (os.getpid() % 400) + (17 if prefetch else 0)
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(_worker, args=(W, port, tmp), nprocs=W, join=True)
+        mp.spawn(_worker, args=(W, port, tmp, prefetch), nprocs=W, join=True)
         res = [torch.load(os.path.join(tmp, f"r{r}.pt"), weights_only=False) for r in range(W)]
     cfg, world, lay, tables, mm = make_world()
     # single-rank reference: one rank owns everything and processes both data-parallel shares
@@ -116,6 +120,9 @@ def test_world_size_2_gloo_matches_single_rank():
         for r in range(W):
             assert res[r]["facts"][phase]["recv_counts"] == [res[s]["facts"][phase]["send_counts"][r] for s in range(W)]
             assert sum(res[r]["facts"][phase]["send_counts"]) == res[r]["facts"][phase]["U"]
+    if prefetch:   # the backward reuses the forward's routing verbatim
+        for r in range(W):
+            assert res[r]["facts"][0] == res[r]["facts"][1]
 
 
 def test_emulated_w4_equals_w1_numpy():
