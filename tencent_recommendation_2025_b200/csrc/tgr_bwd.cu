@@ -20,6 +20,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "tgr_common.cuh"
+#include "tgr_rows.cuh"
 
 namespace tgr {
 
@@ -196,280 +197,8 @@ __global__ void dedup_finish_kernel(int32_t* seg_off, const int32_t* n_unique_de
 }
 
 // =================================================================================================
-// reduce: fixed-tile segmented sum (+ fused AdamW)
-// =================================================================================================
-constexpr int kRedThreads = 256;
-constexpr int kC = 64;        // sorted entries per group tile
-constexpr int kRedUnroll = 4; // gradient rows in flight per thread
-
-struct RedParams {
-  const char* chunk_base[TGR_MAX_CALLS][TGR_MAX_SLOTS];  // d(concat) base of (call, slot), offset to the slot's column
-  int64_t ld_bytes[TGR_MAX_CALLS][TGR_MAX_SLOTS];
-  // tables (fused AdamW / key -> row)
-  float* w[TGR_MAX_TABLES];
-  float* m[TGR_MAX_TABLES];
-  float* v[TGR_MAX_TABLES];
-  uint32_t key_base[TGR_MAX_TABLES + 1];
-  int32_t n_tables;
-  const uint32_t* keys;
-  const uint32_t* srcs;
-  const int32_t* seg_of_entry;  // mode 0
-  float* grads_out;             // mode 0: [U, H]
-  float* cta_head;              // [n_cta, H]
-  float* cta_tail;              // [n_cta, H]
-  int64_t n;
-  int32_t H4;
-  int32_t mode;
-  tgr_adam_t adam;
-};
-
-__device__ __forceinline__ float adam_elem(float& w, float& m, float& v, float g, const tgr_adam_t& a) {
-  // torch/optim/adam.py _single_tensor_adam with decoupled weight decay, rounding for rounding as the CPU
-  // kernels evaluate it (probed against torch 2.11 CPU: lerp_ and addcmul_ fuse their last multiply-add):
-  //   param.mul_(1 - lr*wd)                                   w = w * decay
-  //   exp_avg.lerp_(grad, 1-beta1)                            m = fma(1-b1, g - m, m)
-  //   exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)    v = fma((1-b2)*g, g, v*b2)
-  //   denom = exp_avg_sq.sqrt() / bc2_sqrt + eps
-  //   param.addcdiv_(exp_avg, denom, value=-step_size)        w = w + (-step_size*m)/denom
-  w = __fmul_rn(w, a.decay);
-  m = __fmaf_rn(a.one_minus_beta1, __fsub_rn(g, m), m);
-  v = __fmaf_rn(__fmul_rn(a.one_minus_beta2, g), g, __fmul_rn(v, a.beta2));
-  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), a.bc2_sqrt), a.eps);
-  w = __fadd_rn(w, __fdiv_rn(__fmul_rn(-a.step_size, m), denom));
-  return w;
-}
-
-__device__ __forceinline__ void adam_row4(float4* wp, float4* mp, float4* vp, float4 g, const tgr_adam_t& a) {
-  float4 w = *wp, m = *mp, v = *vp;
-  g.x *= a.grad_scale; g.y *= a.grad_scale; g.z *= a.grad_scale; g.w *= a.grad_scale;
-  adam_elem(w.x, m.x, v.x, g.x, a);
-  adam_elem(w.y, m.y, v.y, g.y, a);
-  adam_elem(w.z, m.z, v.z, g.z, a);
-  adam_elem(w.w, m.w, v.w, g.w, a);
-  *wp = w; *mp = m; *vp = v;
-}
-
-__device__ __forceinline__ int find_table(const uint32_t* key_base, int n_tables, uint32_t key) {
-  int lo = 0, hi = n_tables;  // key_base[lo] <= key < key_base[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (key >= key_base[mid]) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
-// final value of one unique row: either AdamW in place, or store into the compact gradient buffer
-template <int LANES, int NJ>
-__device__ __forceinline__ void finish_row(const RedParams& p, uint32_t key, int64_t entry, const float4 (&acc)[NJ], int lane) {
-  const int H4 = p.H4;
-  if (p.mode == 1) {
-    const int t = find_table(p.key_base, p.n_tables, key);
-    const size_t row = (size_t)(key - p.key_base[t]) * (size_t)(H4 * 4);
-    float4* wp = reinterpret_cast<float4*>(p.w[t] + row);
-    float4* mp = reinterpret_cast<float4*>(p.m[t] + row);
-    float4* vp = reinterpret_cast<float4*>(p.v[t] + row);
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int c = lane + j * LANES;
-      if (c < H4) adam_row4(wp + c, mp + c, vp + c, acc[j], p.adam);
-    }
-  } else {
-    const int u = __ldg(p.seg_of_entry + entry);
-    float4* dst = reinterpret_cast<float4*>(p.grads_out + (size_t)u * (size_t)(H4 * 4));
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int c = lane + j * LANES;
-      if (c < H4) dst[c] = acc[j];
-    }
-  }
-}
-
-template <bool BF16>
-__device__ __forceinline__ float4 load_grad4(const RedParams& p, uint32_t src, int c) {
-  const int call = src >> TGR_SRC_CALL_SHIFT;
-  const int slot = (src >> TGR_SRC_SLOT_SHIFT) & 31;
-  const uint32_t tok = src & TGR_SRC_TOKEN_MASK;
-  const char* row = p.chunk_base[call][slot] + (size_t)tok * p.ld_bytes[call][slot];
-  if constexpr (BF16) return unpack_bf16x4(ld_stream_u2(reinterpret_cast<const uint2*>(row) + c));
-  else return ld_stream(reinterpret_cast<const float4*>(row) + c);
-}
-
-// One CTA = G groups x kC sorted entries. NJ = float4 columns per lane (1 for H <= 128).
-template <int LANES, int NJ, bool BF16>
-__global__ void __launch_bounds__(kRedThreads) reduce_tiles_kernel(const __grid_constant__ RedParams p) {
-  constexpr int G = kRedThreads / LANES;
-  constexpr int TILE = G * kC;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem_raw);            // [TILE + 2]  (index 0 = entry before the tile)
-  uint32_t* s_srcs = s_keys + TILE + 2;                                // [TILE]
-  float4* s_head = reinterpret_cast<float4*>(s_srcs + TILE + 2);       // [G][H4]   (16 B aligned: (2*TILE+4)*4 bytes)
-  float4* s_tail = s_head + G * p.H4;                                  // [G][H4]
-  int32_t* s_flag = reinterpret_cast<int32_t*>(s_tail + G * p.H4);     // [G] bit0 has_head, bit1 head_through, bit2 has_tail
-  uint32_t* s_tkey = reinterpret_cast<uint32_t*>(s_flag + G);          // [G] key of the tail run
-
-  const int tid = threadIdx.x, lane = tid % LANES, grp = tid / LANES;
-  const int H4 = p.H4;
-  const int64_t n = p.n;
-  const int64_t cta_a = (int64_t)blockIdx.x * TILE;
-  const int64_t cta_b = min(n, cta_a + TILE);
-  const int cnt_cta = (int)(cta_b - cta_a);
-
-  for (int i = tid; i < cnt_cta + 2; i += kRedThreads) {
-    const int64_t e = cta_a - 1 + i;
-    s_keys[i] = (e >= 0 && e < n) ? __ldg(p.keys + e) : 0xFFFFFFFFu;  // 0xFFFFFFFF never equals a real key
-  }
-  for (int i = tid; i < cnt_cta; i += kRedThreads) s_srcs[i] = __ldg(p.srcs + cta_a + i);
-  if (tid < G) s_flag[tid] = 0;
-  __syncthreads();
-
-  const int ga = grp * kC;                       // local range of this group
-  const int gb = min(cnt_cta, ga + kC);
-  if (ga < gb) {
-    float4 acc[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t cur = s_keys[ga + 1];
-    const bool from_prev = (s_keys[ga] == cur);
-    int run_start = ga;
-    for (int e0 = ga; e0 < gb; e0 += kRedUnroll) {
-      float4 g[kRedUnroll][NJ];
-#pragma unroll
-      for (int u = 0; u < kRedUnroll; ++u) {
-        if (e0 + u < gb) {
-          const uint32_t src = s_srcs[e0 + u];
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            const int c = lane + j * LANES;
-            if (c < H4) g[u][j] = load_grad4<BF16>(p, src, c);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kRedUnroll; ++u) {
-        const int e = e0 + u;
-        if (e < gb) {
-          const uint32_t k = s_keys[e + 1];
-          if (k != cur) {
-            // the run [run_start, e) ended inside this tile
-            if (run_start == ga && from_prev) {
-#pragma unroll
-              for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) s_head[grp * H4 + c] = acc[j]; }
-              if (lane == 0) s_flag[grp] |= 1;
-            } else {
-              finish_row<LANES, NJ>(p, cur, cta_a + run_start, acc, lane);
-            }
-            cur = k;
-            run_start = e;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = f4_add(acc[j], g[u][j]); }
-        }
-      }
-    }
-    // last run reaches the end of the group tile
-    const bool to_next = (s_keys[gb + 1] == cur);   // s_keys[cnt_cta + 1] is the entry after the CTA tile (or sentinel)
-    if (run_start == ga && from_prev) {
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) s_head[grp * H4 + c] = acc[j]; }
-      if (lane == 0) s_flag[grp] |= to_next ? 3 : 1;
-    } else if (to_next) {
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) s_tail[grp * H4 + c] = acc[j]; }
-      if (lane == 0) { s_flag[grp] |= 4; s_tkey[grp] = cur; }
-    } else {
-      finish_row<LANES, NJ>(p, cur, cta_a + run_start, acc, lane);
-    }
-  }
-  __syncthreads();
-
-  // ---- stitch runs that cross group tiles, in fixed order ----
-  const int g_active = (cnt_cta + kC - 1) / kC;
-  if (grp < g_active) {
-    const int fl = s_flag[grp];
-    if (grp == 0 && (fl & 1)) {
-      // run entering the CTA from the previous one: partial for the cross-CTA fix-up
-      float4 acc[NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = s_head[c]; }
-      if (fl & 2) {
-        for (int q = 1; q < g_active; ++q) {
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = f4_add(acc[j], s_head[q * H4 + c]); }
-          if (!(s_flag[q] & 2)) break;
-        }
-      }
-      float4* dst = reinterpret_cast<float4*>(p.cta_head + (size_t)blockIdx.x * (size_t)(H4 * 4));
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) dst[c] = acc[j]; }
-    }
-    if (fl & 4) {
-      float4 acc[NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = s_tail[grp * H4 + c]; }
-      bool open = true;  // run still continues past what has been summed
-      int q = grp + 1;
-      for (; q < g_active; ++q) {
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = f4_add(acc[j], s_head[q * H4 + c]); }
-        if (!(s_flag[q] & 2)) { open = false; break; }
-      }
-      if (open) {  // continues into the next CTA tile
-        float4* dst = reinterpret_cast<float4*>(p.cta_tail + (size_t)blockIdx.x * (size_t)(H4 * 4));
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) dst[c] = acc[j]; }
-      } else {
-        finish_row<LANES, NJ>(p, s_tkey[grp], cta_a + min(cnt_cta, (grp + 1) * kC) - 1, acc, lane);
-      }
-    }
-  }
-}
-
-// cross-CTA fix-up: one group per CTA tile; the tile that holds the START of a run leaving it owns the run
-template <int LANES, int NJ>
-__global__ void __launch_bounds__(kRedThreads) reduce_fixup_kernel(const __grid_constant__ RedParams p, int n_cta) {
-  constexpr int G = kRedThreads / LANES;
-  constexpr int64_t TILE = (int64_t)G * kC;
-  const int lane = threadIdx.x % LANES, grp = threadIdx.x / LANES;
-  const int c0 = blockIdx.x * G + grp;
-  if (c0 >= n_cta) return;
-  const int64_t n = p.n;
-  const int H4 = p.H4;
-  const int64_t a = (int64_t)c0 * TILE, b = min(n, a + TILE);
-  if (b >= n) return;
-  const uint32_t K = __ldg(p.keys + b - 1);
-  if (__ldg(p.keys + b) != K) return;                                        // nothing leaves this tile
-  if (a > 0 && __ldg(p.keys + a) == K && __ldg(p.keys + a - 1) == K) return;  // "through" tile: an earlier tile owns it
-  float4 acc[NJ];
-  const float4* src = reinterpret_cast<const float4*>(p.cta_tail + (size_t)c0 * (size_t)(H4 * 4));
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = src[c]; }
-  for (int t = c0 + 1; t < n_cta; ++t) {
-    const float4* hs = reinterpret_cast<const float4*>(p.cta_head + (size_t)t * (size_t)(H4 * 4));
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) { const int c = lane + j * LANES; if (c < H4) acc[j] = f4_add(acc[j], hs[c]); }
-    const int64_t te = min(n, (int64_t)(t + 1) * TILE);
-    const bool through = (__ldg(p.keys + te - 1) == K) && te < n && (__ldg(p.keys + te) == K);
-    if (!through) break;
-  }
-  finish_row<LANES, NJ>(p, K, b - 1, acc, lane);
-}
-
-// =================================================================================================
 // row-wise kernels over the compact unique list
 // =================================================================================================
-struct RowParams {
-  float* w[TGR_MAX_TABLES];
-  float* m[TGR_MAX_TABLES];
-  float* v[TGR_MAX_TABLES];
-  float* grad[TGR_MAX_TABLES];
-  uint32_t key_base[TGR_MAX_TABLES + 1];
-  int32_t n_tables;
-  int32_t H4;
-  tgr_adam_t adam;
-};
-
 template <int MODE>  // 0: adam, 1: scatter-add into dense grads
 __global__ void __launch_bounds__(256) rows_kernel(const __grid_constant__ RowParams p, const uint32_t* __restrict__ uniq,
                                                    const float* __restrict__ grads, const int32_t* __restrict__ n_dev) {
@@ -506,25 +235,6 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 }
 
 // ---- helpers -------------------------------------------------------------------------------------
-static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-
-static int fill_row_params(RowParams& rp, const tgr_table_t* tables, int n_tables, int H) {
-  TGR_REQUIRE(tables && n_tables > 0 && n_tables <= TGR_MAX_TABLES, "bad table array");
-  TGR_REQUIRE(H > 0 && H % 4 == 0, "bad H=%d", H);
-  rp.n_tables = n_tables;
-  rp.H4 = H / 4;
-  for (int t = 0; t < n_tables; ++t) {
-    rp.w[t] = tables[t].weight;
-    rp.m[t] = tables[t].exp_avg;
-    rp.v[t] = tables[t].exp_avg_sq;
-    rp.grad[t] = tables[t].grad;
-    rp.key_base[t] = (uint32_t)tables[t].key_base;
-    if (t) TGR_REQUIRE(tables[t].key_base == tables[t - 1].key_base + tables[t - 1].rows, "key bases must be cumulative");
-  }
-  rp.key_base[n_tables] = (uint32_t)(tables[n_tables - 1].key_base + tables[n_tables - 1].rows);
-  return 0;
-}
-
 }  // namespace tgr
 
 // =================================================================================================
@@ -658,100 +368,6 @@ extern "C" int tgr_dedup(const uint32_t* keys_sorted, int64_t n, uint32_t* uniq,
   flag_emit_kernel<<<nb, kScanBlock, 0, st>>>(f, n, block_cnt);
   dedup_finish_kernel<<<1, 1, 0, st>>>(seg_off, n_unique_dev, n);
   return check_launch("dedup");
-}
-
-namespace tgr {
-static int red_lanes(int H4) { return H4 <= 8 ? 8 : (H4 <= 16 ? 16 : 32); }
-static int red_tile(int H4) { return (kRedThreads / red_lanes(H4)) * kC; }
-}  // namespace tgr
-
-extern "C" size_t tgr_reduce_workspace_bytes(int64_t n, int H) {
-  const int H4 = H / 4;
-  const int64_t n_cta = (n + red_tile(H4) - 1) / red_tile(H4);
-  return 2 * align_up((size_t)(n_cta + 1) * H * sizeof(float));
-}
-
-template <int LANES, int NJ>
-static int launch_reduce(RedParams& p, bool bf16, int n_cta, cudaStream_t st) {
-  constexpr int G = kRedThreads / LANES;
-  constexpr int TILE = G * kC;
-  const size_t smem = (size_t)(2 * TILE + 4) * 4 + (size_t)2 * G * p.H4 * 16 + (size_t)2 * G * 4;
-  if (bf16) {
-    cudaFuncSetAttribute(reduce_tiles_kernel<LANES, NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    reduce_tiles_kernel<LANES, NJ, true><<<n_cta, kRedThreads, smem, st>>>(p);
-  } else {
-    cudaFuncSetAttribute(reduce_tiles_kernel<LANES, NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    reduce_tiles_kernel<LANES, NJ, false><<<n_cta, kRedThreads, smem, st>>>(p);
-  }
-  if (int rc = check_launch("reduce_tiles")) return rc;
-  if (n_cta > 1) {
-    reduce_fixup_kernel<LANES, NJ><<<(n_cta + G - 1) / G, kRedThreads, 0, st>>>(p, n_cta);
-    return check_launch("reduce_fixup");
-  }
-  return 0;
-}
-
-extern "C" int tgr_bwd_reduce(const tgr_table_t* tables, int n_tables, int H, const tgr_call_t* calls, int n_calls,
-                              const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n, int mode,
-                              const int32_t* seg_of_entry, float* grads_out, const tgr_adam_t* adam, void* workspace,
-                              size_t workspace_bytes, void* stream) {
-  TGR_REQUIRE(calls && n_calls > 0 && n_calls <= TGR_MAX_CALLS, "bad calls");
-  TGR_REQUIRE(H > 0 && H % 4 == 0 && H <= 512, "H=%d unsupported (multiple of 4, <= 512)", H);
-  TGR_REQUIRE(mode == 0 || mode == 1, "bad mode");
-  TGR_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
-  if (n == 0) return 0;
-  TGR_REQUIRE(keys_sorted && srcs_sorted && workspace, "null argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  RedParams p{};
-  RowParams rp{};
-  if (int rc = fill_row_params(rp, tables, n_tables, H)) return rc;
-  for (int t = 0; t < n_tables; ++t) { p.w[t] = rp.w[t]; p.m[t] = rp.m[t]; p.v[t] = rp.v[t]; }
-  for (int t = 0; t <= n_tables; ++t) p.key_base[t] = rp.key_base[t];
-  p.n_tables = n_tables;
-  const int dtype = calls[0].cat_dtype;
-  for (int c = 0; c < n_calls; ++c) {
-    const tgr_call_t& cl = calls[c];
-    TGR_REQUIRE(cl.cat_dtype == dtype, "all calls must share the concat-gradient dtype");
-    const size_t esz = dtype == TGR_DTYPE_BF16 ? 2 : 4;
-    for (int i = 0; i < cl.n_slots; ++i) {
-      const tgr_slot_t& s = cl.slots[i];
-      if (s.kind == TGR_KIND_MM) continue;
-      const char* base = (const char*)(s.side == TGR_SIDE_ITEM ? cl.item_cat : cl.user_cat);
-      const int64_t ld = s.side == TGR_SIDE_ITEM ? cl.item_ld : cl.user_ld;
-      TGR_REQUIRE(base != nullptr, "call %d slot %d: concat gradient is NULL", c, i);
-      TGR_REQUIRE(s.col % 4 == 0 && ld % 4 == 0, "call %d slot %d: col/ld not 128-bit tileable", c, i);
-      p.chunk_base[c][i] = base + (size_t)s.col * esz;
-      p.ld_bytes[c][i] = ld * (int64_t)esz;
-    }
-  }
-  if (mode == 1) {
-    TGR_REQUIRE(adam != nullptr, "adam is NULL");
-    for (int t = 0; t < n_tables; ++t) TGR_REQUIRE(p.w[t] && p.m[t] && p.v[t], "table %d: weight/exp_avg/exp_avg_sq NULL", t);
-    p.adam = *adam;
-  }
-  p.keys = keys_sorted;
-  p.srcs = srcs_sorted;
-  p.n = n;
-  p.H4 = H / 4;
-  p.mode = mode;
-  const int tile = red_tile(p.H4);
-  const int n_cta = (int)((n + tile - 1) / tile);
-  TGR_REQUIRE(workspace_bytes >= tgr_reduce_workspace_bytes(n, H), "workspace too small");
-  const size_t part = align_up((size_t)(n_cta + 1) * H * sizeof(float));
-  p.cta_head = (float*)workspace;
-  p.cta_tail = (float*)((char*)workspace + part);
-  if (mode == 0) {
-    TGR_REQUIRE(seg_of_entry && grads_out, "mode 0 needs seg_of_entry / grads_out");
-    p.seg_of_entry = seg_of_entry;
-    p.grads_out = grads_out;
-  }
-  const bool bf16 = dtype == TGR_DTYPE_BF16;
-  const int H4 = p.H4;
-  if (H4 <= 8) return launch_reduce<8, 1>(p, bf16, n_cta, st);
-  if (H4 <= 16) return launch_reduce<16, 1>(p, bf16, n_cta, st);
-  if (H4 <= 32) return launch_reduce<32, 1>(p, bf16, n_cta, st);
-  if (H4 <= 64) return launch_reduce<32, 2>(p, bf16, n_cta, st);
-  return launch_reduce<32, 4>(p, bf16, n_cta, st);
 }
 
 extern "C" int tgr_adam_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
