@@ -188,6 +188,12 @@ int tgr_route_bucket(const uint32_t* uniq, const int32_t* n_unique_dev, int64_t 
 int tgr_remap_ids(const int32_t* ids, int64_t n, int n_cols, const uint32_t* col_key_base, const int32_t* col_rows,
                   const uint32_t* uniq, const int32_t* n_unique_dev, const int32_t* perm, int32_t* out, void* stream);
 
+/* Same remap for all SINGLE slots of up to 4 calls at once, without searching: every sorted (key, src) entry
+ * knows its (call, slot, token), so ids_out[call][token, col(slot)] = 1 + perm[seg_of_entry[e]]. ids_out[] must be
+ * zero-filled by the caller (padding ids stay 0). ids_out is a HOST array of device pointers. */
+int tgr_remap_scatter(const uint32_t* srcs_sorted, const int32_t* seg_of_entry, int64_t n, const int32_t* perm,
+                      const tgr_call_t* calls, int n_calls, int32_t* const* ids_out, void* stream);
+
 /* out[perm[u], :] = in[u, :] for u < *n_dev (inverse = 0), or out[u, :] = in[perm[u], :] (inverse = 1). */
 int tgr_permute_rows(const float* in, int H, const int32_t* perm, const int32_t* n_dev, int64_t max_n, int inverse,
                      float* out, void* stream);

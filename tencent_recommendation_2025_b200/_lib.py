@@ -90,6 +90,8 @@ SIGNATURES = {
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "tgr_remap_ids": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, u32p, i32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    "tgr_remap_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Call), C.c_int,
+                                    C.POINTER(C.c_void_p), C.c_void_p]),
     "tgr_permute_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "tgr_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }

@@ -208,3 +208,46 @@ extern "C" int tgr_permute_rows(const float* in, int H, const int32_t* perm, con
   permute_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, H / 4, perm, n_dev, inverse, out);
   return check_launch("permute_rows");
 }
+
+// ---- remap by scatter: the sorted (key, src) pairs already know where every id lives -------------------------
+namespace tgr {
+struct ScatterParams {
+  int32_t* out[TGR_MAX_CALLS];
+  int32_t n_cols[TGR_MAX_CALLS];
+  int8_t col_of_slot[TGR_MAX_CALLS][TGR_MAX_SLOTS];  // ids column of a SINGLE slot, -1 otherwise
+};
+__global__ void __launch_bounds__(256) remap_scatter_kernel(const uint32_t* __restrict__ srcs,
+                                                            const int32_t* __restrict__ seg_of_entry, int64_t n,
+                                                            const int32_t* __restrict__ perm,
+                                                            const __grid_constant__ ScatterParams p) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t src = __ldg(srcs + e);
+    const int call = src >> TGR_SRC_CALL_SHIFT;
+    const int slot = (src >> TGR_SRC_SLOT_SHIFT) & 31;
+    const int col = p.col_of_slot[call][slot];
+    if (col < 0) continue;  // array values are remapped by tgr_remap_ids (a token may hold several)
+    const uint32_t tok = src & TGR_SRC_TOKEN_MASK;
+    p.out[call][(size_t)tok * p.n_cols[call] + col] = 1 + __ldg(perm + __ldg(seg_of_entry + e));
+  }
+}
+}  // namespace tgr
+
+extern "C" int tgr_remap_scatter(const uint32_t* srcs_sorted, const int32_t* seg_of_entry, int64_t n, const int32_t* perm,
+                                 const tgr_call_t* calls, int n_calls, int32_t* const* ids_out, void* stream) {
+  TGR_REQUIRE(n >= 0 && n_calls > 0 && n_calls <= TGR_MAX_CALLS, "bad n / n_calls");
+  if (n == 0) return 0;
+  TGR_REQUIRE(srcs_sorted && seg_of_entry && perm && calls && ids_out, "null argument");
+  ScatterParams p{};
+  for (int c = 0; c < n_calls; ++c) {
+    TGR_REQUIRE(ids_out[c] != nullptr, "ids_out[%d] is NULL", c);
+    p.out[c] = ids_out[c];
+    p.n_cols[c] = calls[c].n_single;
+    for (int i = 0; i < TGR_MAX_SLOTS; ++i) p.col_of_slot[c][i] = -1;
+    for (int i = 0; i < calls[c].n_slots; ++i)
+      if (calls[c].slots[i].kind == TGR_KIND_SINGLE) p.col_of_slot[c][i] = (int8_t)calls[c].slots[i].src;
+  }
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  remap_scatter_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(srcs_sorted, seg_of_entry, n, perm, p);
+  return check_launch("remap_scatter");
+}

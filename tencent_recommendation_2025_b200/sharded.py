@@ -125,13 +125,16 @@ class CudaShardOps:
             self.launches += 1
         return out
 
-    def forward_from_rows(self, pb: PackedBatch, uniq, n_unique, perm, rows_buf: torch.Tensor, out_dtype):
+    def forward_from_rows(self, pb: PackedBatch, uniq, n_unique, perm, rows_buf: torch.Tensor, out_dtype,
+                          remapped=None):
         """rows_buf [U+1, H] (row 0 zero) holds this call's unique rows in bucketed order; remap ids, then run
         the fused gather/pool/concat kernel on it as if it were one table."""
         lay = self.layout
         dev = rows_buf.device
         cl = lay.calls[pb.include_user]
         n_rows = rows_buf.shape[0]
+        if remapped is not None:
+            return self._fwd_remapped(pb, remapped[0], remapped[1], rows_buf, out_dtype)
         names = [s for s in cl.slots if s.kind == KIND_SINGLE]
         kb = (C.c_uint32 * _lib.MAX_SLOTS)()
         rw = (C.c_int32 * _lib.MAX_SLOTS)()
@@ -152,6 +155,13 @@ class CudaShardOps:
                                          n_unique.data_ptr(), perm.data_ptr(), arr_r.data_ptr() + off, _stream()),
                   "tgr_remap_ids(array)")
             self.launches += 1
+        return self._fwd_remapped(pb, ids_r, arr_r, rows_buf, out_dtype)
+
+    def _fwd_remapped(self, pb, ids_r, arr_r, rows_buf, out_dtype):
+        lay = self.layout
+        dev = rows_buf.device
+        cl = lay.calls[pb.include_user]
+        n_rows = rows_buf.shape[0]
         pb_r = PackedBatch(pb.B, pb.L, pb.include_user, ids_r, pb.arr_off, arr_r, pb.arr_tok, pb.arr_begin, pb.arr_nnz,
                            pb.mm_x, pb.n_valid)
         T = pb.T
@@ -199,7 +209,40 @@ class CudaShardOps:
                                  ws.data_ptr(), ws.numel(), _stream()), "tgr_dedup")
         self.launches += 12
         return {"pairs": pairs, "keys": keys, "srcs": srcs, "n": n, "uniq": uniq, "seg_of": seg_of,
-                "n_unique": n_unique, "cap": cap}
+                "n_unique": n_unique, "cap": cap, "pbs": list(pbs)}
+
+    def remap_all(self, pf, perm):
+        """ids of every prefetched call -> row numbers of the received buffer, by ONE scatter over the sorted
+        pairs (no search); the few array values go through the searching remap."""
+        lay = self.layout
+        pbs = pf["pbs"]
+        structs = (Call * len(pbs))()
+        outs = []
+        ptrs = (C.c_void_p * len(pbs))()
+        for i, pb in enumerate(pbs):
+            structs[i] = self._eng.structs._call_tmpl[pb.include_user]
+            o = torch.zeros_like(pb.ids)
+            outs.append(o)
+            ptrs[i] = o.data_ptr()
+        check(self.lib.tgr_remap_scatter(pf["srcs"], pf["seg_of"].data_ptr(), pf["n"], perm.data_ptr(), structs, len(pbs),
+                                         ptrs, _stream()), "tgr_remap_scatter")
+        self.launches += 1 + len(pbs)
+        arrs = []
+        for pb in pbs:
+            cl = lay.calls[pb.include_user]
+            arr_r = torch.empty_like(pb.arr_val)
+            for s in cl.slots:
+                if s.kind != KIND_ARRAY or pb.arr_nnz[s.src] == 0:
+                    continue
+                kb1 = (C.c_uint32 * 1)(lay.tables[s.table].key_base)
+                rw1 = (C.c_int32 * 1)(lay.tables[s.table].rows)
+                off = 4 * pb.arr_begin[s.src]
+                check(self.lib.tgr_remap_ids(pb.arr_val.data_ptr() + off, pb.arr_nnz[s.src], 1, kb1, rw1, pf["uniq"].data_ptr(),
+                                             pf["n_unique"].data_ptr(), perm.data_ptr(), arr_r.data_ptr() + off, _stream()),
+                      "tgr_remap_ids(array)")
+                self.launches += 1
+            arrs.append(arr_r)
+        pf["remapped"] = {id(pb): (o, a) for pb, o, a in zip(pbs, outs, arrs)}
 
     def reduce_cached(self, pf, calls):
         """Per-unique-key gradient rows from the step's cached sorted pairs (no second sort)."""
@@ -382,6 +425,8 @@ class ShardedRank:
         owner_state = ops.prepare_owner(recv_rows, R)
         back = yield ("a2a_v", served, recv_counts, send_counts)
         rows_buf = torch.cat([torch.zeros((1, self.layout.H), dtype=back.dtype, device=back.device), back], dim=0)
+        if hasattr(ops, "remap_all"):
+            ops.remap_all(pf, perm)
         self.pf = {"pbs": list(pbs), "pf": pf, "perm": perm, "rows_buf": rows_buf, "send_counts": send_counts,
                    "recv_counts": recv_counts, "U": U, "R": R, "owner": owner_state}
         self.last_fwd = {"U": U, "R": R, "send_counts": send_counts, "recv_counts": recv_counts}
@@ -391,6 +436,10 @@ class ShardedRank:
         ops, W = self.ops, self.W
         st = getattr(self, "pf", None)
         if st is not None and any(pb is q for q in st["pbs"]):
+            rm = st["pf"].get("remapped")
+            if rm is not None:
+                return ops.forward_from_rows(pb, st["pf"]["uniq"], st["pf"]["n_unique"], st["perm"], st["rows_buf"],
+                                             out_dtype, remapped=rm[id(pb)])
             return ops.forward_from_rows(pb, st["pf"]["uniq"], st["pf"]["n_unique"], st["perm"], st["rows_buf"], out_dtype)
         uniq, n_unique, cap = ops.unique_keys([pb])
         rows_b, perm, counts = ops.route(uniq, n_unique, cap)

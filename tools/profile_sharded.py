@@ -1,0 +1,49 @@
+"""torchrun --nproc-per-node N tools/profile_sharded.py : torch-profiler table of a sharded step on rank 0 (dev tool)."""
+import os, sys, time, types
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+import bench
+from tencent_recommendation_2025_b200 import synth
+from tencent_recommendation_2025_b200.packed import to_device
+from tencent_recommendation_2025_b200.sharded import ShardedBaselineEmbedding
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+dev = torch.device("cuda", lr); torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+torch.backends.cuda.matmul.allow_tf32 = True
+cfg = bench.get_config("c2", 1024); w = synth.SynthWorld(cfg, 0); lay = w.layout
+torch.manual_seed(0)
+m = ShardedBaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(),
+                             types.SimpleNamespace(device=str(dev), hidden_units=cfg.H), rank, world)
+with torch.no_grad():
+    m.local_table.normal_(0, 0.05)
+dense = [p for p in m.parameters() if p is not m.local_table]
+opt = torch.optim.AdamW(dense, lr=1e-3, betas=(0.9, 0.98))
+st = w.make_step(1000 * rank)
+pbs = [to_device(lay, pc, dev) for pc in st.calls]; ups = [torch.from_numpy(r).to(dev) for r in st.upstream]
+
+def step():
+    opt.zero_grad(set_to_none=True)
+    m.prefetch(pbs)
+    outs = [m.feat2emb_packed(pb) for pb in pbs]
+    torch.autograd.backward(outs, ups)
+    flat = torch.cat([p.grad.reshape(-1) for p in dense]); dist.all_reduce(flat); flat /= world
+    o = 0
+    for p in dense:
+        p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+    opt.step()
+    m.fused_step(lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
+
+for _ in range(4): step()
+torch.cuda.synchronize(); dist.barrier()
+t0 = time.perf_counter()
+for _ in range(10): step()
+torch.cuda.synchronize(); t1 = time.perf_counter()
+if rank == 0: print(f"wall {1e3*(t1-t0)/10:.3f} ms/step at W={world}")
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+if rank == 0:
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+dist.barrier(); dist.destroy_process_group()
