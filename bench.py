@@ -400,6 +400,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="sharded path: per-call exchange instead of step prefetch")
+    ap.add_argument("--no-lookahead", action="store_true", help="sharded path: no one-step-ahead key processing")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks (debug)")
     ap.add_argument("--no-kernel-timing", action="store_true", help="no per-kernel CUDA events (debug)")
     ap.add_argument("--clock-period-ms", type=int, default=20)

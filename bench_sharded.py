@@ -50,12 +50,14 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     lookups = [st.n_lookups() for st in steps_np]   # host-side row counting stays out of the timed regions
     flat_numel = sum(p.numel() for p in dense)
 
-    def one_step(pbs, ups):
+    def one_step(pbs, ups, next_pbs=None):
         dense_opt.zero_grad(set_to_none=True)
         if not args.no_prefetch:
             m.prefetch(pbs)                      # one dedup + one exchange for the step's three calls
         outs = [m.feat2emb_packed(pb) for pb in pbs]
         torch.autograd.backward(outs, ups)
+        if next_pbs is not None and not args.no_lookahead:
+            m.prepare_next(next_pbs)             # next step's key processing overlaps this step's tail
         flat = torch.cat([p.grad.reshape(-1) for p in dense])      # replicated dense params: plain data-parallel all-reduce
         dist.all_reduce(flat)
         flat /= world
@@ -65,6 +67,8 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
             o += p.numel()
         dense_opt.step()
         m.fused_step(**hyper)
+        if next_pbs is not None and not args.no_lookahead:
+            m.finish_prepare()
         return outs
 
     eng = m.ops._eng
@@ -72,7 +76,7 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     if clocks:
         clocks.start()
     for i in range(args.warmup):
-        one_step(*dev_steps[i % n_batches])
+        one_step(*dev_steps[i % n_batches], next_pbs=dev_steps[(i + 1) % n_batches][0])
     torch.cuda.synchronize()
     dist.barrier()
     eng.timing = {}
@@ -86,7 +90,7 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     rows = 0
     for i in range(args.steps):
         k = (args.warmup + i) % n_batches
-        one_step(*dev_steps[k])
+        one_step(*dev_steps[k], next_pbs=dev_steps[(k + 1) % n_batches][0])   # the data loader is one batch ahead
         rows += lookups[k]
     ev1.record()
     torch.cuda.synchronize()
@@ -111,14 +115,17 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     t_e2e = 0.0
     rows_e2e = 0
     h2d = 0
+    nxt = None
+    m.rank_state.prep = None
     for i in range(e2e_steps + 1):
         k = i % n_batches
         st = steps_np[k]
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
-        pbs = [hp.upload(dev) for hp in host_steps[k]]
-        outs = one_step(pbs, dev_steps[k][1])
+        pbs = nxt if nxt is not None else [hp.upload(dev) for hp in host_steps[k]]
+        nxt = [hp.upload(dev) for hp in host_steps[(k + 1) % n_batches]]     # next batch's H2D, also inside the timed region
+        outs = one_step(pbs, dev_steps[k][1], next_pbs=nxt)
         _ = float(sum(o.sum() for o in outs).item())
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0

@@ -409,28 +409,69 @@ class ShardedRank:
 
     # Each generator yields ("a2a_equal", tensor[W]) or ("a2a_v", tensor, send_splits, recv_splits) and is sent
     # back the received tensor. Host split sizes come from ONE device->host read per exchange.
-    def prefetch_gen(self, pbs: List[PackedBatch]) -> Generator:
-        """Step-level fast path: ONE sort/dedup and ONE exchange for all calls of the step. Later
-        ``forward_gen`` calls on these batches are local, and ``step_gen`` sends gradient rows only (the owner
-        already knows which rows each source asked for, in which order) — no ids, no counts, no host sync."""
+    # ---- step-level protocol, in three phases so that everything that does not depend on table VALUES can be
+    # issued one step ahead (software pipelining): only phase C sits on the step's critical path.
+    #   A  prepare_gen        : keys -> sort -> dedup -> route -> all-to-all of the per-owner counts; the split
+    #                           sizes travel to the host by an ASYNC pinned copy (no blocking sync)
+    #   B  finish_prepare_gen : (host sizes now known) all-to-all of the local-row ids, owner-side stable sort,
+    #                           id remap — still independent of table values
+    #   C  prefetch_gen       : owner gathers rows -> all-to-all rows back -> rows_buf
+    # The backward then sends gradient rows only (the owner already knows which rows each source asked for,
+    # in which order): no ids, no counts, no host sync.
+    @staticmethod
+    def _to_host_async(t: torch.Tensor):
+        if t.is_cuda:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return h, ev
+        return t.clone(), None
+
+    def prepare_gen(self, pbs: List[PackedBatch]) -> Generator:
         ops = self.ops
         pf = ops.prepare(list(pbs))
         rows_b, perm, counts = ops.route(pf["uniq"], pf["n_unique"], pf["cap"])
         recv_counts_t = yield ("a2a_equal", counts)
-        both = torch.stack([counts, recv_counts_t]).cpu()
-        send_counts, recv_counts = both[0].tolist(), both[1].tolist()
+        host = self._to_host_async(torch.stack([counts, recv_counts_t]))
+        self.prep = {"pbs": list(pbs), "pf": pf, "rows_b": rows_b, "perm": perm, "host": host, "stage": 1}
+        return None
+
+    def finish_prepare_gen(self) -> Generator:
+        ops = self.ops
+        p = self.prep
+        if p is None or p["stage"] != 1:
+            raise RuntimeError("finish_prepare without a pending prepare")
+        h, ev = p["host"]
+        if ev is not None:
+            ev.synchronize()          # normally long complete: the copy was issued a phase earlier
+        send_counts, recv_counts = h[0].tolist(), h[1].tolist()
         U, R = sum(send_counts), sum(recv_counts)
-        recv_rows = yield ("a2a_v", rows_b[:U], send_counts, recv_counts)
-        served = ops.gather(recv_rows, R)
+        recv_rows = yield ("a2a_v", p["rows_b"][:U], send_counts, recv_counts)
         owner_state = ops.prepare_owner(recv_rows, R)
-        back = yield ("a2a_v", served, recv_counts, send_counts)
-        rows_buf = torch.cat([torch.zeros((1, self.layout.H), dtype=back.dtype, device=back.device), back], dim=0)
         if hasattr(ops, "remap_all"):
-            ops.remap_all(pf, perm)
-        self.pf = {"pbs": list(pbs), "pf": pf, "perm": perm, "rows_buf": rows_buf, "send_counts": send_counts,
-                   "recv_counts": recv_counts, "U": U, "R": R, "owner": owner_state}
-        self.last_fwd = {"U": U, "R": R, "send_counts": send_counts, "recv_counts": recv_counts}
-        return U
+            ops.remap_all(p["pf"], p["perm"])
+        p.update(send_counts=send_counts, recv_counts=recv_counts, U=U, R=R, recv_rows=recv_rows, owner=owner_state, stage=2)
+        return None
+
+    def prefetch_gen(self, pbs: List[PackedBatch]) -> Generator:
+        """Fetch the unique rows of ALL calls of the step with one exchange. Uses the state prepared ahead by
+        prepare_gen/finish_prepare_gen when it is for these very batches, else runs those phases inline."""
+        ops = self.ops
+        p = getattr(self, "prep", None)
+        if p is None or len(p["pbs"]) != len(pbs) or any(a is not b for a, b in zip(p["pbs"], pbs)):
+            yield from self.prepare_gen(pbs)
+            p = self.prep
+        if p["stage"] == 1:
+            yield from self.finish_prepare_gen()
+        self.prep = None
+        served = ops.gather(p["recv_rows"], p["R"])
+        back = yield ("a2a_v", served, p["recv_counts"], p["send_counts"])
+        rows_buf = torch.cat([torch.zeros((1, self.layout.H), dtype=back.dtype, device=back.device), back], dim=0)
+        self.pf = {"pbs": list(pbs), "pf": p["pf"], "perm": p["perm"], "rows_buf": rows_buf, "send_counts": p["send_counts"],
+                   "recv_counts": p["recv_counts"], "U": p["U"], "R": p["R"], "owner": p["owner"]}
+        self.last_fwd = {"U": p["U"], "R": p["R"], "send_counts": p["send_counts"], "recv_counts": p["recv_counts"]}
+        return p["U"]
 
     def forward_gen(self, pb: PackedBatch, out_dtype=torch.float32) -> Generator:
         ops, W = self.ops, self.W
@@ -623,6 +664,14 @@ class ShardedBaselineEmbedding(torch.nn.Module):
     def prefetch(self, pbs: Sequence[PackedBatch]):
         """Optional step-level fast path: exchange the unique rows of ALL the step's calls at once."""
         return self._run(self.rank_state.prefetch_gen(list(pbs)))
+
+    def prepare_next(self, pbs: Sequence[PackedBatch]):
+        """Look-ahead: start the key processing of the NEXT step's batches (independent of table values) so it
+        overlaps this step; call ``finish_prepare`` later in the step, ``prefetch`` at the start of the next."""
+        return self._run(self.rank_state.prepare_gen(list(pbs)))
+
+    def finish_prepare(self):
+        return self._run(self.rank_state.finish_prepare_gen())
 
     def fused_step(self, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
         hyper = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale)

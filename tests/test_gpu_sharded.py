@@ -146,6 +146,9 @@ def test_prefetch_protocol_equals_per_call_protocol(W):
     for prefetch in (False, True):
         cfg, full, lay, ranks, steps, pbs = setup(W)
         if prefetch:
+            if W == 2:   # look-ahead form: phases issued separately
+                run_emulated([ranks[r].prepare_gen(pbs[r]) for r in range(W)])
+                run_emulated([ranks[r].finish_prepare_gen() for r in range(W)])
             run_emulated([ranks[r].prefetch_gen(pbs[r]) for r in range(W)])
         fwd = []
         for c in range(3):

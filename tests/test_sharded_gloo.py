@@ -61,6 +61,9 @@ def rank_job(rank, W, lay, world, tables, mm, run, prefetch=False):
     st = world.make_step(rank)
     pbs = [to_device(lay, pc, "cpu", pin=False) for pc in st.calls]
     if prefetch:
+        # look-ahead form: phases A and B issued separately (as one step ahead), then phase C
+        run(rk.prepare_gen(pbs))
+        run(rk.finish_prepare_gen())
         run(rk.prefetch_gen(pbs))
     outs = [run(rk.forward_gen(pb)) for pb in pbs]
     facts = [dict(rk.last_fwd)]

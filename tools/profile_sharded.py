@@ -40,6 +40,33 @@ t0 = time.perf_counter()
 for _ in range(10): step()
 torch.cuda.synchronize(); t1 = time.perf_counter()
 if rank == 0: print(f"wall {1e3*(t1-t0)/10:.3f} ms/step at W={world}")
+# phase timing with CUDA events (GPU time between phase boundaries on the compute stream) and host time
+names = ["prefetch", "fwd x3", "backward", "dense allreduce+opt", "fused_step"]
+acc = {k: [0.0, 0.0] for k in names}
+def phase(name, f):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t = time.perf_counter(); e0.record(); r = f(); e1.record(); acc[name][1] += time.perf_counter() - t
+    evs.append((name, e0, e1)); return r
+def dense_sync():
+    flat = torch.cat([p.grad.reshape(-1) for p in dense]); dist.all_reduce(flat); flat /= world
+    o = 0
+    for p in dense:
+        p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+    opt.step()
+evs = []
+N = 10
+torch.cuda.synchronize(); dist.barrier()
+for _ in range(N):
+    opt.zero_grad(set_to_none=True)
+    phase("prefetch", lambda: m.prefetch(pbs))
+    outs = phase("fwd x3", lambda: [m.feat2emb_packed(pb) for pb in pbs])
+    phase("backward", lambda: torch.autograd.backward(outs, ups))
+    phase("dense allreduce+opt", dense_sync)
+    phase("fused_step", lambda: m.fused_step(lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2))
+torch.cuda.synchronize()
+for name, e0, e1 in evs: acc[name][0] += e0.elapsed_time(e1)
+if rank == 0:
+    for k in names: print(f"  {k:22s} gpu {acc[k][0]/N:.3f} ms   host {1e3*acc[k][1]/N:.3f} ms")
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3): step()
