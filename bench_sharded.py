@@ -48,23 +48,24 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
                  for st in steps_np]
     hyper = dict(lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
     lookups = [st.n_lookups() for st in steps_np]   # host-side row counting stays out of the timed regions
-    flat_numel = sum(p.numel() for p in dense)
+    # replicated dense parameters: their .grad tensors are views of ONE flat buffer, so the data-parallel
+    # all-reduce is a single collective with no flatten / copy-back kernels
+    flat_grad = torch.zeros(sum(p.numel() for p in dense), device=dev)
+    o = 0
+    for p in dense:
+        p.grad = flat_grad[o:o + p.numel()].view_as(p)
+        o += p.numel()
 
     def one_step(pbs, ups, next_pbs=None):
-        dense_opt.zero_grad(set_to_none=True)
+        flat_grad.zero_()
         if not args.no_prefetch:
             m.prefetch(pbs)                      # one dedup + one exchange for the step's three calls
         outs = [m.feat2emb_packed(pb) for pb in pbs]
         torch.autograd.backward(outs, ups)
         if next_pbs is not None and not args.no_lookahead:
             m.prepare_next(next_pbs)             # next step's key processing overlaps this step's tail
-        flat = torch.cat([p.grad.reshape(-1) for p in dense])      # replicated dense params: plain data-parallel all-reduce
-        dist.all_reduce(flat)
-        flat /= world
-        o = 0
-        for p in dense:
-            p.grad.copy_(flat[o:o + p.numel()].view_as(p))
-            o += p.numel()
+        dist.all_reduce(flat_grad)
+        flat_grad.div_(world)
         dense_opt.step()
         m.fused_step(**hyper)
         if next_pbs is not None and not args.no_lookahead:

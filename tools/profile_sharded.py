@@ -22,17 +22,22 @@ opt = torch.optim.AdamW(dense, lr=1e-3, betas=(0.9, 0.98))
 st = w.make_step(1000 * rank)
 pbs = [to_device(lay, pc, dev) for pc in st.calls]; ups = [torch.from_numpy(r).to(dev) for r in st.upstream]
 
+flat_grad = torch.zeros(sum(p.numel() for p in dense), device=dev)
+o = 0
+for p in dense:
+    p.grad = flat_grad[o:o + p.numel()].view_as(p); o += p.numel()
+LOOK = os.environ.get("LOOKAHEAD", "1") == "1"
+
 def step():
-    opt.zero_grad(set_to_none=True)
+    flat_grad.zero_()
     m.prefetch(pbs)
     outs = [m.feat2emb_packed(pb) for pb in pbs]
     torch.autograd.backward(outs, ups)
-    flat = torch.cat([p.grad.reshape(-1) for p in dense]); dist.all_reduce(flat); flat /= world
-    o = 0
-    for p in dense:
-        p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+    if LOOK: m.prepare_next(pbs)
+    dist.all_reduce(flat_grad); flat_grad.div_(world)
     opt.step()
     m.fused_step(lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
+    if LOOK: m.finish_prepare()
 
 for _ in range(4): step()
 torch.cuda.synchronize(); dist.barrier()
@@ -72,5 +77,6 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
 if rank == 0:
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+    prof.export_chrome_trace("gpurun_out/trace_sharded_r0.json")
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
 dist.barrier(); dist.destroy_process_group()
