@@ -131,11 +131,11 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def init_module(cfg: synth.SynthConfig, device, mode="fused"):
+def init_module(cfg: synth.SynthConfig, device, mode="fused", path="concat"):
     from tencent_recommendation_2025_b200.module import BaselineEmbedding
     args = types.SimpleNamespace(device=str(device), hidden_units=cfg.H)
     with torch.device(device):
-        m = BaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), args, mode=mode)
+        m = BaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), args, mode=mode, path=path)
     g = torch.Generator(device=device).manual_seed(0)
     with torch.no_grad():
         for p in m.parameters():
@@ -195,7 +195,7 @@ def run_gpu(args):
     cfg = get_config(args.config, args.batch)
     worldgen = synth.SynthWorld(cfg, 0)
     lay = worldgen.layout
-    m = init_module(cfg, dev, "fused")
+    m = init_module(cfg, dev, "fused", args.path)
     dense_opt = torch.optim.AdamW(m.dense_parameters(), lr=1e-3, betas=(0.9, 0.98))
     eng = m.engine
     n_batches = max(1, min(args.batches, args.steps + args.warmup))
@@ -211,6 +211,7 @@ def run_gpu(args):
 
     def one_step(pbs, ups):
         dense_opt.zero_grad(set_to_none=True)
+        m.prefetch(pbs)                          # factored path: one key sort / row projection per step
         outs = [m.feat2emb_packed(pb) for pb in pbs]
         torch.autograd.backward(outs, ups)
         dense_opt.step()
@@ -395,6 +396,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--path", default="concat", choices=["concat", "factored"],
+                    help="concat: gather/pool/concat kernels + torch itemdnn/userdnn; factored: DNN folded into unique rows")
     ap.add_argument("--batch", type=int, default=1024, help="sequences per GPU")
     ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches to cycle")
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU baseline sample")

@@ -187,6 +187,7 @@ int tgr_route_bucket(const uint32_t* uniq, const int32_t* n_unique_dev, int64_t 
  * gather kernel runs on it. col_key_base / col_rows are HOST arrays [n_cols]. */
 int tgr_remap_ids(const int32_t* ids, int64_t n, int n_cols, const uint32_t* col_key_base, const int32_t* col_rows,
                   const uint32_t* uniq, const int32_t* n_unique_dev, const int32_t* perm, int32_t* out, void* stream);
+/* (perm == NULL means the identity in tgr_remap_ids / tgr_remap_scatter.) */
 
 /* Same remap for all SINGLE slots of up to 4 calls at once, without searching: every sorted (key, src) entry
  * knows its (call, slot, token), so ids_out[call][token, col(slot)] = 1 + perm[seg_of_entry[e]]. ids_out[] must be
@@ -201,6 +202,58 @@ int tgr_permute_rows(const float* in, int H, const int32_t* perm, const int32_t*
 /* Gather rows of a flat table by local row index: out[i, :] = table[rows[i], :] for i < *n_dev. */
 int tgr_gather_rows(const float* table, int H, const uint32_t* rows, const int32_t* n_dev, int64_t max_n, float* out,
                     void* stream);
+
+/* ---- factored path: the item/user DNN applied to DEDUPLICATED rows -----------------
+ * model.py:302-307 computes out = relu(itemdnn(cat(item slots))) + relu(userdnn(cat(user slots))); a Linear over
+ * a concat is a sum of per-slot H x H blocks applied to the slot's row, and every table feeds exactly one slot
+ * (model.py:244-245,252-263), so the block product is formed ONCE per unique row of the step and the concat
+ * buffers, their gradients and the [T, 1024] GEMMs never exist. Pipeline (keys/sort/dedup shared with the backward):
+ *   build_keys -> sort_pairs -> dedup -> remap_scatter/remap_ids (ids -> 1 + unique index)
+ *   fact_project_rows -> [fact_mm_fold, mm_proj_fwd] -> fact_forward                      (forward)
+ *   fact_relu_mask -> bwd_reduce(mode 0 on dZ) -> fact_unique_backward [-> mm_proj_bwd, fact_mm_chain_bwd]
+ *   -> adam_rows | scatter_rows                                                            (backward + update)
+ * Supported H: 32, 64, 128. All fp32; every reduction order is fixed by the sorted unique list. */
+typedef struct tgr_dnn {
+  const float* w_item; /* itemdnn.weight [H, item_ld] (model.py:151) */
+  const float* w_user; /* userdnn.weight [H, user_ld] (model.py:150) or NULL */
+  int64_t item_ld, user_ld;
+  int32_t table_side[TGR_MAX_TABLES]; /* TGR_SIDE_* of the one slot table t feeds */
+  int32_t table_col[TGR_MAX_TABLES];  /* first DNN-input column of that slot */
+} tgr_dnn_t;
+
+/* P[u, :] = W_side[:, col : col+H] . row(uniq[u]) for u < *n_unique_dev (uniq sorted ascending). */
+int tgr_fact_project_rows(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn, const uint32_t* uniq,
+                          const int32_t* n_unique_dev, int64_t max_unique, float* P, void* stream);
+
+/* One feat2emb call from the projected rows: out[t] = relu(b_item + sum P[ids_u[t, item slots]-1] + sum_f mmz[f][t])
+ * + relu(b_user + sum P[ids_u[t, user slots]-1]); arrays via call->arr_off and arr_u (remapped arr_val). ids 0 add
+ * nothing. mask[t, H/4]: bit j / 4+j = z_item / z_user element 4c+j > 0 (the ReLU masks of model.py:303,306). */
+int tgr_fact_forward(const tgr_call_t* call, int H, const int32_t* ids_u, const int32_t* arr_u, const float* P,
+                     const float* const* mmz, int n_mm, const float* bias_item, const float* bias_user, float* out,
+                     uint8_t* mask, void* stream);
+
+/* dz_item = d_out * mask_item, dz_user = d_out * mask_user (NULL without users); db_* += column sums
+ * (autograd of relu + the Linear bias, model.py:303-307). */
+size_t tgr_fact_relu_mask_workspace_bytes(int64_t T, int H);
+int tgr_fact_relu_mask(const float* d_out, const uint8_t* mask, int64_t T, int H, float* dz_item, float* dz_user,
+                       float* db_item, float* db_user, void* workspace, size_t workspace_bytes, void* stream);
+
+/* G[u, :] (sum of dz over the row's lookups, from tgr_bwd_reduce mode 0) -> row gradient G[u] . W[:, cols] in place;
+ * dW_item / dW_user [H, ld] += sum_u G[u]^T (x) row[u] in the slot's columns (autograd of the Linear weight). */
+size_t tgr_fact_backward_workspace_bytes(int n_tables, int H);
+int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn, const uint32_t* uniq,
+                             const int32_t* n_unique_dev, int64_t max_unique, float* G, float* dW_item, float* dW_user,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* mm feature folded through its item-DNN block: M = W_slot . W_mm [H, mm_dim], c = W_slot . b_mm [H]
+ * (emb_transform then itemdnn, model.py:297-303); x . M^T + c is then produced by tgr_mm_proj_fwd. */
+int tgr_fact_mm_fold(const float* w_slot, int64_t ld, const float* w_mm, const float* b_mm, int H, int mm_dim, float* M,
+                     float* c, void* stream);
+/* Chain rule back from A = dz^T x [H, mm_dim], s = colsum(dz) [H] (tgr_mm_proj_bwd):
+ * dW_mm += W_slot^T A ; db_mm += W_slot^T s ; dW_slot += A W_mm^T + s b_mm^T. */
+int tgr_fact_mm_chain_bwd(const float* w_slot, int64_t ld, const float* w_mm, const float* b_mm, const float* A,
+                          const float* s, int H, int mm_dim, float* dW_mm, float* db_mm, float* dW_slot, int64_t dld,
+                          void* stream);
 
 #ifdef __cplusplus
 }

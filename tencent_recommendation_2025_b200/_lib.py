@@ -41,6 +41,11 @@ class Call(C.Structure):
                 ("err_flag", C.c_void_p)]
 
 
+class Dnn(C.Structure):
+    _fields_ = [("w_item", C.c_void_p), ("w_user", C.c_void_p), ("item_ld", C.c_int64), ("user_ld", C.c_int64),
+                ("table_side", C.c_int32 * MAX_TABLES), ("table_col", C.c_int32 * MAX_TABLES)]
+
+
 class Adam(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float), ("step_size", C.c_float), ("bc2_sqrt", C.c_float),
@@ -94,6 +99,21 @@ SIGNATURES = {
                                     C.POINTER(C.c_void_p), C.c_void_p]),
     "tgr_permute_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "tgr_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tgr_fact_project_rows": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Dnn), C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_void_p]),
+    "tgr_fact_forward": (C.c_int, [C.POINTER(Call), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tgr_fact_relu_mask_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "tgr_fact_relu_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tgr_fact_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "tgr_fact_unique_backward": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Dnn), C.c_void_p, C.c_void_p,
+                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                           C.c_void_p]),
+    "tgr_fact_mm_fold": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "tgr_fact_mm_chain_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -1,0 +1,602 @@
+// Factored feat2emb: the item/user DNN is applied to DEDUPLICATED table rows, so the [T,1024]/[T,576] concat
+// buffers, their gradients and the [T,1024]x[1024,64] GEMMs (forward, dX, dW) never exist.
+//
+// Reference (model/BaseLine/model.py:302-307):  out = relu(itemdnn(cat(item slots))) + relu(userdnn(cat(user slots)))
+// and  itemdnn(cat(...)) = b + sum_slots W[:, cols(slot)] . row_slot(id)  — linear in every gathered row. A training
+// step looks up ~2.8 M rows but only ~0.23 M DISTINCT ones (Zipf ids, small-vocabulary features; each table feeds
+// exactly one slot, model.py:244-245,252-263), hence:
+//
+//   project_rows     P[u]      = W[:, cols(table(u))] . row[u]             once per unique row (fp32 FFMA tile GEMM)
+//   forward          z_side[t] = b_side + sum_slots P[idx(t, slot)] (+ folded mm projections);
+//                    out       = relu(z_item) + relu(z_user);  mask = sign bits for the backward
+//                                                                           gather-sum of 256 B rows that live in L2
+//   relu_mask        dZ_side   = dOut * mask_side ; db_side = column sums   (fixed-order partials)
+//   (tgr_bwd_reduce) G[u]      = sum over the row's lookups of dZ_side[token]  (mode 0 on the dZ buffers, ld = H)
+//   unique_backward  g_row[u]  = G[u] . W[:, cols]      -> AdamW row update / dense scatter
+//                    dW[:, cols] += sum_u G[u]^T (x) row[u]                  split-K partials, reduced in fixed order
+//   mm features      z_item   += x . (W_s Wmm)^T + W_s bmm   with the folded [H, mm_dim] matrix (mm_fold);
+//                    dWmm, dbmm, dW_s from A = dZ^T x, s = colsum(dZ)        (mm_chain_bwd)
+//
+// Sums are re-associated (per-slot H-term dot products, then a <= 25-term sum) — fp32 throughout, inside the 1e-5
+// parity bar. Every reduction order is a function of the sorted unique-key list and the launch geometry only.
+// This is SURVEY.md §8(f) N4 obtained through deduplication instead of a gather-prologue GEMM.
+#include "tgr_common.cuh"
+#include "tgr_rows.cuh"
+
+namespace tgr {
+
+constexpr int kFT = 256;          // threads per CTA
+constexpr int kRT = 64;           // unique rows per tile
+constexpr int kRowsGrid = 2 * kNumSMs;
+
+struct FactParams {
+  const float* w[TGR_MAX_TABLES];       // table rows
+  uint32_t key_base[TGR_MAX_TABLES + 1];
+  int32_t col[TGR_MAX_TABLES];          // first DNN-input column of the table's slot
+  int8_t side[TGR_MAX_TABLES];          // which DNN the table's slot feeds
+  const float* dnn_w[2];                // itemdnn.weight [H, item_dim], userdnn.weight [H, user_dim]
+  int64_t dnn_ld[2];
+  int32_t n_tables;
+};
+
+__device__ __forceinline__ void fma4(float4& a, float x, const float4& w) {
+  a.x = fmaf(x, w.x, a.x); a.y = fmaf(x, w.y, a.y); a.z = fmaf(x, w.z, a.z); a.w = fmaf(x, w.w, a.w);
+}
+
+// MODE 0: PG[u] = W_s . row[u]                       (forward projection; PG is write-only)
+// MODE 1: PG[u] (holding G[u]) <- G[u] . W_s  in place, and the CTA's split-K partial of dW_s = sum_u G[u]^T row[u]
+// Persistent: CTA b owns the contiguous tile range [b*tpc, (b+1)*tpc) of the sorted unique list, so the rows of one
+// table are consecutive and its H x H weight block / dW accumulator stay on chip across tiles.
+template <int H, int MODE>
+__global__ void __launch_bounds__(kFT) fact_rows_kernel(const __grid_constant__ FactParams p,
+                                                        const uint32_t* __restrict__ uniq,
+                                                        const int32_t* __restrict__ n_unique_dev,
+                                                        float* __restrict__ PG, float* __restrict__ dw_part) {
+  constexpr int NV = H > 64 ? H / 64 : 1;   // float4 column groups per thread
+  constexpr int TXN = H / (4 * NV);         // threads along the output columns
+  constexpr int TYN = kFT / TXN;
+  constexpr int RPT = kRT / TYN;            // rows per thread of the [kRT, H] row GEMM
+  constexpr int HPT = H / TYN;              // dW rows per thread
+  constexpr int LD = H + 4;
+  static_assert(RPT >= 1 && HPT >= 1, "tile shape");
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;              // [H][LD]   MODE 0: Ws[k][h] = W[h][col+k]   MODE 1: Ws[h][k] = W[h][col+k]
+  float* Xs = Ws + H * LD;     // [kRT][LD] MODE 0: table rows               MODE 1: G rows
+  float* Rs = Xs + kRT * LD;   // [kRT][LD] MODE 1: table rows
+  __shared__ uint32_t s_key[kRT];
+  const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
+  const int U = *n_unique_dev;
+  const int n_tiles = (U + kRT - 1) / kRT;
+  const int tpc = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_a = blockIdx.x * tpc, tile_b = min(n_tiles, tile_a + tpc);
+  int cur_t = -1;
+  float4 dw[HPT][NV];
+#pragma unroll
+  for (int i = 0; i < HPT; ++i)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) dw[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto flush_dw = [&](int t) {
+    float* dst = dw_part + (size_t)(blockIdx.x + t) * H * H;   // (cta, table) pairs are monotone => unique slots
+#pragma unroll
+    for (int i = 0; i < HPT; ++i)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        *reinterpret_cast<float4*>(dst + (ty * HPT + i) * H + tx * 4 + 64 * v) = dw[i][v];
+        dw[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+  };
+
+  for (int tile = tile_a; tile < tile_b; ++tile) {
+    const int r0 = tile * kRT;
+    const int nr = min(kRT, U - r0);
+    __syncthreads();
+    if (tid < kRT) s_key[tid] = tid < nr ? __ldg(uniq + r0 + tid) : 0xFFFFFFFFu;
+    __syncthreads();
+    int seg_a = 0;
+    while (seg_a < nr) {
+      const int t = find_table(p.key_base, p.n_tables, s_key[seg_a]);
+      const uint32_t kend = p.key_base[t + 1];
+      int seg_b = seg_a + 1;
+      if (s_key[nr - 1] < kend) seg_b = nr;
+      else while (s_key[seg_b] < kend) ++seg_b;   // uniform across the CTA (shared-memory broadcast reads)
+      const int ns = seg_b - seg_a;
+      __syncthreads();   // previous segment's readers of Xs / Rs / Ws are done
+      if (t != cur_t) {
+        if (MODE == 1 && cur_t >= 0) flush_dw(cur_t);
+        const float* W = p.dnn_w[p.side[t]];
+        const int64_t ld = p.dnn_ld[p.side[t]];
+        const int col = p.col[t];
+        for (int i = tid; i < H * H; i += kFT) {
+          const int h = i / H, k = i - h * H;
+          const float wv = __ldg(W + (size_t)h * ld + col + k);
+          if (MODE == 1) Ws[h * LD + k] = wv; else Ws[k * LD + h] = wv;
+        }
+        cur_t = t;
+      }
+      const float* tab = p.w[t];
+      const uint32_t kb = p.key_base[t];
+      for (int i = tid; i < kRT * (H / 4); i += kFT) {
+        const int r = i / (H / 4), c = i - r * (H / 4);
+        float4 row = make_float4(0.f, 0.f, 0.f, 0.f), g = row;
+        if (r < ns) {
+          row = __ldg(reinterpret_cast<const float4*>(tab + (size_t)(s_key[seg_a + r] - kb) * H) + c);
+          if (MODE == 1) g = *reinterpret_cast<const float4*>(PG + (size_t)(r0 + seg_a + r) * H + c * 4);
+        }
+        if (MODE == 1) {
+          *reinterpret_cast<float4*>(Rs + r * LD + c * 4) = row;
+          *reinterpret_cast<float4*>(Xs + r * LD + c * 4) = g;
+        } else {
+          *reinterpret_cast<float4*>(Xs + r * LD + c * 4) = row;
+        }
+      }
+      __syncthreads();
+      // ---- row GEMM: out[r][j] = sum_q Xs[r][q] * Ws[q][j]
+      {
+        float4 acc[RPT][NV];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) acc[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int q = 0; q < H; q += 4) {
+          float4 xv[RPT];
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) xv[i] = *reinterpret_cast<const float4*>(Xs + (ty + TYN * i) * LD + q);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            float4 wv[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) wv[v] = *reinterpret_cast<const float4*>(Ws + (q + qq) * LD + tx * 4 + 64 * v);
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+              const float x = qq == 0 ? xv[i].x : (qq == 1 ? xv[i].y : (qq == 2 ? xv[i].z : xv[i].w));
+#pragma unroll
+              for (int v = 0; v < NV; ++v) fma4(acc[i][v], x, wv[v]);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = ty + TYN * i;
+          if (r < ns) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+              *reinterpret_cast<float4*>(PG + (size_t)(r0 + seg_a + r) * H + tx * 4 + 64 * v) = acc[i][v];
+          }
+        }
+      }
+      // ---- dW GEMM: dw[h][k] += sum_r G[r][h] * R[r][k], rows in sorted order
+      if (MODE == 1) {
+        for (int r = 0; r < ns; ++r) {
+          float4 rv[NV];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) rv[v] = *reinterpret_cast<const float4*>(Rs + r * LD + tx * 4 + 64 * v);
+          float gv[HPT];
+          if constexpr (HPT % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < HPT; i += 4) {
+              const float4 g4 = *reinterpret_cast<const float4*>(Xs + r * LD + ty * HPT + i);
+              gv[i] = g4.x; gv[i + 1] = g4.y; gv[i + 2] = g4.z; gv[i + 3] = g4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < HPT; ++i) gv[i] = Xs[r * LD + ty * HPT + i];
+          }
+#pragma unroll
+          for (int i = 0; i < HPT; ++i)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) fma4(dw[i][v], gv[i], rv[v]);
+        }
+      }
+      seg_a = seg_b;
+    }
+  }
+  if (MODE == 1 && cur_t >= 0) flush_dw(cur_t);
+}
+
+// dW[:, col(t) : col(t)+H] (+)= sum of table t's split-K partials in CTA order. grid = (n_tables, H*H/256).
+template <int H>
+__global__ void __launch_bounds__(kFT) fact_dw_reduce_kernel(const __grid_constant__ FactParams p,
+                                                             const uint32_t* __restrict__ uniq,
+                                                             const int32_t* __restrict__ n_unique_dev,
+                                                             const float* __restrict__ dw_part, int rows_grid,
+                                                             float* dW_item, float* dW_user) {
+  const int t = blockIdx.x;
+  const int U = *n_unique_dev;
+  int lo = 0, hi = U;   // unique-row range [a, b) of table t by binary search on the sorted keys
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(uniq + mid) < p.key_base[t]) lo = mid + 1; else hi = mid; }
+  const int a = lo;
+  hi = U;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(uniq + mid) < p.key_base[t + 1]) lo = mid + 1; else hi = mid; }
+  const int b = lo;
+  if (b <= a) return;
+  float* dW = p.side[t] == 0 ? dW_item : dW_user;
+  if (dW == nullptr) return;
+  const int64_t ld = p.dnn_ld[p.side[t]];
+  const int n_tiles = (U + kRT - 1) / kRT;
+  const int tpc = (n_tiles + rows_grid - 1) / rows_grid;
+  const int cta_a = (a / kRT) / tpc, cta_b = ((b - 1) / kRT) / tpc;
+  const int i = blockIdx.y * kFT + threadIdx.x;
+  if (i >= H * H) return;
+  float s = 0.f;
+  for (int c = cta_a; c <= cta_b; ++c) s = __fadd_rn(s, dw_part[(size_t)(c + t) * H * H + i]);
+  const int h = i / H, k = i - h * H;
+  float* d = dW + (size_t)h * ld + p.col[t] + k;
+  *d = __fadd_rn(*d, s);
+}
+
+// ---- per-token fused forward ----------------------------------------------------------------------------------
+constexpr int kFTok = 32;   // tokens per CTA tile
+constexpr int kFU = 8;      // P rows in flight per lane
+
+struct FwdFactParams {
+  const int32_t* ids_u;     // [T, n_single]  1 + unique index, 0 = padding
+  const int32_t* arr_off[TGR_MAX_ARRAYS];
+  const int32_t* arr_u;     // remapped array values (same indexing as arr_val)
+  const float* mmz[6];      // per mm feature: x . Mfold^T + cfold, [T, H]
+  const float* bias[2];     // itemdnn.bias, userdnn.bias
+  const float* P;           // [U, H]
+  float* out;               // [T, H]
+  uint8_t* mask;            // [T, H/4]: bit j = z_item[4c+j] > 0, bit 4+j = z_user[4c+j] > 0
+  int8_t s_col[TGR_MAX_SLOTS];   // ids column of the SINGLE slots, item side first then user side
+  int8_t a_idx[TGR_MAX_ARRAYS];  // array index of the ARRAY slots, item side first then user side
+  int32_t n_item_single, n_user_single, n_item_array, n_user_array, n_mm, n_single, T, H4, include_user;
+};
+
+__device__ __forceinline__ void gather_sum(float4& z, const int32_t* idr, const int8_t* cols, int s_a, int s_b,
+                                           const float4* __restrict__ P4, int H4, int c) {
+  for (int s0 = s_a; s0 < s_b; s0 += kFU) {
+    float4 v[kFU];
+#pragma unroll
+    for (int u = 0; u < kFU; ++u) {
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s0 + u < s_b) {
+        const int r = idr[cols[s0 + u]];
+        if (r) v[u] = __ldg(P4 + (size_t)(r - 1) * H4 + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kFU; ++u)
+      if (s0 + u < s_b) z = f4_add(z, v[u]);   // slot order
+  }
+}
+
+__device__ __forceinline__ void array_sum(float4& z, const FwdFactParams& p, int a_a, int a_b, int t,
+                                          const float4* __restrict__ P4, int H4, int c) {
+  for (int a = a_a; a < a_b; ++a) {
+    const int ai = p.a_idx[a];
+    const int lo = __ldg(p.arr_off[ai] + t), hi = __ldg(p.arr_off[ai] + t + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = lo; e < hi; ++e) {
+      const int r = __ldg(p.arr_u + e);
+      if (r) acc = f4_add(acc, __ldg(P4 + (size_t)(r - 1) * H4 + c));
+    }
+    z = f4_add(z, acc);
+  }
+}
+
+__device__ __forceinline__ unsigned pos_bits(const float4& z) {
+  return (z.x > 0.f ? 1u : 0u) | (z.y > 0.f ? 2u : 0u) | (z.z > 0.f ? 4u : 0u) | (z.w > 0.f ? 8u : 0u);
+}
+__device__ __forceinline__ float4 relu4(const float4& z) {
+  return make_float4(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f), fmaxf(z.z, 0.f), fmaxf(z.w, 0.f));
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kFT) fact_forward_kernel(const __grid_constant__ FwdFactParams p) {
+  extern __shared__ int32_t s_ids[];   // [kFTok * n_single]
+  constexpr int G = kFT / LANES;
+  const int tid = threadIdx.x, lane = tid % LANES, grp = tid / LANES;
+  const int H4 = p.H4;
+  const int t0 = blockIdx.x * kFTok;
+  const int nt = min(kFTok, p.T - t0);
+  {
+    const int n = nt * p.n_single;
+    const int32_t* src = p.ids_u + (size_t)t0 * p.n_single;   // 16 B aligned: kFTok * n_single * 4 % 16 == 0
+    const int n4 = n >> 2;
+    const int4* src4 = reinterpret_cast<const int4*>(src);
+    int4* dst4 = reinterpret_cast<int4*>(s_ids);
+    for (int i = tid; i < n4; i += kFT) dst4[i] = __ldg(src4 + i);
+    for (int i = (n4 << 2) + tid; i < n; i += kFT) s_ids[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const float4* P4 = reinterpret_cast<const float4*>(p.P);
+  const int ns_i = p.n_item_single, ns = ns_i + p.n_user_single;
+  const int na_i = p.n_item_array, na = na_i + p.n_user_array;
+  for (int tl = grp; tl < nt; tl += G) {
+    const int t = t0 + tl;
+    const int32_t* idr = s_ids + tl * p.n_single;
+    for (int c = lane; c < H4; c += LANES) {
+      float4 zi = __ldg(reinterpret_cast<const float4*>(p.bias[0]) + c);
+      gather_sum(zi, idr, p.s_col, 0, ns_i, P4, H4, c);
+      array_sum(zi, p, 0, na_i, t, P4, H4, c);
+      for (int f = 0; f < p.n_mm; ++f)
+        zi = f4_add(zi, ld_stream(reinterpret_cast<const float4*>(p.mmz[f]) + (size_t)t * H4 + c));
+      unsigned bits = pos_bits(zi);
+      float4 o = relu4(zi);
+      if (p.include_user) {
+        float4 zu = __ldg(reinterpret_cast<const float4*>(p.bias[1]) + c);
+        gather_sum(zu, idr, p.s_col, ns_i, ns, P4, H4, c);
+        array_sum(zu, p, na_i, na, t, P4, H4, c);
+        bits |= pos_bits(zu) << 4;
+        o = f4_add(o, relu4(zu));
+      }
+      st_stream(reinterpret_cast<float4*>(p.out) + (size_t)t * H4 + c, o);
+      p.mask[(size_t)t * H4 + c] = (uint8_t)bits;
+    }
+  }
+}
+
+// dZ_side = dOut * mask_side, plus per-CTA column partial sums (fixed token chunks, fixed order).
+// thread = (column c = tid % H4, row lane rl = tid / H4); CTA b owns tokens [b*chunk, (b+1)*chunk)
+__global__ void __launch_bounds__(kFT) fact_relu_mask_kernel(const float4* __restrict__ d_out,
+                                                             const uint8_t* __restrict__ mask, float4* __restrict__ dzi,
+                                                             float4* __restrict__ dzu, int T, int H4, int chunk,
+                                                             float4* __restrict__ part /* [grid][2][H4] */) {
+  __shared__ float4 s_acc[2][kFT];
+  const int c = threadIdx.x % H4, rl = threadIdx.x / H4, RL = kFT / H4;
+  const int ta = blockIdx.x * chunk, tb = min(T, ta + chunk);
+  float4 si = make_float4(0.f, 0.f, 0.f, 0.f), su = si;
+  for (int t = ta + rl; t < tb; t += RL) {
+    const size_t i = (size_t)t * H4 + c;
+    const float4 d = ld_stream(d_out + i);
+    const unsigned m = mask[i];
+    const float4 a = make_float4(m & 1u ? d.x : 0.f, m & 2u ? d.y : 0.f, m & 4u ? d.z : 0.f, m & 8u ? d.w : 0.f);
+    dzi[i] = a;
+    si = f4_add(si, a);
+    if (dzu != nullptr) {
+      const float4 b = make_float4(m & 16u ? d.x : 0.f, m & 32u ? d.y : 0.f, m & 64u ? d.z : 0.f, m & 128u ? d.w : 0.f);
+      dzu[i] = b;
+      su = f4_add(su, b);
+    }
+  }
+  s_acc[0][threadIdx.x] = si;
+  s_acc[1][threadIdx.x] = su;
+  __syncthreads();
+  if (threadIdx.x < 2 * H4) {
+    const int side = threadIdx.x / H4, cc = threadIdx.x % H4;
+    float4 s = s_acc[side][cc];
+    for (int r = 1; r < RL; ++r) s = f4_add(s, s_acc[side][r * H4 + cc]);
+    part[((size_t)blockIdx.x * 2 + side) * H4 + cc] = s;
+  }
+}
+
+// db_side[h] += sum over CTA partials in CTA order. One thread per (side, column).
+__global__ void fact_colsum_finish_kernel(const float* __restrict__ part, int n_part, int H, float* db_item, float* db_user) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * H) return;
+  const int side = i / H, h = i - side * H;
+  float* db = side == 0 ? db_item : db_user;
+  if (db == nullptr) return;
+  float s = 0.f;
+  for (int b = 0; b < n_part; ++b) s = __fadd_rn(s, part[((size_t)b * 2 + side) * H + h]);
+  db[h] = __fadd_rn(db[h], s);
+}
+
+// ---- mm features folded through the item DNN -------------------------------------------------------------------
+// M[h][j] = sum_q Ws[h][q] Wmm[q][j] ; c[h] = sum_q Ws[h][q] bmm[q]         (Ws = itemdnn.weight[:, col:col+H])
+__global__ void __launch_bounds__(256) fact_mm_fold_kernel(const float* __restrict__ Ws, int64_t ld, const float* __restrict__ Wmm,
+                                                           const float* __restrict__ bmm, int H, int mm_dim,
+                                                           float* __restrict__ M, float* __restrict__ cvec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H * mm_dim) {
+    const int h = i / mm_dim, j = i - h * mm_dim;
+    float s = 0.f;
+    for (int q = 0; q < H; ++q) s = fmaf(__ldg(Ws + (size_t)h * ld + q), __ldg(Wmm + (size_t)q * mm_dim + j), s);
+    M[i] = s;
+  } else if (i < H * mm_dim + H) {
+    const int h = i - H * mm_dim;
+    float s = 0.f;
+    if (bmm != nullptr)
+      for (int q = 0; q < H; ++q) s = fmaf(__ldg(Ws + (size_t)h * ld + q), __ldg(bmm + q), s);
+    cvec[h] = s;
+  }
+}
+
+// From A = dZ^T x [H, mm_dim] and s = colsum(dZ) [H]:
+//   dWmm[q][j] += sum_h Ws[h][q] A[h][j] ; dbmm[q] += sum_h Ws[h][q] s[h] ; dWs[h][q] += sum_j A[h][j] Wmm[q][j] + s[h] bmm[q]
+__global__ void __launch_bounds__(256) fact_mm_chain_kernel(const float* __restrict__ Ws, int64_t ld, const float* __restrict__ Wmm,
+                                                            const float* __restrict__ bmm, const float* __restrict__ A,
+                                                            const float* __restrict__ s, int H, int mm_dim, float* dWmm,
+                                                            float* dbmm, float* dWs, int64_t dld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n1 = H * mm_dim, n2 = n1 + H, n3 = n2 + H * H;
+  if (i < n1) {
+    const int q = i / mm_dim, j = i - q * mm_dim;
+    float a = 0.f;
+    for (int h = 0; h < H; ++h) a = fmaf(__ldg(Ws + (size_t)h * ld + q), __ldg(A + (size_t)h * mm_dim + j), a);
+    dWmm[i] = __fadd_rn(dWmm[i], a);
+  } else if (i < n2) {
+    const int q = i - n1;
+    if (dbmm != nullptr) {
+      float a = 0.f;
+      for (int h = 0; h < H; ++h) a = fmaf(__ldg(Ws + (size_t)h * ld + q), __ldg(s + h), a);
+      dbmm[q] = __fadd_rn(dbmm[q], a);
+    }
+  } else if (i < n3) {
+    const int e = i - n2;
+    const int h = e / H, q = e - h * H;
+    float a = 0.f;
+    for (int j = 0; j < mm_dim; ++j) a = fmaf(__ldg(A + (size_t)h * mm_dim + j), __ldg(Wmm + (size_t)q * mm_dim + j), a);
+    if (bmm != nullptr) a = fmaf(__ldg(s + h), __ldg(bmm + q), a);
+    float* d = dWs + (size_t)h * dld + q;
+    *d = __fadd_rn(*d, a);
+  }
+}
+
+static int fill_fact(FactParams& p, const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn) {
+  TGR_REQUIRE(tables && n_tables > 0 && n_tables <= TGR_MAX_TABLES, "bad table array");
+  TGR_REQUIRE(H == 32 || H == 64 || H == 128, "the factored path supports H in {32, 64, 128} (H=%d)", H);
+  TGR_REQUIRE(dnn && dnn->w_item, "dnn / itemdnn weight is NULL");
+  p.n_tables = n_tables;
+  for (int t = 0; t < n_tables; ++t) {
+    p.w[t] = tables[t].weight;
+    TGR_REQUIRE(p.w[t] != nullptr, "table %d: weight NULL", t);
+    p.key_base[t] = (uint32_t)tables[t].key_base;
+    p.side[t] = (int8_t)dnn->table_side[t];
+    p.col[t] = dnn->table_col[t];
+    TGR_REQUIRE(p.side[t] == 0 || (p.side[t] == 1 && dnn->w_user), "table %d: bad side %d", t, (int)p.side[t]);
+    const int64_t ld = p.side[t] == 0 ? dnn->item_ld : dnn->user_ld;
+    TGR_REQUIRE(p.col[t] >= 0 && p.col[t] + H <= ld, "table %d: DNN columns out of range", t);
+    if (t) TGR_REQUIRE(tables[t].key_base == tables[t - 1].key_base + tables[t - 1].rows, "key bases must be cumulative");
+  }
+  p.key_base[n_tables] = (uint32_t)(tables[n_tables - 1].key_base + tables[n_tables - 1].rows);
+  p.dnn_w[0] = dnn->w_item; p.dnn_ld[0] = dnn->item_ld;
+  p.dnn_w[1] = dnn->w_user; p.dnn_ld[1] = dnn->user_ld;
+  return 0;
+}
+
+static size_t fact_smem(int H, bool bwd) { return (size_t)(H * (H + 4) + (bwd ? 2 : 1) * kRT * (H + 4)) * sizeof(float); }
+
+template <int H, int MODE>
+static int launch_rows(const FactParams& p, const uint32_t* uniq, const int32_t* n_unique_dev, float* PG, float* dw_part,
+                       cudaStream_t st) {
+  const size_t smem = fact_smem(H, MODE == 1);
+  cudaFuncSetAttribute(fact_rows_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fact_rows_kernel<H, MODE><<<kRowsGrid, kFT, smem, st>>>(p, uniq, n_unique_dev, PG, dw_part);
+  return check_launch(MODE ? "fact_unique_backward" : "fact_project_rows");
+}
+
+}  // namespace tgr
+
+using namespace tgr;
+
+extern "C" int tgr_fact_project_rows(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn,
+                                     const uint32_t* uniq, const int32_t* n_unique_dev, int64_t max_unique, float* P,
+                                     void* stream) {
+  FactParams p{};
+  if (int rc = fill_fact(p, tables, n_tables, H, dnn)) return rc;
+  TGR_REQUIRE(uniq && n_unique_dev && P, "null argument");
+  if (max_unique <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H == 32) return launch_rows<32, 0>(p, uniq, n_unique_dev, P, nullptr, st);
+  if (H == 64) return launch_rows<64, 0>(p, uniq, n_unique_dev, P, nullptr, st);
+  return launch_rows<128, 0>(p, uniq, n_unique_dev, P, nullptr, st);
+}
+
+extern "C" size_t tgr_fact_backward_workspace_bytes(int n_tables, int H) {
+  return (size_t)(kRowsGrid + n_tables + 1) * H * H * sizeof(float);
+}
+
+extern "C" int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn,
+                                        const uint32_t* uniq, const int32_t* n_unique_dev, int64_t max_unique, float* G,
+                                        float* dW_item, float* dW_user, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  FactParams p{};
+  if (int rc = fill_fact(p, tables, n_tables, H, dnn)) return rc;
+  TGR_REQUIRE(uniq && n_unique_dev && G && workspace, "null argument");
+  TGR_REQUIRE(workspace_bytes >= tgr_fact_backward_workspace_bytes(n_tables, H), "workspace too small");
+  if (max_unique <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = (float*)workspace;
+  int rc;
+  if (H == 32) rc = launch_rows<32, 1>(p, uniq, n_unique_dev, G, part, st);
+  else if (H == 64) rc = launch_rows<64, 1>(p, uniq, n_unique_dev, G, part, st);
+  else rc = launch_rows<128, 1>(p, uniq, n_unique_dev, G, part, st);
+  if (rc) return rc;
+  if (dW_item == nullptr && dW_user == nullptr) return 0;
+  const dim3 grid(n_tables, (H * H + kFT - 1) / kFT);
+  if (H == 32) fact_dw_reduce_kernel<32><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGrid, dW_item, dW_user);
+  else if (H == 64) fact_dw_reduce_kernel<64><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGrid, dW_item, dW_user);
+  else fact_dw_reduce_kernel<128><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGrid, dW_item, dW_user);
+  return check_launch("fact_dw_reduce");
+}
+
+extern "C" int tgr_fact_forward(const tgr_call_t* call, int H, const int32_t* ids_u, const int32_t* arr_u, const float* P,
+                                const float* const* mmz, int n_mm, const float* bias_item, const float* bias_user,
+                                float* out, uint8_t* mask, void* stream) {
+  TGR_REQUIRE(call && P && bias_item && out && mask, "null argument");
+  TGR_REQUIRE(H == 32 || H == 64 || H == 128, "the factored path supports H in {32, 64, 128}");
+  TGR_REQUIRE(n_mm >= 0 && n_mm <= 6, "n_mm out of range");
+  TGR_REQUIRE(call->T >= 0 && call->n_slots >= 0 && call->n_slots <= TGR_MAX_SLOTS, "bad call");
+  if (call->T == 0) return 0;
+  FwdFactParams p{};
+  p.ids_u = ids_u; p.arr_u = arr_u; p.P = P; p.out = out; p.mask = mask;
+  p.bias[0] = bias_item; p.bias[1] = bias_user;
+  p.T = call->T; p.H4 = H / 4; p.n_single = call->n_single; p.n_mm = n_mm;
+  for (int f = 0; f < n_mm; ++f) { TGR_REQUIRE(mmz && mmz[f], "mmz[%d] NULL", f); p.mmz[f] = mmz[f]; }
+  int ns = 0, na = 0;
+  bool user = false;
+  for (int side = 0; side < 2; ++side) {
+    for (int i = 0; i < call->n_slots; ++i) {
+      const tgr_slot_t& s = call->slots[i];
+      if (s.side != side) continue;
+      if (s.kind == TGR_KIND_SINGLE) {
+        TGR_REQUIRE(s.src >= 0 && s.src < call->n_single, "slot %d: ids column out of range", i);
+        p.s_col[ns++] = (int8_t)s.src;
+        (side == 0 ? p.n_item_single : p.n_user_single)++;
+      } else if (s.kind == TGR_KIND_ARRAY) {
+        TGR_REQUIRE(s.src >= 0 && s.src < call->n_arrays && s.src < TGR_MAX_ARRAYS, "slot %d: array index out of range", i);
+        TGR_REQUIRE(call->arr_off[s.src] != nullptr && (arr_u != nullptr || call->arr_nnz[s.src] == 0), "array pointers NULL");
+        p.a_idx[na++] = (int8_t)s.src;
+        p.arr_off[s.src] = call->arr_off[s.src];
+        (side == 0 ? p.n_item_array : p.n_user_array)++;
+      } else {
+        TGR_REQUIRE(s.kind == TGR_KIND_MM && side == 0, "slot %d: bad kind/side", i);
+      }
+      if (side == 1) user = true;
+    }
+  }
+  TGR_REQUIRE(ns == 0 || ids_u != nullptr, "ids_u is NULL");
+  TGR_REQUIRE(((uintptr_t)ids_u & 15) == 0, "ids_u must be 16-byte aligned");
+  p.include_user = user ? 1 : 0;
+  TGR_REQUIRE(!user || bias_user, "user side needs the userdnn bias");
+  const int grid = (call->T + kFTok - 1) / kFTok;
+  const size_t smem = (size_t)kFTok * (p.n_single > 0 ? p.n_single : 1) * sizeof(int32_t);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H == 32) fact_forward_kernel<8><<<grid, kFT, smem, st>>>(p);
+  else if (H == 64) fact_forward_kernel<16><<<grid, kFT, smem, st>>>(p);
+  else fact_forward_kernel<32><<<grid, kFT, smem, st>>>(p);
+  return check_launch("fact_forward");
+}
+
+static int relu_grid(int64_t T, int* chunk) {
+  int64_t g = (T + 255) / 256;   // >= 256 tokens per CTA
+  if (g > 4 * kNumSMs) g = 4 * kNumSMs;
+  if (g < 1) g = 1;
+  *chunk = (int)((T + g - 1) / g);
+  return (int)((T + *chunk - 1) / *chunk);
+}
+
+extern "C" size_t tgr_fact_relu_mask_workspace_bytes(int64_t T, int H) {
+  int chunk;
+  return (size_t)relu_grid(T, &chunk) * 2 * H * sizeof(float) + 256;
+}
+
+extern "C" int tgr_fact_relu_mask(const float* d_out, const uint8_t* mask, int64_t T, int H, float* dz_item, float* dz_user,
+                                  float* db_item, float* db_user, void* workspace, size_t workspace_bytes, void* stream) {
+  TGR_REQUIRE(H == 32 || H == 64 || H == 128, "the factored path supports H in {32, 64, 128}");
+  TGR_REQUIRE(T >= 0 && T < (1ll << 31), "T out of range");
+  if (T == 0) return 0;
+  TGR_REQUIRE(d_out && mask && dz_item && workspace, "null argument");
+  TGR_REQUIRE(workspace_bytes >= tgr_fact_relu_mask_workspace_bytes(T, H), "workspace too small");
+  int chunk;
+  const int grid = relu_grid(T, &chunk);
+  cudaStream_t st = (cudaStream_t)stream;
+  fact_relu_mask_kernel<<<grid, kFT, 0, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user, (int)T, H / 4,
+                                             chunk, (float4*)workspace);
+  if (int rc = check_launch("fact_relu_mask")) return rc;
+  if (db_item == nullptr && db_user == nullptr) return 0;
+  fact_colsum_finish_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>((const float*)workspace, grid, H, db_item,
+                                                                dz_user ? db_user : nullptr);
+  return check_launch("fact_colsum_finish");
+}
+
+extern "C" int tgr_fact_mm_fold(const float* w_slot, int64_t ld, const float* w_mm, const float* b_mm, int H, int mm_dim,
+                                float* M, float* c, void* stream) {
+  TGR_REQUIRE(w_slot && w_mm && M && c && H > 0 && mm_dim > 0, "bad argument");
+  const int n = H * mm_dim + H;
+  fact_mm_fold_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_slot, ld, w_mm, b_mm, H, mm_dim, M, c);
+  return check_launch("fact_mm_fold");
+}
+
+extern "C" int tgr_fact_mm_chain_bwd(const float* w_slot, int64_t ld, const float* w_mm, const float* b_mm, const float* A,
+                                     const float* s, int H, int mm_dim, float* dW_mm, float* db_mm, float* dW_slot,
+                                     int64_t dld, void* stream) {
+  TGR_REQUIRE(w_slot && w_mm && A && s && dW_mm && dW_slot && H > 0 && mm_dim > 0, "bad argument");
+  const int n = H * mm_dim + H + H * H;
+  fact_mm_chain_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_slot, ld, w_mm, b_mm, A, s, H, mm_dim, dW_mm,
+                                                                          db_mm, dW_slot, dld);
+  return check_launch("fact_mm_chain_bwd");
+}

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) remap_ids_kernel(const int32_t* __restric
         const int mid = (lo + hi) >> 1;
         if (__ldg(uniq + mid) < key) lo = mid + 1; else hi = mid;
       }
-      if (lo < U && __ldg(uniq + lo) == key) r = 1 + __ldg(perm + lo);
+      if (lo < U && __ldg(uniq + lo) == key) r = 1 + (perm ? __ldg(perm + lo) : lo);
     }
     out[i] = r;
   }
@@ -189,7 +189,7 @@ extern "C" int tgr_remap_ids(const int32_t* ids, int64_t n, int n_cols, const ui
                              const int32_t* perm, int32_t* out, void* stream) {
   TGR_REQUIRE(n >= 0 && n_cols > 0 && n_cols <= TGR_MAX_SLOTS, "bad n / n_cols");
   if (n == 0) return 0;
-  TGR_REQUIRE(ids && col_key_base && col_rows && uniq && n_unique_dev && perm && out, "null argument");
+  TGR_REQUIRE(ids && col_key_base && col_rows && uniq && n_unique_dev && out, "null argument");
   RemapCols cols{};
   for (int c = 0; c < n_cols; ++c) { cols.key_base[c] = col_key_base[c]; cols.rows[c] = col_rows[c]; }
   int64_t blocks = (n + 255) / 256;
@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(256) remap_scatter_kernel(const uint32_t* __re
     const int col = p.col_of_slot[call][slot];
     if (col < 0) continue;  // array values are remapped by tgr_remap_ids (a token may hold several)
     const uint32_t tok = src & TGR_SRC_TOKEN_MASK;
-    p.out[call][(size_t)tok * p.n_cols[call] + col] = 1 + __ldg(perm + __ldg(seg_of_entry + e));
+    const int u = __ldg(seg_of_entry + e);
+    p.out[call][(size_t)tok * p.n_cols[call] + col] = 1 + (perm ? __ldg(perm + u) : u);
   }
 }
 }  // namespace tgr
@@ -236,7 +237,7 @@ extern "C" int tgr_remap_scatter(const uint32_t* srcs_sorted, const int32_t* seg
                                  const tgr_call_t* calls, int n_calls, int32_t* const* ids_out, void* stream) {
   TGR_REQUIRE(n >= 0 && n_calls > 0 && n_calls <= TGR_MAX_CALLS, "bad n / n_calls");
   if (n == 0) return 0;
-  TGR_REQUIRE(srcs_sorted && seg_of_entry && perm && calls && ids_out, "null argument");
+  TGR_REQUIRE(srcs_sorted && seg_of_entry && calls && ids_out, "null argument");
   ScatterParams p{};
   for (int c = 0; c < n_calls; ++c) {
     TGR_REQUIRE(ids_out[c] != nullptr, "ids_out[%d] is NULL", c);

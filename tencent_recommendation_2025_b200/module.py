@@ -25,6 +25,7 @@ import numpy as np
 import torch
 
 from .engine import EmbeddingEngine, GatherConcatFn
+from .factored import FactoredEngine, FactoredFn
 from .layout import FeatureLayout
 from .packed import PackedBatch, pack_from_dicts, to_device
 
@@ -80,12 +81,27 @@ class _FeatEmbMixin:
         params = [t for t in eng.tables]
         for k in lay.item_emb_feat:
             params += [self.emb_transform[k].weight, self.emb_transform[k].bias]
+        if getattr(eng, "path", "concat") == "factored":
+            # itemdnn / userdnn + ReLU + add (model.py:303-307) happen inside the factored kernels
+            params += [self.itemdnn.weight, self.itemdnn.bias, self.userdnn.weight, self.userdnn.bias]
+            needs = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+            out = FactoredFn.apply(eng, pb, needs, *params)
+            if _concat_dtype() == torch.bfloat16:
+                out = out.to(torch.bfloat16)   # the autocast Linear of the reference returns bf16
+            return out
         item_cat, user_cat = GatherConcatFn.apply(eng, pb, _concat_dtype(), *params)
         B, L = pb.B, pb.L
         out = torch.relu(self.itemdnn(item_cat.view(B, L, -1)))            # model.py:303
         if pb.include_user:
             out = out + torch.relu(self.userdnn(user_cat.view(B, L, -1)))  # model.py:306-307
         return out
+
+    def prefetch(self, pbs):
+        """Optional step-level fast path of the factored engine: prepare all of a step's calls as ONE group (one
+        sort / dedup, rows shared between the seq / pos / neg calls projected once). No-op on the concat path."""
+        eng = self._tgr_engine
+        if getattr(eng, "path", "concat") == "factored":
+            eng.prefetch(list(pbs))
 
     def fused_step(self, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
         return self._tgr_engine.fused_step(lr, betas, eps, weight_decay, grad_scale)
@@ -108,10 +124,22 @@ def _table_params(mod, layout: FeatureLayout) -> List[torch.nn.Parameter]:
     return out
 
 
+def _make_engine(mod, lay: FeatureLayout, mode: str, path: str):
+    """path 'concat': fused gather/pool/concat kernels + the caller's torch itemdnn/userdnn (SURVEY.md §8 a5-a10);
+    path 'factored': DNN folded into the deduplicated rows (§8(f) N4) — same results, no concat buffers."""
+    if path == "concat":
+        return EmbeddingEngine(lay, _table_params(mod, lay), dict(mod.emb_transform.items()), mode)
+    if path == "factored":
+        return FactoredEngine(lay, _table_params(mod, lay), dict(mod.emb_transform.items()),
+                              {"item": mod.itemdnn, "user": mod.userdnn}, mode)
+    raise ValueError("path must be 'concat' or 'factored'")
+
+
 class BaselineEmbedding(_FeatEmbMixin, torch.nn.Module):
     """The hot-path slice of the reference ``BaselineModel`` with the CUDA ``feat2emb``."""
 
-    def __init__(self, user_num, item_num, feat_statistics, feat_types, args, mode: str = "parity"):
+    def __init__(self, user_num, item_num, feat_statistics, feat_types, args, mode: str = "parity",
+                 path: str = "concat"):
         super().__init__()
         self.user_num, self.item_num = user_num, item_num
         self.dev = args.device
@@ -130,7 +158,7 @@ class BaselineEmbedding(_FeatEmbMixin, torch.nn.Module):
                 self.sparse_emb[k] = torch.nn.Embedding(vocab + 1, H, padding_idx=0)
         for k, d in lay.item_emb_feat.items():
             self.emb_transform[k] = torch.nn.Linear(d, H)
-        self._tgr_engine = EmbeddingEngine(lay, _table_params(self, lay), dict(self.emb_transform.items()), mode)
+        self._tgr_engine = _make_engine(self, lay, mode, path)
 
     @property
     def layout(self) -> FeatureLayout:
@@ -146,7 +174,7 @@ class BaselineEmbedding(_FeatEmbMixin, torch.nn.Module):
         return [p for p in self.parameters() if id(p) not in tabs]
 
 
-def install(model, optimizer: Optional[torch.optim.Optimizer] = None, mode: str = "parity"):
+def install(model, optimizer: Optional[torch.optim.Optimizer] = None, mode: str = "parity", path: str = "concat"):
     """Replace ``model.feat2emb`` of a reference-style ``BaselineModel`` with the CUDA path, in place.
 
     The model keeps its own nn.Embedding / nn.Linear parameters (so init, checkpoints and, in parity
@@ -166,8 +194,8 @@ def install(model, optimizer: Optional[torch.optim.Optimizer] = None, mode: str 
         stats.update(d)
     lay = FeatureLayout(model.user_num, model.item_num, stats, feat_types, H)
     model._tgr_layout = lay
-    model._tgr_engine = EmbeddingEngine(lay, _table_params(model, lay), dict(model.emb_transform.items()), mode)
-    for name in ("feat2tensor", "pack", "feat2emb", "feat2emb_packed", "fused_step", "check_padding_rows"):
+    model._tgr_engine = _make_engine(model, lay, mode, path)
+    for name in ("feat2tensor", "pack", "feat2emb", "feat2emb_packed", "prefetch", "fused_step", "check_padding_rows"):
         setattr(model, name, types.MethodType(getattr(_FeatEmbMixin, name), model))
     if mode == "fused":
         if optimizer is None:
