@@ -149,7 +149,8 @@ def init_module(cfg: synth.SynthConfig, device, mode="fused", path="concat"):
 
 
 def algorithmic_bytes(lay, calls, uniq_per_call, uniq_step, cat_esz=4, x_esz=4):
-    """SURVEY.md §8(d), counted compulsory from the actual batch. Returns (fwd_bytes, bwd_bytes, detail)."""
+    """SURVEY.md §8(d), counted compulsory from the actual batch (the REFERENCE dataflow: concat buffers written in
+    the forward and their gradients read in the backward). Returns (fwd_bytes, bwd_bytes)."""
     H = lay.H
     fwd = bwd = 0
     for pc, U in zip(calls, uniq_per_call):
@@ -174,8 +175,51 @@ def unique_counts(lay, calls):
     return per, int(np.unique(np.concatenate(allk)).size)
 
 
+def kernel_bytes_step(lay, st, pbs, per_u, step_u, path):
+    """Compulsory (algorithmic) bytes of OUR kernels for one step, by C-ABI entry name. Every operand is counted once
+    per launch that must touch it (a row read by many lookups counts once: cache hits cannot inflate the figure)."""
+    H = lay.H
+    n = sum(pb.n_valid for pb in pbs)
+    X = sum(lay.item_emb_feat.values())
+    S = sum(pc.ids.size + pc.arr_val.size for pc in st.calls)
+    out = {}
+    if path == "concat":
+        fw = 0
+        for pc, U in zip(st.calls, per_u):
+            cl = lay.calls[pc.include_user]
+            d_tab = cl.item_dim + cl.user_dim - H * cl.n_mm
+            fw += 4 * (pc.ids.size + pc.arr_val.size + pc.arr_off.size) + U * H * 4 + pc.T * d_tab * 4
+        out["fwd_gather_pool_concat"] = fw
+        out["bwd_reduce"] = 8 * n + n * H * 4 + step_u * 6 * H * 4
+        out["build_keys"] = 4 * S + 8 * n
+        out["sort_pairs"] = 16 * n
+        out["mm_proj_fwd"] = sum(pc.T * (X * 4 + H * 4 * len(lay.item_emb_feat)) for pc in st.calls)
+        out["mm_proj_bwd"] = out["mm_proj_fwd"]
+        return out
+    U = step_u
+    out["build_keys"] = 4 * S + 8 * n
+    out["sort_pairs"] = 16 * n
+    out["dedup"] = 4 * n + 4 * n + 4 * U
+    out["remap_scatter"] = 8 * n + 4 * n
+    out["fact_project_rows"] = 2 * U * H * 4
+    out["mm_proj_fwd"] = sum(pc.T * (X * 4 + H * 4 * len(lay.item_emb_feat)) for pc in st.calls)
+    fw = rm = red = 0
+    for pc, Uc in zip(st.calls, per_u):
+        sides = 2 if pc.include_user else 1
+        fw += 4 * pc.ids.size + 4 * pc.arr_val.size + Uc * H * 4 + pc.T * H * 4 * (1 + len(lay.item_emb_feat)) + pc.T * H // 4
+        rm += pc.T * H * 4 * (1 + sides) + pc.T * H // 4 + pc.T * X * 4
+        red += pc.T * H * 4 * sides
+    out["fact_forward"] = fw
+    out["fact_relu_mask"] = rm
+    out["bwd_reduce"] = 12 * n + red + U * H * 4
+    out["fact_unique_backward"] = 3 * U * H * 4
+    out["adam_rows"] = 7 * U * H * 4
+    return out
+
+
 def run_gpu(args):
-    from tencent_recommendation_2025_b200.packed import to_device
+    from tencent_recommendation_2025_b200 import _lib
+    from tencent_recommendation_2025_b200.packed import HostPrefetcher, stage_pinned, to_device
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -188,15 +232,15 @@ def run_gpu(args):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    # itemdnn/userdnn stay the caller's torch Linear calls; the reference's launcher runs them with TF32
-    # (run.sh:8 --use_tf32 -> main.py:66-68). Tables, concat buffers, gradients and the row update stay fp32.
+    # concat path only: itemdnn/userdnn stay the caller's torch Linear calls; the reference's launcher runs them with
+    # TF32 (run.sh:8 --use_tf32 -> main.py:66-68). The factored path computes them in fp32 inside its own kernels.
     torch.backends.cuda.matmul.allow_tf32 = args.dnn_matmul == "tf32"
     hbm_peak, peak_src = load_peaks()
     cfg = get_config(args.config, args.batch)
     worldgen = synth.SynthWorld(cfg, 0)
     lay = worldgen.layout
     m = init_module(cfg, dev, "fused", args.path)
-    dense_opt = torch.optim.AdamW(m.dense_parameters(), lr=1e-3, betas=(0.9, 0.98))
+    dense_opt = torch.optim.AdamW(m.dense_parameters(), lr=1e-3, betas=(0.9, 0.98), fused=True)
     eng = m.engine
     n_batches = max(1, min(args.batches, args.steps + args.warmup))
     steps_np = [worldgen.make_step(s) for s in range(n_batches)]
@@ -222,10 +266,9 @@ def run_gpu(args):
     clocks = ClockSampler(local_rank, period_ms=args.clock_period_ms)
     if not args.no_clocks:
         clocks.start()
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 3)):
         one_step(*dev_steps[i % n_batches])
     torch.cuda.synchronize()
-    eng.timing = None if args.no_kernel_timing else {}
     clocks.mark()
     l0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -241,70 +284,105 @@ def run_gpu(args):
     clk = clocks.stop()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launches - l0
-    kern_ms = eng.timing_summary()
-    eng.timing = None
     value = rows / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel -------------------------------------------------------
-    per_u, step_u = [], []
-    alg_f = alg_b = 0
+    # ---- per-kernel CUDA-event timing inside the library (a second pass over the same steps; the event pairs are
+    #      recorded on the launching stream around every C-ABI entry) -> roofline of the dominant kernel -------------
+    kern_ms = {}
     used = [(args.warmup + i) % n_batches for i in range(args.steps)]
+    if not args.no_kernel_timing:
+        _lib.timing_enable(True)
+        for k in used:
+            one_step(*dev_steps[k])
+        torch.cuda.synchronize()
+        kern_ms = _lib.timing_collect()
+        _lib.timing_enable(False)
+    alg_f = alg_b = 0
     stats = {}
     for k in sorted(set(used)):
         pu, su = unique_counts(lay, steps_np[k].calls)
         f, b = algorithmic_bytes(lay, steps_np[k].calls, pu, su)
-        stats[k] = (pu, su, f, b)
-    H = lay.H
-    kernel_bytes = {"fwd_gather_pool_concat": 0.0, "bwd_reduce_adam": 0.0}
+        stats[k] = (pu, su, f, b, kernel_bytes_step(lay, steps_np[k], dev_steps[k][0], pu, su, args.path))
+    kbytes = {}
+    nominal = 0
     for k in used:
-        pu, su, f, b = stats[k]
+        pu, su, f, b, kb = stats[k]
         alg_f += f
         alg_b += b
-        st = steps_np[k]
-        for pc, U in zip(st.calls, pu):
-            cl = lay.calls[pc.include_user]
-            d_tab = cl.item_dim + cl.user_dim - H * cl.n_mm       # columns the gather kernel writes
-            kernel_bytes["fwd_gather_pool_concat"] += 4 * (pc.ids.size + pc.arr_val.size + pc.arr_off.size) + U * H * 4 + pc.T * d_tab * 4
-        n_valid = sum(pb.n_valid for pb in dev_steps[k][0])
-        # reduce+AdamW: sorted (key, src) pairs + one gradient row per non-padding lookup + w,m,v read+write per unique row
-        kernel_bytes["bwd_reduce_adam"] += 8 * n_valid + n_valid * H * 4 + su * 6 * H * 4
-    dom = max(kernel_bytes, key=lambda n: kern_ms.get(n, (0.0, 0))[0])
-    dom_ms, dom_launches = kern_ms.get(dom, (0.0, 0))
-    achieved = kernel_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
-                "kernel_ms_per_step": round(dom_ms / args.steps, 4), "launches": dom_launches,
-                "kernels_ms_per_step": {n: round(v[0] / args.steps, 4) for n, v in kern_ms.items()},
-                "step_algorithmic_GB": round((alg_f + alg_b) / args.steps / 1e9, 3),
-                "step_frac_of_hbm_peak": round((alg_f + alg_b) / (ms * 1e-3) / 1e9 / hbm_peak, 4)}
+        for name, v in kb.items():
+            kbytes[name] = kbytes.get(name, 0) + v
+        nominal += sum(pb.n_valid for pb in dev_steps[k][0]) * lay.H * 4
+    table = {}
+    for name, (t_ms, cnt) in kern_ms.items():
+        e = {"ms_per_step": round(t_ms / args.steps, 4), "launches_per_step": round(cnt / args.steps, 2)}
+        if name in kbytes and t_ms > 0:
+            gbs = kbytes[name] / (t_ms * 1e-3) / 1e9
+            e.update({"alg_MB_per_step": round(kbytes[name] / args.steps / 1e6, 1), "GBs": round(gbs, 1),
+                      "frac": round(gbs / hbm_peak, 4)})
+        table[name] = e
+    cand = [n_ for n_ in table if "GBs" in table[n_]]
+    dom = max(cand, key=lambda n_: table[n_]["ms_per_step"]) if cand else None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": table[dom]["GBs"] if dom else 0.0, "peak": hbm_peak,
+                "unit": "GB/s", "frac": table[dom]["frac"] if dom else 0.0, "traffic": load_traffic(dom),
+                "peak_source": peak_src,
+                "kernel_ms_per_step": table[dom]["ms_per_step"] if dom else 0.0,
+                "launches": int(kern_ms[dom][1]) if dom else 0,
+                "note": ("achieved = compulsory bytes of the entry / its CUDA-event time; the gather-sum forward and the "
+                         "segmented reduce read each row once per LOOKUP out of L2 (nominal per-lookup traffic "
+                         f"{round(nominal / args.steps / 1e6)} MB/step each), so their compulsory-HBM fraction is low by "
+                         "design") if args.path == "factored" else "",
+                "kernels": table,
+                "kernels_ms_per_step_sum": round(sum(v["ms_per_step"] for v in table.values()), 4),
+                "reference_dataflow_GB_per_step": round((alg_f + alg_b) / args.steps / 1e9, 3),
+                "reference_dataflow_frac_of_hbm_peak": round((alg_f + alg_b) / (ms * 1e-3) / 1e9 / hbm_peak, 4)}
 
-    # ---- end to end from host buffers (e2e) ----------------------------------------------------
-    from tencent_recommendation_2025_b200.packed import stage_pinned
+    # ---- end to end from host buffers (e2e): pinned host batches -> copy stream -> step -> loss read back ----------
     host_steps = [[stage_pinned(lay, pc) for pc in st.calls] for st in steps_np]   # as a pin_memory DataLoader would
-    e2e_steps = max(3, min(args.steps, 10))
-    torch.cuda.synchronize()
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_warm = n_batches + 1
+    feeder = HostPrefetcher(dev)
+    loss_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+    loss_ev = [None, None]
     h2d = d2h = 0
-    t_e2e = 0.0
     rows_e2e = 0
-    for i in range(e2e_steps + 1):
+    losses = []
+    feeder.submit(host_steps[0])
+    torch.cuda.synchronize()
+    t0 = None
+    for i in range(e2e_warm + e2e_steps):
         k = i % n_batches
-        st = steps_np[k]
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        pbs = [hp.upload(dev) for hp in host_steps[k]]              # async H2D from pinned host memory
+        if i == e2e_warm:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        pbs = feeder.take()                                        # waits (on the stream) for this step's H2D copies
+        feeder.submit(host_steps[(i + 1) % n_batches])             # next step's copies overlap this step's kernels
         outs = one_step(pbs, dev_steps[k][1])
-        loss_host = float(sum(o.sum() for o in outs).item())        # D2H read of the step's result
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if i == 0:
-            continue  # warm-up of the host path
-        t_e2e += dt
-        rows_e2e += lookups[k]
-        h2d += sum(pb.h2d_bytes for pb in pbs)
-        d2h += 4
+        with torch.no_grad():
+            loss = sum(o.detach().sum() for o in outs)
+        slot = i & 1
+        if loss_ev[slot] is not None:                              # step i-2's loss has long arrived: read it
+            loss_ev[slot].synchronize()
+            losses.append(float(loss_host[slot]))
+        loss_host[slot:slot + 1].copy_(loss.reshape(1), non_blocking=True)   # D2H of the step's result
+        loss_ev[slot] = torch.cuda.Event()
+        loss_ev[slot].record()
+        if i >= e2e_warm:
+            rows_e2e += lookups[k]
+            h2d += sum(pb.h2d_bytes for pb in pbs)
+            d2h += 4
+    for slot in ((e2e_warm + e2e_steps) & 1, (e2e_warm + e2e_steps + 1) & 1):
+        if loss_ev[slot] is not None:
+            loss_ev[slot].synchronize()
+            losses.append(float(loss_host[slot]))
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    feeder.take()   # drain the look-ahead submission
     e2e = {"value": rows_e2e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps,
            "d2h_bytes_per_step": d2h // e2e_steps, "ms_per_step": round(t_e2e / e2e_steps * 1e3, 3),
-           "entry": "BaselineEmbedding.feat2emb_packed from pinned host packed buffers (H2D + step + loss read-back timed)"}
+           "entry": "BaselineEmbedding.prefetch + feat2emb_packed x3 + backward + fused_step from pinned host packed "
+                    "buffers; H2D of step k+1 on a copy stream overlaps step k, every step's loss is copied back and "
+                    "read on the host (two steps later, so the read never stalls the queue); wall clock",
+           "loss_finite": bool(np.all(np.isfinite(losses)))}
 
     # ---- CPU baseline (bounded sample, rank 0, N=1) ---------------------------------------------
     cpu = None
@@ -317,12 +395,25 @@ def run_gpu(args):
             "config": {"workload": WORKLOADS[args.config], "batch_per_gpu": cfg.B, "seq_len": cfg.L, "hidden": cfg.H,
                        "item_rows": cfg.item_num + 1, "user_rows": cfg.user_num + 1, "zipf_alpha": cfg.alpha,
                        "mm_features": list(cfg.mm_ids), "row_update": "fused sparse AdamW (lazy rows)",
-                       "dnn_matmul": f"torch F.linear (caller side, unchanged), {args.dnn_matmul} as reference run.sh --use_tf32",
+                       "path": args.path,
+                       "dnn": ("itemdnn/userdnn folded into the deduplicated rows, fp32 (factored kernels)" if args.path == "factored"
+                               else f"torch F.linear (caller side, unchanged), {args.dnn_matmul} as reference run.sh --use_tf32"),
                        "rows_per_step": rows // args.steps, "tokens_per_step": 3 * cfg.B * cfg.L,
-                       "l2": "per-step working set (concat buffers ~1.3 GB + 6 GB of tables/state) >> 126 MB L2; "
-                             f"{n_batches} distinct batches cycled"},
+                       "l2": "tables + AdamW state 6 GB >> 126 MB L2; "
+                             f"{n_batches} distinct batches cycled (each step touches different rows)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
     print(json.dumps(line))
+
+
+def load_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if kernel is None or not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -396,7 +487,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=list(WORKLOADS))
-    ap.add_argument("--path", default="concat", choices=["concat", "factored"],
+    ap.add_argument("--path", default="factored", choices=["concat", "factored"],
                     help="concat: gather/pool/concat kernels + torch itemdnn/userdnn; factored: DNN folded into unique rows")
     ap.add_argument("--batch", type=int, default=1024, help="sequences per GPU")
     ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches to cycle")

@@ -111,6 +111,13 @@ typedef struct tgr_adam {
 int tgr_abi_version(void);
 const char* tgr_last_error(void);
 
+/* Instrumentation for bench.py / profiling (off by default; the one piece of process-wide state in the library):
+ * after tgr_timing_enable(1) every kernel-launching entry brackets its launches with a CUDA-event pair on the
+ * caller's stream; tgr_timing_collect synchronises those events and returns, per entry name ('\n'-joined in
+ * `names`), the summed milliseconds and the number of calls. Returns the number of distinct names. */
+int tgr_timing_enable(int on);
+int tgr_timing_collect(char* names, size_t names_bytes, float* ms, int32_t* counts, int max_entries);
+
 /* ---- forward ---------------------------------------------------------------------------------
  * Fused multi-table gather + array sum-pool + concat write: every SINGLE/ARRAY slot of the call in
  * one launch, straight into item_cat/user_cat (fp32 or bf16 RNE). Replaces aten::embedding x(15|24),
@@ -195,6 +202,12 @@ int tgr_remap_ids(const int32_t* ids, int64_t n, int n_cols, const uint32_t* col
 int tgr_remap_scatter(const uint32_t* srcs_sorted, const int32_t* seg_of_entry, int64_t n, const int32_t* perm,
                       const tgr_call_t* calls, int n_calls, int32_t* const* ids_out, void* stream);
 
+/* The same remap for the values of every ARRAY slot of up to 4 calls in one launch (searching: a token may hold
+ * several values, so the pairs' (call, slot, token) code does not address them). arr_out[c] is indexed like
+ * calls[c].arr_val; arr_out is a HOST array of device pointers. */
+int tgr_remap_arrays(const tgr_table_t* tables, int n_tables, const tgr_call_t* calls, int n_calls, const uint32_t* uniq,
+                     const int32_t* n_unique_dev, const int32_t* perm, int32_t* const* arr_out, void* stream);
+
 /* out[perm[u], :] = in[u, :] for u < *n_dev (inverse = 0), or out[u, :] = in[perm[u], :] (inverse = 1). */
 int tgr_permute_rows(const float* in, int H, const int32_t* perm, const int32_t* n_dev, int64_t max_n, int inverse,
                      float* out, void* stream);
@@ -233,10 +246,12 @@ int tgr_fact_forward(const tgr_call_t* call, int H, const int32_t* ids_u, const 
                      uint8_t* mask, void* stream);
 
 /* dz_item = d_out * mask_item, dz_user = d_out * mask_user (NULL without users); db_* += column sums
- * (autograd of relu + the Linear bias, model.py:303-307). */
+ * (autograd of relu + the Linear bias, model.py:303-307). Optional fused mm statistics for ONE 32-wide mm feature
+ * ('81'): mm_A [H, 32] = dz_item^T . mm_x and mm_s [H] = colsum(dz_item), from the same pass (mm_x NULL = off). */
 size_t tgr_fact_relu_mask_workspace_bytes(int64_t T, int H);
 int tgr_fact_relu_mask(const float* d_out, const uint8_t* mask, int64_t T, int H, float* dz_item, float* dz_user,
-                       float* db_item, float* db_user, void* workspace, size_t workspace_bytes, void* stream);
+                       float* db_item, float* db_user, const void* mm_x, int mm_x_dtype, int mm_dim, float* mm_A,
+                       float* mm_s, void* workspace, size_t workspace_bytes, void* stream);
 
 /* G[u, :] (sum of dz over the row's lookups, from tgr_bwd_reduce mode 0) -> row gradient G[u] . W[:, cols] in place;
  * dW_item / dW_user [H, ld] += sum_u G[u]^T (x) row[u] in the slot's columns (autograd of the Linear weight). */
@@ -254,6 +269,78 @@ int tgr_fact_mm_fold(const float* w_slot, int64_t ld, const float* w_mm, const f
 int tgr_fact_mm_chain_bwd(const float* w_slot, int64_t ld, const float* w_mm, const float* b_mm, const float* A,
                           const float* s, int H, int mm_dim, float* dW_mm, float* db_mm, float* dW_slot, int64_t dld,
                           void* stream);
+
+/* ---- factored path, step-level driver: one call per phase instead of one per kernel ------------------------
+ * The launch sequence of the factored pipeline is fixed once the packed calls are known, so it is sequenced in
+ * the library (tgr_fact_step.cu) and the host makes ~8 calls per training step instead of ~45. All buffers are
+ * carved from ONE caller-provided arena; results are identical to the per-kernel entries above. */
+#define TGR_MAX_MM 6
+
+typedef struct tgr_mm_feat { /* one emb_transform[k] (model.py:167) and its slot's first item-DNN input column */
+  const float* w;            /* [H, mm_dim] */
+  const float* b;            /* [H] or NULL */
+  int32_t mm_dim;
+  int32_t col;
+} tgr_mm_feat_t;
+
+typedef struct tgr_fact_params { /* parameters a group's forward / backward reads (borrowed per call) */
+  tgr_dnn_t dnn;
+  const float* b_item; /* itemdnn.bias */
+  const float* b_user; /* userdnn.bias */
+  tgr_mm_feat_t mm[TGR_MAX_MM];
+  int32_t n_mm;
+  int32_t reserved;
+} tgr_fact_params_t;
+
+typedef struct tgr_fact_grads { /* zero-initialised accumulators (+=), NULL = not wanted */
+  float* dW_item;
+  float* db_item;
+  float* dW_user;
+  float* db_user;
+  float* dW_mm[TGR_MAX_MM];
+  float* db_mm[TGR_MAX_MM];
+} tgr_fact_grads_t;
+
+typedef struct tgr_fact_group {
+  /* ---- filled by the caller before tgr_fact_group_bytes / tgr_fact_prepare ---- */
+  int32_t n_calls, H, key_bits, n_mm;
+  int64_t n;                           /* exact count of non-padding in-range ids over the calls (host-known) */
+  int32_t mm_dim[TGR_MAX_MM];
+  int32_t mm_x_dtype;                  /* TGR_DTYPE_* of the mm inputs */
+  int32_t reserved;
+  tgr_call_t calls[TGR_MAX_CALLS];     /* ids / arrays of every call; item_cat / user_cat unused */
+  const void* mm_x[TGR_MAX_CALLS][TGR_MAX_MM]; /* [T, mm_dim] inputs of every call */
+  /* ---- carved from the arena by tgr_fact_prepare (device pointers; read-only for the caller) ---- */
+  int64_t cap;                         /* rows of uniq / P / G (= max(n, 1)) */
+  uint32_t *keys_in, *srcs_in, *keys, *srcs; /* unsorted / stably sorted (key, src) pairs [n] */
+  uint32_t* uniq;                      /* sorted unique keys [*n_unique] */
+  int32_t *seg_off, *seg_of, *n_unique, *n_valid;
+  float* P;                            /* projected rows [*n_unique, H] */
+  float* G;                            /* after the finishing backward: row gradients [*n_unique, H] */
+  int32_t* ids_u[TGR_MAX_CALLS];
+  int32_t* arr_u[TGR_MAX_CALLS];
+  uint8_t* mask[TGR_MAX_CALLS];
+  float* dz_item[TGR_MAX_CALLS];
+  float* dz_user[TGR_MAX_CALLS];
+  float* mmz[TGR_MAX_CALLS][TGR_MAX_MM];
+  float *fold_M[TGR_MAX_MM], *fold_c[TGR_MAX_MM], *mm_A[TGR_MAX_MM], *mm_s[TGR_MAX_MM];
+  void* ws;
+  size_t ws_bytes;
+  int32_t projected, n_backward;       /* progress */
+} tgr_fact_group_t;
+
+/* Arena bytes tgr_fact_prepare needs for this group (depends on n, the calls' T / n_single / arr_nnz, H, mm dims). */
+size_t tgr_fact_group_bytes(const tgr_fact_group_t* g, int n_tables);
+/* keys -> sort -> dedup -> ids remapped to 1 + unique index, for all calls of the group. Value independent. */
+int tgr_fact_prepare(const tgr_table_t* tables, int n_tables, tgr_fact_group_t* g, void* arena, size_t arena_bytes,
+                     void* stream);
+/* feat2emb forward of call c into out [T, H]; the first forward of a group projects the unique rows. */
+int tgr_fact_call_forward(const tgr_table_t* tables, int n_tables, const tgr_fact_params_t* prm, tgr_fact_group_t* g,
+                          int c, float* out, void* stream);
+/* Backward of call c from d_out [T, H] (c < 0: none). finish != 0 (after the group's last call): segmented reduce of
+ * dZ by key, row gradients into g->G, DNN weight gradients into gr. */
+int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, const tgr_fact_params_t* prm, tgr_fact_group_t* g,
+                           int c, const float* d_out, const tgr_fact_grads_t* gr, int finish, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,6 +46,41 @@ class Dnn(C.Structure):
                 ("table_side", C.c_int32 * MAX_TABLES), ("table_col", C.c_int32 * MAX_TABLES)]
 
 
+MAX_MM = 6
+
+
+class MmFeat(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("mm_dim", C.c_int32), ("col", C.c_int32)]
+
+
+class FactParams(C.Structure):
+    _fields_ = [("dnn", Dnn), ("b_item", C.c_void_p), ("b_user", C.c_void_p), ("mm", MmFeat * MAX_MM),
+                ("n_mm", C.c_int32), ("reserved", C.c_int32)]
+
+
+class FactGrads(C.Structure):
+    _fields_ = [("dW_item", C.c_void_p), ("db_item", C.c_void_p), ("dW_user", C.c_void_p), ("db_user", C.c_void_p),
+                ("dW_mm", C.c_void_p * MAX_MM), ("db_mm", C.c_void_p * MAX_MM)]
+
+
+class FactGroup(C.Structure):
+    _fields_ = [("n_calls", C.c_int32), ("H", C.c_int32), ("key_bits", C.c_int32), ("n_mm", C.c_int32),
+                ("n", C.c_int64), ("mm_dim", C.c_int32 * MAX_MM), ("mm_x_dtype", C.c_int32), ("reserved", C.c_int32),
+                ("calls", Call * MAX_CALLS), ("mm_x", (C.c_void_p * MAX_MM) * MAX_CALLS),
+                ("cap", C.c_int64),
+                ("keys_in", C.c_void_p), ("srcs_in", C.c_void_p), ("keys", C.c_void_p), ("srcs", C.c_void_p),
+                ("uniq", C.c_void_p),
+                ("seg_off", C.c_void_p), ("seg_of", C.c_void_p), ("n_unique", C.c_void_p), ("n_valid", C.c_void_p),
+                ("P", C.c_void_p), ("G", C.c_void_p),
+                ("ids_u", C.c_void_p * MAX_CALLS), ("arr_u", C.c_void_p * MAX_CALLS), ("mask", C.c_void_p * MAX_CALLS),
+                ("dz_item", C.c_void_p * MAX_CALLS), ("dz_user", C.c_void_p * MAX_CALLS),
+                ("mmz", (C.c_void_p * MAX_MM) * MAX_CALLS),
+                ("fold_M", C.c_void_p * MAX_MM), ("fold_c", C.c_void_p * MAX_MM), ("mm_A", C.c_void_p * MAX_MM),
+                ("mm_s", C.c_void_p * MAX_MM),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
+                ("projected", C.c_int32), ("n_backward", C.c_int32)]
+
+
 class Adam(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float), ("step_size", C.c_float), ("bc2_sqrt", C.c_float),
@@ -66,6 +101,8 @@ def make_adam(lr: float, beta1: float, beta2: float, eps: float, weight_decay: f
 SIGNATURES = {
     "tgr_abi_version": (C.c_int, []),
     "tgr_last_error": (C.c_char_p, []),
+    "tgr_timing_enable": (C.c_int, [C.c_int]),
+    "tgr_timing_collect": (C.c_int, [C.c_char_p, C.c_size_t, f32p, i32p, C.c_int]),
     "tgr_fwd_gather_pool_concat": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Call), C.c_void_p]),
     "tgr_mm_proj_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_int64, C.c_int, C.c_void_p]),
@@ -97,6 +134,8 @@ SIGNATURES = {
                                 C.c_void_p]),
     "tgr_remap_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Call), C.c_int,
                                     C.POINTER(C.c_void_p), C.c_void_p]),
+    "tgr_remap_arrays": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(Call), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_void_p), C.c_void_p]),
     "tgr_permute_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "tgr_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "tgr_fact_project_rows": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Dnn), C.c_void_p, C.c_void_p,
@@ -105,13 +144,20 @@ SIGNATURES = {
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_fact_relu_mask_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "tgr_fact_relu_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]),
     "tgr_fact_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "tgr_fact_unique_backward": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Dnn), C.c_void_p, C.c_void_p,
                                            C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                            C.c_void_p]),
     "tgr_fact_mm_fold": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    "tgr_fact_group_bytes": (C.c_size_t, [C.POINTER(FactGroup), C.c_int]),
+    "tgr_fact_prepare": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(FactGroup), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tgr_fact_call_forward": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(FactParams), C.POINTER(FactGroup), C.c_int,
+                                        C.c_void_p, C.c_void_p]),
+    "tgr_fact_call_backward": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(FactParams), C.POINTER(FactGroup), C.c_int,
+                                         C.c_void_p, C.POINTER(FactGrads), C.c_int, C.c_void_p]),
     "tgr_fact_mm_chain_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
@@ -142,6 +188,22 @@ def load():
             raise TgrError(f"ABI mismatch: library {lib.tgr_abi_version()} vs binding {TGR_ABI_VERSION}")
         _lib = lib
         return lib
+
+
+def timing_enable(on: bool = True):
+    """Per-entry CUDA-event timing inside the library (bench / profiling)."""
+    load().tgr_timing_enable(1 if on else 0)
+
+
+def timing_collect():
+    """{entry name: (total ms, calls)} since timing_enable(True); clears the records."""
+    lib = load()
+    names = C.create_string_buffer(4096)
+    ms = (C.c_float * 64)()
+    cnt = (C.c_int32 * 64)()
+    n = lib.tgr_timing_collect(names, 4096, ms, cnt, 64)
+    keys = names.value.decode().split("\n")[:n]
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(keys)}
 
 
 def check(rc: int, what: str = ""):

@@ -174,6 +174,103 @@ struct KeyFunctor {
   __device__ __forceinline__ void every(int64_t, int64_t) const {}
 };
 
+// ---- block-wise key builder: 2048 consecutive entries of ONE segment per CTA, 8 per thread ------------------------
+// (the first version decoded one entry per thread through the generic compaction functor: 126 us per step, bound by
+//  per-entry divisions and divergent constant-bank lookups; here the per-column tables sit in shared memory, the
+//  (token, column) pair is advanced incrementally and the compacted pairs leave through a coalesced copy-out)
+constexpr int kKT = 256;             // threads
+constexpr int kKE = 8;               // entries per thread
+constexpr int kKB = kKT * kKE;       // entries per CTA
+
+struct KeyBlockParams {
+  KeyParams kp;
+  int32_t seg_first_block[kMaxKeySegs + 1];
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kKT) keys_block_kernel(const __grid_constant__ KeyBlockParams P,
+                                                         int32_t* __restrict__ block_cnt,   // count: out; emit: exclusive offsets
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ srcs) {
+  __shared__ uint32_t s_base[TGR_MAX_SLOTS];
+  __shared__ int32_t s_rows[TGR_MAX_SLOTS];
+  __shared__ uint32_t s_slot[TGR_MAX_SLOTS];
+  __shared__ int32_t s_warp[kKT / 32];
+  __shared__ uint32_t s_k[EMIT ? kKB : 1], s_s[EMIT ? kKB : 1];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int s = 0;
+  while (s + 1 < P.kp.n_seg && (int)blockIdx.x >= P.seg_first_block[s + 1]) ++s;
+  const KeySeg& g = P.kp.seg[s];
+  if (g.n_cols > 0 && tid < g.n_cols) {
+    s_base[tid] = P.kp.col_key_base[g.call][tid];
+    s_rows[tid] = P.kp.col_rows[g.call][tid];
+    s_slot[tid] = ((uint32_t)g.call << TGR_SRC_CALL_SHIFT) | ((uint32_t)P.kp.col_slot[g.call][tid] << TGR_SRC_SLOT_SHIFT);
+  }
+  __syncthreads();
+  const uint32_t cnt = (uint32_t)g.count;
+  const uint32_t i0 = (uint32_t)(blockIdx.x - P.seg_first_block[s]) * kKB + tid * kKE;
+  int id[kKE];
+  const int32_t* src = g.vals + i0;
+  if (i0 + kKE <= cnt && (((uintptr_t)src) & 15) == 0) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(src)), b = __ldg(reinterpret_cast<const int4*>(src) + 1);
+    id[0] = a.x; id[1] = a.y; id[2] = a.z; id[3] = a.w; id[4] = b.x; id[5] = b.y; id[6] = b.z; id[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kKE; ++k) id[k] = i0 + k < cnt ? __ldg(src + k) : 0;
+  }
+  uint32_t key[kKE], sc[kKE];
+  unsigned vm = 0;
+  if (g.n_cols > 0) {
+    uint32_t t = i0 / (uint32_t)g.n_cols;
+    int c = (int)(i0 - t * (uint32_t)g.n_cols);
+#pragma unroll
+    for (int k = 0; k < kKE; ++k) {
+      if (id[k] > 0 && id[k] < s_rows[c]) {
+        vm |= 1u << k;
+        key[k] = s_base[c] + (uint32_t)id[k];
+        sc[k] = s_slot[c] | t;
+      }
+      if (++c == g.n_cols) { c = 0; ++t; }
+    }
+  } else {
+    const uint32_t hi = ((uint32_t)g.call << TGR_SRC_CALL_SHIFT) | ((uint32_t)g.slot << TGR_SRC_SLOT_SHIFT);
+#pragma unroll
+    for (int k = 0; k < kKE; ++k) {
+      if (id[k] > 0 && id[k] < g.rows) {
+        vm |= 1u << k;
+        key[k] = g.key_base + (uint32_t)id[k];
+        sc[k] = EMIT ? (hi | (uint32_t)__ldg(g.toks + i0 + k)) : 0u;
+      }
+    }
+  }
+  const int mine = __popc(vm);
+  int x = mine;   // inclusive warp scan
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_warp[wid] = x;
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kKT / 32; ++w) {
+    const int v = s_warp[w];
+    if (w < wid) before += v;
+    total += v;
+  }
+  if (!EMIT) {
+    if (tid == 0) block_cnt[blockIdx.x] = total;
+    return;
+  }
+  int pos = before + x - mine;
+#pragma unroll
+  for (int k = 0; k < kKE; ++k)
+    if (vm & (1u << k)) { s_k[pos] = key[k]; s_s[pos] = sc[k]; ++pos; }
+  __syncthreads();
+  const size_t off = (size_t)block_cnt[blockIdx.x];
+  for (int j = tid; j < total; j += kKT) { keys[off + j] = s_k[j]; srcs[off + j] = s_s[j]; }
+}
+
 // =================================================================================================
 // dedup (run-length encode of sorted keys)
 // =================================================================================================
@@ -252,19 +349,20 @@ extern "C" int64_t tgr_bwd_max_entries(const tgr_call_t* calls, int n_calls) {
 }
 
 extern "C" size_t tgr_build_keys_workspace_bytes(int64_t max_entries) {
-  const size_t nb = (size_t)((max_entries + kScanBlock - 1) / kScanBlock) + 1;
+  const size_t nb = (size_t)((max_entries + kScanBlock - 1) / kScanBlock) + kMaxKeySegs + 1;
   return align_up(nb * sizeof(int32_t));
 }
 
 extern "C" int tgr_bwd_build_keys(const tgr_table_t* tables, int n_tables, const tgr_call_t* calls, int n_calls,
                                   uint32_t* keys, uint32_t* srcs, int32_t* n_valid_dev, void* workspace,
                                   size_t workspace_bytes, void* stream) {
+  tgr::TimedScope tgr_timed_("build_keys", stream);
   TGR_REQUIRE(tables && calls && keys && srcs && n_valid_dev && workspace, "null argument");
   TGR_REQUIRE(n_calls > 0 && n_calls <= TGR_MAX_CALLS, "n_calls=%d out of range", n_calls);
   TGR_REQUIRE(n_tables > 0 && n_tables <= TGR_MAX_TABLES, "n_tables=%d out of range", n_tables);
   cudaStream_t st = (cudaStream_t)stream;
-  KeyFunctor f{};
-  KeyParams& kp = f.kp;
+  KeyBlockParams P{};
+  KeyParams& kp = P.kp;
   int64_t total = 0;
   int ns = 0;
   for (int c = 0; c < n_calls; ++c) {
@@ -312,12 +410,15 @@ extern "C" int tgr_bwd_build_keys(const tgr_table_t* tables, int n_tables, const
   }
   TGR_REQUIRE(total < (1ll << 31), "too many entries");
   int32_t* block_cnt = (int32_t*)workspace;
-  const int nb = (int)((total + kScanBlock - 1) / kScanBlock);
-  f.keys = keys;
-  f.srcs = srcs;
-  flag_count_kernel<<<nb, kScanBlock, 0, st>>>(f, total, block_cnt);
+  int nb = 0;
+  for (int i = 0; i < ns; ++i) {
+    P.seg_first_block[i] = nb;
+    nb += (int)((kp.seg[i].count + kKB - 1) / kKB);
+  }
+  P.seg_first_block[ns] = nb;
+  keys_block_kernel<false><<<nb, kKT, 0, st>>>(P, block_cnt, nullptr, nullptr);
   block_scan_kernel<<<1, kScanBlock, 0, st>>>(block_cnt, nb, n_valid_dev);
-  flag_emit_kernel<<<nb, kScanBlock, 0, st>>>(f, total, block_cnt);
+  keys_block_kernel<true><<<nb, kKT, 0, st>>>(P, block_cnt, keys, srcs);
   return check_launch("build_keys");
 }
 
@@ -330,6 +431,7 @@ extern "C" size_t tgr_sort_workspace_bytes(int64_t n) {
 
 extern "C" int tgr_sort_pairs(const uint32_t* keys_in, const uint32_t* srcs_in, uint32_t* keys_out, uint32_t* srcs_out,
                               int64_t n, int key_bits, void* workspace, size_t workspace_bytes, void* stream) {
+  tgr::TimedScope tgr_timed_("sort_pairs", stream);
   TGR_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
   TGR_REQUIRE(key_bits > 0 && key_bits <= 32, "key_bits=%d out of range", key_bits);
   if (n == 0) return 0;
@@ -350,6 +452,7 @@ extern "C" size_t tgr_dedup_workspace_bytes(int64_t n) {
 
 extern "C" int tgr_dedup(const uint32_t* keys_sorted, int64_t n, uint32_t* uniq, int32_t* seg_off, int32_t* seg_of_entry,
                          int32_t* n_unique_dev, void* workspace, size_t workspace_bytes, void* stream) {
+  tgr::TimedScope tgr_timed_("dedup", stream);
   TGR_REQUIRE(uniq && seg_off && n_unique_dev && workspace, "null argument");
   TGR_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
   TGR_REQUIRE(workspace_bytes >= tgr_dedup_workspace_bytes(n), "workspace too small");
@@ -372,6 +475,7 @@ extern "C" int tgr_dedup(const uint32_t* keys_sorted, int64_t n, uint32_t* uniq,
 
 extern "C" int tgr_adam_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
                              const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam, void* stream) {
+  tgr::TimedScope tgr_timed_("adam_rows", stream);
   TGR_REQUIRE(uniq && grads && n_unique_dev && adam, "null argument");
   RowParams rp{};
   if (int rc = fill_row_params(rp, tables, n_tables, H)) return rc;
@@ -386,6 +490,7 @@ extern "C" int tgr_adam_rows(const tgr_table_t* tables, int n_tables, int H, con
 
 extern "C" int tgr_scatter_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
                                 const int32_t* n_unique_dev, int64_t max_unique, void* stream) {
+  tgr::TimedScope tgr_timed_("scatter_rows", stream);
   TGR_REQUIRE(uniq && grads && n_unique_dev, "null argument");
   RowParams rp{};
   if (int rc = fill_row_params(rp, tables, n_tables, H)) return rc;
@@ -398,6 +503,7 @@ extern "C" int tgr_scatter_rows(const tgr_table_t* tables, int n_tables, int H, 
 
 extern "C" int tgr_gather_rows(const float* table, int H, const uint32_t* rows, const int32_t* n_dev, int64_t max_n,
                                float* out, void* stream) {
+  tgr::TimedScope tgr_timed_("gather_rows", stream);
   TGR_REQUIRE(table && rows && n_dev && out, "null argument");
   TGR_REQUIRE(H > 0 && H % 4 == 0, "bad H");
   if (max_n <= 0) return 0;

@@ -22,6 +22,17 @@ int check_launch(const char* what);
     }                                 \
   } while (0)
 
+// RAII CUDA-event pair around one C-ABI entry's launches; a no-op unless tgr_timing_enable(1) was called.
+class TimedScope {
+ public:
+  TimedScope(const char* name, void* stream);
+  ~TimedScope();
+ private:
+  const char* name_;
+  void* stream_;
+  void* a_;
+};
+
 constexpr int kNumSMs = 148;  // B200
 
 // ---- cache-hinted 128-bit accesses --------------------------------------------------------

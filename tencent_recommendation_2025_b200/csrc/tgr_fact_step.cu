@@ -1,0 +1,219 @@
+// Step-level driver of the factored path: one C-ABI call per phase instead of one per kernel.
+//
+// A training step of the reference issues ~70 feat2emb-side torch ops from Python (model/BaseLine/model.py:226-310 x3,
+// autograd, main.py:188-190); the factored pipeline is ~45 small kernels whose launch sequence is fixed once the
+// packed calls are known. Driving them one ctypes call at a time left the GPU idle behind the Python interpreter
+// (1.85 ms of host time per 1.4 ms of kernels, profiles/README.md), so the sequencing lives here:
+//
+//   tgr_fact_prepare        carve the group's arena, keys -> sort -> dedup -> id remap                (value independent)
+//   tgr_fact_call_forward   [first call: project unique rows, fold mm weights] mm projection, gather-sum forward
+//   tgr_fact_call_backward  relu mask + bias grads + mm chain; with `finish`: segmented reduce, row grads, dW
+//
+// Every buffer is carved from ONE caller-provided arena (torch-allocated); nothing is allocated here and all work is
+// enqueued on the caller's stream in a fixed order, so results are identical to the per-kernel entry points.
+#include "tgr_common.cuh"
+#include "tgr_rows.cuh"
+
+namespace tgr {
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base((char*)b) {}
+  template <class T>
+  T* take(size_t count) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align_up(count * sizeof(T));
+    return p;
+  }
+};
+
+static bool call_has_user(const tgr_call_t& c) {
+  for (int i = 0; i < c.n_slots; ++i)
+    if (c.slots[i].side == TGR_SIDE_USER) return true;
+  return false;
+}
+
+static int64_t call_nnz(const tgr_call_t& c) {
+  int64_t z = 0;
+  for (int a = 0; a < c.n_arrays; ++a) z += c.arr_nnz[a];
+  return z;
+}
+
+// arr_u is indexed exactly like arr_val: extent = end of the last array
+static int64_t call_arr_extent(const tgr_call_t& c) {
+  int64_t z = 0;
+  for (int a = 0; a < c.n_arrays; ++a) z = max(z, (int64_t)c.arr_begin[a] + c.arr_nnz[a]);
+  return z;
+}
+
+// lays the group's buffers out over `arena` (or just measures when arena == nullptr)
+static size_t carve(tgr_fact_group_t* g, void* arena, int n_tables) {
+  Carver cv(arena);
+  const int H = g->H;
+  const size_t cap = (size_t)(g->n > 0 ? g->n : 1);
+  g->cap = (int64_t)cap;
+  g->keys_in = cv.take<uint32_t>(cap);
+  g->srcs_in = cv.take<uint32_t>(cap);
+  g->keys = cv.take<uint32_t>(cap);
+  g->srcs = cv.take<uint32_t>(cap);
+  g->uniq = cv.take<uint32_t>(cap);
+  g->seg_off = cv.take<int32_t>(cap + 1);
+  g->seg_of = cv.take<int32_t>(cap);
+  g->n_unique = cv.take<int32_t>(4);
+  g->n_valid = cv.take<int32_t>(4);
+  g->P = cv.take<float>(cap * H);
+  g->G = cv.take<float>(cap * H);
+  size_t ws = 0;
+  int64_t max_entries = 0;
+  for (int c = 0; c < g->n_calls; ++c) {
+    const tgr_call_t& cl = g->calls[c];
+    const size_t T = (size_t)cl.T;
+    max_entries += (int64_t)T * cl.n_single + call_nnz(cl);
+    g->ids_u[c] = cv.take<int32_t>(T * (size_t)cl.n_single);
+    g->arr_u[c] = cv.take<int32_t>((size_t)call_arr_extent(cl));
+    g->mask[c] = cv.take<uint8_t>(T * (H / 4));
+    g->dz_item[c] = cv.take<float>(T * H);
+    g->dz_user[c] = call_has_user(cl) ? cv.take<float>(T * H) : nullptr;
+    for (int f = 0; f < g->n_mm; ++f) g->mmz[c][f] = cv.take<float>(T * H);
+    ws = max(ws, tgr_fact_relu_mask_workspace_bytes((int64_t)T, H));
+    for (int f = 0; f < g->n_mm; ++f) ws = max(ws, tgr_mm_proj_bwd_workspace_bytes((int64_t)T, g->mm_dim[f], H));
+  }
+  for (int f = 0; f < g->n_mm; ++f) {
+    g->fold_M[f] = cv.take<float>((size_t)H * g->mm_dim[f]);
+    g->fold_c[f] = cv.take<float>(H);
+    g->mm_A[f] = cv.take<float>((size_t)H * g->mm_dim[f]);
+    g->mm_s[f] = cv.take<float>(H);
+  }
+  ws = max(ws, tgr_build_keys_workspace_bytes(max_entries));
+  ws = max(ws, tgr_sort_workspace_bytes(g->n));
+  ws = max(ws, tgr_dedup_workspace_bytes(g->n));
+  ws = max(ws, 2 * align_up((size_t)(g->n / 512 + 2) * H * sizeof(float)));   // reduce mode 0: per-CTA head/tail partials
+  ws = max(ws, tgr_fact_backward_workspace_bytes(n_tables, H));
+  g->ws = cv.take<char>(ws);
+  g->ws_bytes = ws;
+  return cv.off;
+}
+
+}  // namespace tgr
+
+using namespace tgr;
+
+static int check_group(const tgr_fact_group_t* g) {
+  TGR_REQUIRE(g != nullptr, "group is NULL");
+  TGR_REQUIRE(g->n_calls > 0 && g->n_calls <= TGR_MAX_CALLS, "n_calls=%d out of range", g->n_calls);
+  TGR_REQUIRE(g->H == 32 || g->H == 64 || g->H == 128, "the factored path supports H in {32, 64, 128} (H=%d)", g->H);
+  TGR_REQUIRE(g->n >= 0 && g->n < (1ll << 31), "n out of range");
+  TGR_REQUIRE(g->n_mm >= 0 && g->n_mm <= TGR_MAX_MM, "n_mm out of range");
+  return 0;
+}
+
+extern "C" size_t tgr_fact_group_bytes(const tgr_fact_group_t* g, int n_tables) {
+  if (check_group(g)) return 0;
+  tgr_fact_group_t tmp = *g;
+  return carve(&tmp, nullptr, n_tables) + 256;
+}
+
+extern "C" int tgr_fact_prepare(const tgr_table_t* tables, int n_tables, tgr_fact_group_t* g, void* arena,
+                                size_t arena_bytes, void* stream) {
+  if (int rc = check_group(g)) return rc;
+  TGR_REQUIRE(tables && arena, "null argument");
+  TGR_REQUIRE(((uintptr_t)arena & 255) == 0, "arena must be 256-byte aligned");
+  const size_t need = carve(g, arena, n_tables);
+  TGR_REQUIRE(arena_bytes >= need, "arena too small (%zu < %zu)", arena_bytes, need);
+  g->projected = 0;
+  g->n_backward = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = tgr_bwd_build_keys(tables, n_tables, g->calls, g->n_calls, g->keys_in, g->srcs_in, g->n_valid, g->ws,
+                                  g->ws_bytes, stream)) return rc;
+  if (int rc = tgr_sort_pairs(g->keys_in, g->srcs_in, g->keys, g->srcs, g->n, g->key_bits, g->ws, g->ws_bytes, stream))
+    return rc;
+  if (int rc = tgr_dedup(g->keys, g->n, g->uniq, g->seg_off, g->seg_of, g->n_unique, g->ws, g->ws_bytes, stream)) return rc;
+  int32_t* outs[TGR_MAX_CALLS];
+  for (int c = 0; c < g->n_calls; ++c) {
+    const tgr_call_t& cl = g->calls[c];
+    outs[c] = g->ids_u[c];
+    cudaMemsetAsync(g->ids_u[c], 0, (size_t)cl.T * cl.n_single * sizeof(int32_t), st);
+  }
+  if (int rc = tgr_remap_scatter(g->srcs, g->seg_of, g->n, nullptr, g->calls, g->n_calls, outs, stream)) return rc;
+  // array values (a token may hold several): searching remap, they are few — one launch for all of them
+  if (int rc = tgr_remap_arrays(tables, n_tables, g->calls, g->n_calls, g->uniq, g->n_unique, nullptr, g->arr_u, stream))
+    return rc;
+  return check_launch("fact_prepare");
+}
+
+extern "C" int tgr_fact_call_forward(const tgr_table_t* tables, int n_tables, const tgr_fact_params_t* prm,
+                                     tgr_fact_group_t* g, int c, float* out, void* stream) {
+  if (int rc = check_group(g)) return rc;
+  TGR_REQUIRE(tables && prm && out, "null argument");
+  TGR_REQUIRE(c >= 0 && c < g->n_calls, "call index out of range");
+  TGR_REQUIRE(prm->n_mm == g->n_mm, "n_mm mismatch");
+  const int H = g->H;
+  if (!g->projected) {
+    if (int rc = tgr_fact_project_rows(tables, n_tables, H, &prm->dnn, g->uniq, g->n_unique, g->n, g->P, stream)) return rc;
+    for (int f = 0; f < g->n_mm; ++f) {
+      const tgr_mm_feat_t& m = prm->mm[f];
+      TGR_REQUIRE(m.mm_dim == g->mm_dim[f], "mm_dim mismatch");
+      if (int rc = tgr_fact_mm_fold(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, H, m.mm_dim, g->fold_M[f],
+                                    g->fold_c[f], stream)) return rc;
+    }
+    g->projected = 1;
+  }
+  tgr_call_t& cl = g->calls[c];
+  for (int f = 0; f < g->n_mm; ++f) {
+    TGR_REQUIRE(g->mm_x[c][f] != nullptr, "mm input %d of call %d is NULL", f, c);
+    if (int rc = tgr_mm_proj_fwd(g->mm_x[c][f], g->mm_x_dtype, cl.T, g->mm_dim[f], g->fold_M[f], g->fold_c[f], H,
+                                 g->mmz[c][f], H, TGR_DTYPE_F32, stream)) return rc;
+  }
+  return tgr_fact_forward(&cl, H, g->ids_u[c], call_arr_extent(cl) ? g->arr_u[c] : nullptr, g->P, (const float* const*)g->mmz[c], g->n_mm, prm->b_item,
+                          call_has_user(cl) ? prm->b_user : nullptr, out, g->mask[c], stream);
+}
+
+extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, const tgr_fact_params_t* prm,
+                                      tgr_fact_group_t* g, int c, const float* d_out, const tgr_fact_grads_t* gr,
+                                      int finish, void* stream) {
+  if (int rc = check_group(g)) return rc;
+  TGR_REQUIRE(tables && prm && gr, "null argument");
+  const int H = g->H;
+  if (c >= 0) {
+    TGR_REQUIRE(c < g->n_calls && d_out, "bad call index / d_out");
+    const tgr_call_t& cl = g->calls[c];
+    const bool user = call_has_user(cl);
+    // one 32-wide mm feature rides along in the dZ pass (A = dz^T x, s = colsum); the others use the generic kernels
+    int fused = -1;
+    for (int f = 0; f < g->n_mm; ++f)
+      if (prm->mm[f].mm_dim == 32 && gr->dW_mm[f] != nullptr) { fused = f; break; }
+    if (int rc = tgr_fact_relu_mask(d_out, g->mask[c], cl.T, H, g->dz_item[c], user ? g->dz_user[c] : nullptr, gr->db_item,
+                                    user ? gr->db_user : nullptr, fused >= 0 ? g->mm_x[c][fused] : nullptr, g->mm_x_dtype,
+                                    fused >= 0 ? 32 : 0, fused >= 0 ? g->mm_A[fused] : nullptr,
+                                    fused >= 0 ? g->mm_s[fused] : nullptr, g->ws, g->ws_bytes, stream)) return rc;
+    for (int f = 0; f < g->n_mm; ++f) {
+      const tgr_mm_feat_t& m = prm->mm[f];
+      if (gr->dW_mm[f] == nullptr) continue;
+      if (f != fused)
+        if (int rc = tgr_mm_proj_bwd(g->mm_x[c][f], g->mm_x_dtype, cl.T, m.mm_dim, g->dz_item[c], H, TGR_DTYPE_F32, H,
+                                     g->mm_A[f], g->mm_s[f], 0, g->ws, g->ws_bytes, stream)) return rc;
+      TGR_REQUIRE(gr->dW_item != nullptr, "dW_item is NULL");
+      if (int rc = tgr_fact_mm_chain_bwd(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, g->mm_A[f], g->mm_s[f], H,
+                                         m.mm_dim, gr->dW_mm[f], gr->db_mm[f], gr->dW_item + m.col, prm->dnn.item_ld,
+                                         stream)) return rc;
+    }
+    g->n_backward++;
+  }
+  if (!finish || g->n == 0) return 0;
+  // "concat gradient" of the reduction = dZ [T, H]: every slot at column 0 of its side, row pitch H
+  tgr_call_t calls[TGR_MAX_CALLS];
+  for (int i = 0; i < g->n_calls; ++i) {
+    calls[i] = g->calls[i];
+    for (int s = 0; s < calls[i].n_slots; ++s) calls[i].slots[s].col = 0;
+    calls[i].item_cat = g->dz_item[i];
+    calls[i].item_ld = H;
+    calls[i].user_cat = g->dz_user[i];
+    calls[i].user_ld = H;
+    calls[i].cat_dtype = TGR_DTYPE_F32;
+  }
+  if (int rc = tgr_bwd_reduce(tables, n_tables, H, calls, g->n_calls, g->keys, g->srcs, g->n, 0, g->seg_of, g->G, nullptr,
+                              g->ws, g->ws_bytes, stream)) return rc;
+  return tgr_fact_unique_backward(tables, n_tables, H, &prm->dnn, g->uniq, g->n_unique, g->n, g->G, gr->dW_item,
+                                  gr->dW_user, g->ws, g->ws_bytes, stream);
+}

@@ -27,7 +27,8 @@ namespace tgr {
 
 constexpr int kFT = 256;          // threads per CTA
 constexpr int kRT = 64;           // unique rows per tile
-constexpr int kRowsGrid = 2 * kNumSMs;
+constexpr int kRowsGridFwd = 4 * kNumSMs;   // 35 KB smem, 64 regs: 4 CTAs / SM (H = 64)
+constexpr int kRowsGridBwd = 3 * kNumSMs;   // 52 KB smem, 80 regs: 3 CTAs / SM
 
 struct FactParams {
   const float* w[TGR_MAX_TABLES];       // table rows
@@ -328,50 +329,123 @@ __global__ void __launch_bounds__(kFT) fact_forward_kernel(const __grid_constant
   }
 }
 
-// dZ_side = dOut * mask_side, plus per-CTA column partial sums (fixed token chunks, fixed order).
-// thread = (column c = tid % H4, row lane rl = tid / H4); CTA b owns tokens [b*chunk, (b+1)*chunk)
-__global__ void __launch_bounds__(kFT) fact_relu_mask_kernel(const float4* __restrict__ d_out,
-                                                             const uint8_t* __restrict__ mask, float4* __restrict__ dzi,
-                                                             float4* __restrict__ dzu, int T, int H4, int chunk,
-                                                             float4* __restrict__ part /* [grid][2][H4] */) {
+// dZ_side = dOut * mask_side, per-CTA column partial sums, and (MM) the CTA's partial of A = dZ_item^T x for ONE
+// 32-wide mm feature — all from one pass over dOut (fixed token chunks, fixed order => bitwise reproducible).
+// thread = (column c = tid % H4, row lane rl = tid / H4); CTA b owns tokens [b*chunk, (b+1)*chunk), chunk % kDzTok == 0
+constexpr int kDzTok = 64;   // tokens per smem tile
+constexpr int kDzMM = 32;    // mm width the fused A accumulation supports ('81', model.py:183)
+
+template <int H, bool MM, bool XBF16>
+__global__ void __launch_bounds__(kFT) fact_dz_kernel(const float4* __restrict__ d_out, const uint8_t* __restrict__ mask,
+                                                      float4* __restrict__ dzi, float4* __restrict__ dzu,
+                                                      const void* __restrict__ x, int T, int chunk,
+                                                      float* __restrict__ part /* [grid][2H (+ H*32)] */) {
+  constexpr int H4 = H / 4, RL = kFT / H4, NJ = kDzTok / RL, LD = H + 4, XLD = kDzMM + 4, NI = H / 32;
+  constexpr int PART = 2 * H + (MM ? H * kDzMM : 0);
+  extern __shared__ __align__(16) float dsm[];
+  float* Ds = dsm;                      // [kDzTok][LD]   (MM)
+  float* Xs = Ds + kDzTok * LD;         // [kDzTok][XLD]  (MM)
   __shared__ float4 s_acc[2][kFT];
-  const int c = threadIdx.x % H4, rl = threadIdx.x / H4, RL = kFT / H4;
+  const int tid = threadIdx.x, c = tid % H4, rl = tid / H4;
+  const int tk = tid % 8, th = tid / 8;
   const int ta = blockIdx.x * chunk, tb = min(T, ta + chunk);
   float4 si = make_float4(0.f, 0.f, 0.f, 0.f), su = si;
-  for (int t = ta + rl; t < tb; t += RL) {
-    const size_t i = (size_t)t * H4 + c;
-    const float4 d = ld_stream(d_out + i);
-    const unsigned m = mask[i];
-    const float4 a = make_float4(m & 1u ? d.x : 0.f, m & 2u ? d.y : 0.f, m & 4u ? d.z : 0.f, m & 8u ? d.w : 0.f);
-    dzi[i] = a;
-    si = f4_add(si, a);
-    if (dzu != nullptr) {
-      const float4 b = make_float4(m & 16u ? d.x : 0.f, m & 32u ? d.y : 0.f, m & 64u ? d.z : 0.f, m & 128u ? d.w : 0.f);
-      dzu[i] = b;
-      su = f4_add(su, b);
+  float4 acc[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t0 = ta; t0 < tb; t0 += kDzTok) {
+    float4 d[NJ];
+    unsigned m[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int t = t0 + rl + RL * j;
+      d[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      m[j] = 0;
+      if (t < tb) {
+        const size_t i = (size_t)t * H4 + c;
+        d[j] = ld_stream(d_out + i);
+        m[j] = mask[i];
+      }
+    }
+    if (MM) {
+      for (int i = tid; i < kDzTok * (kDzMM / 4); i += kFT) {
+        const int r = i / (kDzMM / 4), c4 = i % (kDzMM / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t0 + r < tb) {
+          const size_t e = (size_t)(t0 + r) * kDzMM + c4 * 4;
+          if constexpr (XBF16) v = unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + e)));
+          else v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + e));
+        }
+        *reinterpret_cast<float4*>(Xs + r * XLD + c4 * 4) = v;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int t = t0 + rl + RL * j;
+      const float4 dd = d[j];
+      const unsigned mm = m[j];
+      const float4 a = make_float4(mm & 1u ? dd.x : 0.f, mm & 2u ? dd.y : 0.f, mm & 4u ? dd.z : 0.f, mm & 8u ? dd.w : 0.f);
+      if (MM) *reinterpret_cast<float4*>(Ds + (rl + RL * j) * LD + c * 4) = a;   // zero beyond tb
+      if (t < tb) {
+        const size_t i = (size_t)t * H4 + c;
+        dzi[i] = a;
+        si = f4_add(si, a);
+        if (dzu != nullptr) {
+          const float4 b = make_float4(mm & 16u ? dd.x : 0.f, mm & 32u ? dd.y : 0.f, mm & 64u ? dd.z : 0.f, mm & 128u ? dd.w : 0.f);
+          dzu[i] = b;
+          su = f4_add(su, b);
+        }
+      }
+    }
+    if (MM) {
+      __syncthreads();
+#pragma unroll 4
+      for (int r = 0; r < kDzTok; ++r) {
+        const float4 xv = *reinterpret_cast<const float4*>(Xs + r * XLD + tk * 4);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) fma4(acc[i], Ds[r * LD + th + 32 * i], xv);
+      }
+      __syncthreads();
     }
   }
-  s_acc[0][threadIdx.x] = si;
-  s_acc[1][threadIdx.x] = su;
+  s_acc[0][tid] = si;
+  s_acc[1][tid] = su;
   __syncthreads();
-  if (threadIdx.x < 2 * H4) {
-    const int side = threadIdx.x / H4, cc = threadIdx.x % H4;
+  float* dst = part + (size_t)blockIdx.x * PART;
+  if (tid < 2 * H4) {
+    const int side = tid / H4, cc = tid % H4;
     float4 s = s_acc[side][cc];
     for (int r = 1; r < RL; ++r) s = f4_add(s, s_acc[side][r * H4 + cc]);
-    part[((size_t)blockIdx.x * 2 + side) * H4 + cc] = s;
+    *reinterpret_cast<float4*>(dst + side * H + cc * 4) = s;
+  }
+  if (MM) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) *reinterpret_cast<float4*>(dst + 2 * H + (th + 32 * i) * kDzMM + tk * 4) = acc[i];
   }
 }
 
-// db_side[h] += sum over CTA partials in CTA order. One thread per (side, column).
-__global__ void fact_colsum_finish_kernel(const float* __restrict__ part, int n_part, int H, float* db_item, float* db_user) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * H) return;
-  const int side = i / H, h = i - side * H;
-  float* db = side == 0 ? db_item : db_user;
-  if (db == nullptr) return;
+// Ordered sum of the per-CTA partial vectors: output o = sum_b part[b][o], b ascending within each of 4 strided
+// lanes, lanes combined in fixed order. o < H: db_item += , mm_s = ; o < 2H: db_user += ; else mm_A = .
+__global__ void __launch_bounds__(256) fact_dz_finish_kernel(const float* __restrict__ part, int n_part, int part_ld, int H,
+                                                             float* db_item, float* db_user, float* mm_A, float* mm_s) {
+  __shared__ float s_p[4][64];
+  const int ol = threadIdx.x % 64, pl = threadIdx.x / 64;
+  const int o = blockIdx.x * 64 + ol;
   float s = 0.f;
-  for (int b = 0; b < n_part; ++b) s = __fadd_rn(s, part[((size_t)b * 2 + side) * H + h]);
-  db[h] = __fadd_rn(db[h], s);
+  if (o < part_ld)
+    for (int b = pl; b < n_part; b += 4) s = __fadd_rn(s, part[(size_t)b * part_ld + o]);
+  s_p[pl][ol] = s;
+  __syncthreads();
+  if (pl != 0 || o >= part_ld) return;
+  s = __fadd_rn(__fadd_rn(s_p[0][ol], s_p[1][ol]), __fadd_rn(s_p[2][ol], s_p[3][ol]));
+  if (o < H) {
+    if (db_item) db_item[o] = __fadd_rn(db_item[o], s);
+    if (mm_s) mm_s[o] = s;
+  } else if (o < 2 * H) {
+    if (db_user) db_user[o - H] = __fadd_rn(db_user[o - H], s);
+  } else if (mm_A) {
+    mm_A[o - 2 * H] = s;
+  }
 }
 
 // ---- mm features folded through the item DNN -------------------------------------------------------------------
@@ -453,8 +527,8 @@ template <int H, int MODE>
 static int launch_rows(const FactParams& p, const uint32_t* uniq, const int32_t* n_unique_dev, float* PG, float* dw_part,
                        cudaStream_t st) {
   const size_t smem = fact_smem(H, MODE == 1);
-  cudaFuncSetAttribute(fact_rows_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  fact_rows_kernel<H, MODE><<<kRowsGrid, kFT, smem, st>>>(p, uniq, n_unique_dev, PG, dw_part);
+  { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_rows_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
+  fact_rows_kernel<H, MODE><<<MODE ? kRowsGridBwd : kRowsGridFwd, kFT, smem, st>>>(p, uniq, n_unique_dev, PG, dw_part);
   return check_launch(MODE ? "fact_unique_backward" : "fact_project_rows");
 }
 
@@ -465,6 +539,7 @@ using namespace tgr;
 extern "C" int tgr_fact_project_rows(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn,
                                      const uint32_t* uniq, const int32_t* n_unique_dev, int64_t max_unique, float* P,
                                      void* stream) {
+  tgr::TimedScope tgr_timed_("fact_project_rows", stream);
   FactParams p{};
   if (int rc = fill_fact(p, tables, n_tables, H, dnn)) return rc;
   TGR_REQUIRE(uniq && n_unique_dev && P, "null argument");
@@ -476,13 +551,14 @@ extern "C" int tgr_fact_project_rows(const tgr_table_t* tables, int n_tables, in
 }
 
 extern "C" size_t tgr_fact_backward_workspace_bytes(int n_tables, int H) {
-  return (size_t)(kRowsGrid + n_tables + 1) * H * H * sizeof(float);
+  return (size_t)(kRowsGridBwd + n_tables + 1) * H * H * sizeof(float);
 }
 
 extern "C" int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn,
                                         const uint32_t* uniq, const int32_t* n_unique_dev, int64_t max_unique, float* G,
                                         float* dW_item, float* dW_user, void* workspace, size_t workspace_bytes,
                                         void* stream) {
+  tgr::TimedScope tgr_timed_("fact_unique_backward", stream);
   FactParams p{};
   if (int rc = fill_fact(p, tables, n_tables, H, dnn)) return rc;
   TGR_REQUIRE(uniq && n_unique_dev && G && workspace, "null argument");
@@ -497,15 +573,16 @@ extern "C" int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables,
   if (rc) return rc;
   if (dW_item == nullptr && dW_user == nullptr) return 0;
   const dim3 grid(n_tables, (H * H + kFT - 1) / kFT);
-  if (H == 32) fact_dw_reduce_kernel<32><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGrid, dW_item, dW_user);
-  else if (H == 64) fact_dw_reduce_kernel<64><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGrid, dW_item, dW_user);
-  else fact_dw_reduce_kernel<128><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGrid, dW_item, dW_user);
+  if (H == 32) fact_dw_reduce_kernel<32><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
+  else if (H == 64) fact_dw_reduce_kernel<64><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
+  else fact_dw_reduce_kernel<128><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
   return check_launch("fact_dw_reduce");
 }
 
 extern "C" int tgr_fact_forward(const tgr_call_t* call, int H, const int32_t* ids_u, const int32_t* arr_u, const float* P,
                                 const float* const* mmz, int n_mm, const float* bias_item, const float* bias_user,
                                 float* out, uint8_t* mask, void* stream) {
+  tgr::TimedScope tgr_timed_("fact_forward", stream);
   TGR_REQUIRE(call && P && bias_item && out && mask, "null argument");
   TGR_REQUIRE(H == 32 || H == 64 || H == 128, "the factored path supports H in {32, 64, 128}");
   TGR_REQUIRE(n_mm >= 0 && n_mm <= 6, "n_mm out of range");
@@ -552,39 +629,69 @@ extern "C" int tgr_fact_forward(const tgr_call_t* call, int H, const int32_t* id
 }
 
 static int relu_grid(int64_t T, int* chunk) {
-  int64_t g = (T + 255) / 256;   // >= 256 tokens per CTA
+  int64_t g = (T + 4 * kDzTok - 1) / (4 * kDzTok);   // >= 256 tokens per CTA
   if (g > 4 * kNumSMs) g = 4 * kNumSMs;
   if (g < 1) g = 1;
-  *chunk = (int)((T + g - 1) / g);
-  return (int)((T + *chunk - 1) / *chunk);
+  int64_t ch = (T + g - 1) / g;
+  ch = (ch + kDzTok - 1) / kDzTok * kDzTok;
+  if (ch < kDzTok) ch = kDzTok;
+  *chunk = (int)ch;
+  return (int)((T + ch - 1) / ch);
 }
 
 extern "C" size_t tgr_fact_relu_mask_workspace_bytes(int64_t T, int H) {
   int chunk;
-  return (size_t)relu_grid(T, &chunk) * 2 * H * sizeof(float) + 256;
+  return (size_t)relu_grid(T, &chunk) * (2 * H + H * kDzMM) * sizeof(float) + 256;
+}
+
+template <int H>
+static int launch_dz(const float* d_out, const uint8_t* mask, int T, float* dz_item, float* dz_user, const void* mm_x,
+                     int mm_x_dtype, float* part, int grid, int chunk, cudaStream_t st) {
+  const size_t smem = (size_t)(kDzTok * (H + 4) + kDzTok * (kDzMM + 4)) * sizeof(float);
+  if (mm_x == nullptr) {
+    fact_dz_kernel<H, false, false><<<grid, kFT, 0, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user,
+                                                         nullptr, T, chunk, part);
+  } else if (mm_x_dtype == TGR_DTYPE_BF16) {
+    { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_dz_kernel<H, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
+    fact_dz_kernel<H, true, true><<<grid, kFT, smem, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user,
+                                                          mm_x, T, chunk, part);
+  } else {
+    { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_dz_kernel<H, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
+    fact_dz_kernel<H, true, false><<<grid, kFT, smem, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user,
+                                                           mm_x, T, chunk, part);
+  }
+  return check_launch("fact_dz");
 }
 
 extern "C" int tgr_fact_relu_mask(const float* d_out, const uint8_t* mask, int64_t T, int H, float* dz_item, float* dz_user,
-                                  float* db_item, float* db_user, void* workspace, size_t workspace_bytes, void* stream) {
+                                  float* db_item, float* db_user, const void* mm_x, int mm_x_dtype, int mm_dim, float* mm_A,
+                                  float* mm_s, void* workspace, size_t workspace_bytes, void* stream) {
+  tgr::TimedScope tgr_timed_("fact_relu_mask", stream);
   TGR_REQUIRE(H == 32 || H == 64 || H == 128, "the factored path supports H in {32, 64, 128}");
   TGR_REQUIRE(T >= 0 && T < (1ll << 31), "T out of range");
   if (T == 0) return 0;
   TGR_REQUIRE(d_out && mask && dz_item && workspace, "null argument");
   TGR_REQUIRE(workspace_bytes >= tgr_fact_relu_mask_workspace_bytes(T, H), "workspace too small");
+  TGR_REQUIRE(mm_x == nullptr || (mm_dim == kDzMM && mm_A && mm_s), "the fused A = dz^T x supports mm_dim == 32 only");
   int chunk;
   const int grid = relu_grid(T, &chunk);
   cudaStream_t st = (cudaStream_t)stream;
-  fact_relu_mask_kernel<<<grid, kFT, 0, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user, (int)T, H / 4,
-                                             chunk, (float4*)workspace);
-  if (int rc = check_launch("fact_relu_mask")) return rc;
-  if (db_item == nullptr && db_user == nullptr) return 0;
-  fact_colsum_finish_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>((const float*)workspace, grid, H, db_item,
-                                                                dz_user ? db_user : nullptr);
-  return check_launch("fact_colsum_finish");
+  float* part = (float*)workspace;
+  int rc;
+  if (H == 32) rc = launch_dz<32>(d_out, mask, (int)T, dz_item, dz_user, mm_x, mm_x_dtype, part, grid, chunk, st);
+  else if (H == 64) rc = launch_dz<64>(d_out, mask, (int)T, dz_item, dz_user, mm_x, mm_x_dtype, part, grid, chunk, st);
+  else rc = launch_dz<128>(d_out, mask, (int)T, dz_item, dz_user, mm_x, mm_x_dtype, part, grid, chunk, st);
+  if (rc) return rc;
+  if (db_item == nullptr && db_user == nullptr && mm_x == nullptr) return 0;
+  const int part_ld = 2 * H + (mm_x ? H * kDzMM : 0);
+  fact_dz_finish_kernel<<<(part_ld + 63) / 64, 256, 0, st>>>(part, grid, part_ld, H, db_item, dz_user ? db_user : nullptr,
+                                                           mm_x ? mm_A : nullptr, mm_x ? mm_s : nullptr);
+  return check_launch("fact_dz_finish");
 }
 
 extern "C" int tgr_fact_mm_fold(const float* w_slot, int64_t ld, const float* w_mm, const float* b_mm, int H, int mm_dim,
                                 float* M, float* c, void* stream) {
+  tgr::TimedScope tgr_timed_("fact_mm_fold", stream);
   TGR_REQUIRE(w_slot && w_mm && M && c && H > 0 && mm_dim > 0, "bad argument");
   const int n = H * mm_dim + H;
   fact_mm_fold_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_slot, ld, w_mm, b_mm, H, mm_dim, M, c);
@@ -594,6 +701,7 @@ extern "C" int tgr_fact_mm_fold(const float* w_slot, int64_t ld, const float* w_
 extern "C" int tgr_fact_mm_chain_bwd(const float* w_slot, int64_t ld, const float* w_mm, const float* b_mm, const float* A,
                                      const float* s, int H, int mm_dim, float* dW_mm, float* db_mm, float* dW_slot,
                                      int64_t dld, void* stream) {
+  tgr::TimedScope tgr_timed_("fact_mm_chain_bwd", stream);
   TGR_REQUIRE(w_slot && w_mm && A && s && dW_mm && dW_slot && H > 0 && mm_dim > 0, "bad argument");
   const int n = H * mm_dim + H + H * H;
   fact_mm_chain_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_slot, ld, w_mm, b_mm, A, s, H, mm_dim, dW_mm,

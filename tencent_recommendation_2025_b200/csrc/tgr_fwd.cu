@@ -168,6 +168,7 @@ static int launch_fwd(const FwdParams& p, bool bf16, cudaStream_t st) {
 
 extern "C" int tgr_fwd_gather_pool_concat(const tgr_table_t* tables, int n_tables, int H, const tgr_call_t* call,
                                           void* stream) {
+  tgr::TimedScope tgr_timed_("fwd_gather_pool_concat", stream);
   using namespace tgr;
   TGR_REQUIRE(tables && call, "null argument");
   TGR_REQUIRE(H > 0 && H % 4 == 0, "H=%d must be a positive multiple of 4", H);

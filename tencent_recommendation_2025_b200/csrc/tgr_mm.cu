@@ -233,6 +233,7 @@ static int bwd_chunks(int64_t T, int K) {
 
 extern "C" int tgr_mm_proj_fwd(const void* x, int x_dtype, int64_t T, int mm_dim, const float* W, const float* bias,
                                int H, void* out, int64_t out_ld, int out_dtype, void* stream) {
+  tgr::TimedScope tgr_timed_("mm_proj_fwd", stream);
   using namespace tgr;
   TGR_REQUIRE(x && W && out, "null argument");
   TGR_REQUIRE(H > 0 && H % 4 == 0 && mm_dim > 0, "bad H=%d / mm_dim=%d", H, mm_dim);
@@ -269,6 +270,7 @@ extern "C" size_t tgr_mm_proj_bwd_workspace_bytes(int64_t T, int mm_dim, int H) 
 extern "C" int tgr_mm_proj_bwd(const void* x, int x_dtype, int64_t T, int mm_dim, const void* dy, int64_t dy_ld,
                                int dy_dtype, int H, float* dW, float* db, int accumulate, void* workspace,
                                size_t workspace_bytes, void* stream) {
+  tgr::TimedScope tgr_timed_("mm_proj_bwd", stream);
   using namespace tgr;
   TGR_REQUIRE(x && dy && dW && workspace, "null argument");
   TGR_REQUIRE(H > 0 && H % 4 == 0 && H <= 128, "mm backward supports H <= 128 (H=%d)", H);

@@ -292,10 +292,10 @@ static int launch_reduce(RedParams& p, const RowParams* rp, bool bf16, int n_cta
   constexpr int TILE = G * kC;
   const size_t smem = (size_t)(2 * TILE + 4) * 4 + (size_t)2 * G * p.H4 * 16 + (size_t)2 * G * 4 + 16;
   if (bf16) {
-    cudaFuncSetAttribute(reduce_tiles_kernel<LANES, NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(reduce_tiles_kernel<LANES, NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
     reduce_tiles_kernel<LANES, NJ, true><<<n_cta, kRedThreads, smem, st>>>(p);
   } else {
-    cudaFuncSetAttribute(reduce_tiles_kernel<LANES, NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(reduce_tiles_kernel<LANES, NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
     reduce_tiles_kernel<LANES, NJ, false><<<n_cta, kRedThreads, smem, st>>>(p);
   }
   if (int rc = check_launch("reduce_tiles")) return rc;
@@ -330,6 +330,7 @@ extern "C" int tgr_bwd_reduce(const tgr_table_t* tables, int n_tables, int H, co
                               const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n, int mode,
                               const int32_t* seg_of_entry, float* grads_out, const tgr_adam_t* adam, void* workspace,
                               size_t workspace_bytes, void* stream) {
+  tgr::TimedScope tgr_timed_("bwd_reduce", stream);
   TGR_REQUIRE(calls && n_calls > 0 && n_calls <= TGR_MAX_CALLS, "bad calls");
   TGR_REQUIRE(H > 0 && H % 4 == 0 && H <= 512, "H=%d unsupported (multiple of 4, <= 512)", H);
   TGR_REQUIRE(mode == 0 || mode == 1, "bad mode");

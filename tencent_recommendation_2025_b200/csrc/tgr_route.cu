@@ -118,6 +118,7 @@ extern "C" size_t tgr_route_workspace_bytes(int64_t max_unique, int W) {
 extern "C" int tgr_route_bucket(const uint32_t* uniq, const int32_t* n_unique_dev, int64_t max_unique, int W,
                                 uint32_t* bucketed_local_rows, int32_t* perm, int32_t* counts_dev, void* workspace,
                                 size_t workspace_bytes, void* stream) {
+  tgr::TimedScope tgr_timed_("route_bucket", stream);
   TGR_REQUIRE(uniq && n_unique_dev && bucketed_local_rows && perm && counts_dev && workspace, "null argument");
   TGR_REQUIRE(W >= 1 && W <= kMaxW, "W=%d out of range", W);
   TGR_REQUIRE(max_unique >= 0 && max_unique < (1ll << 31), "max_unique out of range");
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(256) permute_rows_kernel(const float* __restri
 extern "C" int tgr_remap_ids(const int32_t* ids, int64_t n, int n_cols, const uint32_t* col_key_base,
                              const int32_t* col_rows, const uint32_t* uniq, const int32_t* n_unique_dev,
                              const int32_t* perm, int32_t* out, void* stream) {
+  tgr::TimedScope tgr_timed_("remap_ids", stream);
   TGR_REQUIRE(n >= 0 && n_cols > 0 && n_cols <= TGR_MAX_SLOTS, "bad n / n_cols");
   if (n == 0) return 0;
   TGR_REQUIRE(ids && col_key_base && col_rows && uniq && n_unique_dev && out, "null argument");
@@ -200,6 +202,7 @@ extern "C" int tgr_remap_ids(const int32_t* ids, int64_t n, int n_cols, const ui
 
 extern "C" int tgr_permute_rows(const float* in, int H, const int32_t* perm, const int32_t* n_dev, int64_t max_n,
                                 int inverse, float* out, void* stream) {
+  tgr::TimedScope tgr_timed_("permute_rows", stream);
   TGR_REQUIRE(in && perm && n_dev && out, "null argument");
   TGR_REQUIRE(H > 0 && H % 4 == 0, "bad H");
   if (max_n <= 0) return 0;
@@ -235,6 +238,7 @@ __global__ void __launch_bounds__(256) remap_scatter_kernel(const uint32_t* __re
 
 extern "C" int tgr_remap_scatter(const uint32_t* srcs_sorted, const int32_t* seg_of_entry, int64_t n, const int32_t* perm,
                                  const tgr_call_t* calls, int n_calls, int32_t* const* ids_out, void* stream) {
+  tgr::TimedScope tgr_timed_("remap_scatter", stream);
   TGR_REQUIRE(n >= 0 && n_calls > 0 && n_calls <= TGR_MAX_CALLS, "bad n / n_calls");
   if (n == 0) return 0;
   TGR_REQUIRE(srcs_sorted && seg_of_entry && calls && ids_out, "null argument");
@@ -251,4 +255,75 @@ extern "C" int tgr_remap_scatter(const uint32_t* srcs_sorted, const int32_t* seg
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   remap_scatter_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(srcs_sorted, seg_of_entry, n, perm, p);
   return check_launch("remap_scatter");
+}
+
+// ---- all ARRAY slots of up to 4 calls in ONE launch (they are few values each: one launch instead of 4..16) ------
+namespace tgr {
+constexpr int kMaxArrSegs = TGR_MAX_CALLS * TGR_MAX_ARRAYS;
+struct ArrSegs {
+  const int32_t* vals[kMaxArrSegs];
+  int32_t* out[kMaxArrSegs];
+  int32_t first[kMaxArrSegs + 1];   // prefix of the value counts
+  uint32_t key_base[kMaxArrSegs];
+  int32_t rows[kMaxArrSegs];
+  int32_t n_seg;
+};
+__global__ void __launch_bounds__(256) remap_arrays_kernel(const __grid_constant__ ArrSegs a, const uint32_t* __restrict__ uniq,
+                                                           const int32_t* __restrict__ n_unique_dev,
+                                                           const int32_t* __restrict__ perm) {
+  const int U = *n_unique_dev;
+  const int total = a.first[a.n_seg];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int s = 0;
+    while (i >= a.first[s + 1]) ++s;
+    const int j = i - a.first[s];
+    const int id = __ldg(a.vals[s] + j);
+    int r = 0;
+    if (id > 0 && id < a.rows[s]) {
+      const uint32_t key = a.key_base[s] + (uint32_t)id;
+      int lo = 0, hi = U;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(uniq + mid) < key) lo = mid + 1; else hi = mid;
+      }
+      if (lo < U && __ldg(uniq + lo) == key) r = 1 + (perm ? __ldg(perm + lo) : lo);
+    }
+    a.out[s][j] = r;
+  }
+}
+}  // namespace tgr
+
+extern "C" int tgr_remap_arrays(const tgr_table_t* tables, int n_tables, const tgr_call_t* calls, int n_calls,
+                                const uint32_t* uniq, const int32_t* n_unique_dev, const int32_t* perm,
+                                int32_t* const* arr_out, void* stream) {
+  tgr::TimedScope tgr_timed_("remap_arrays", stream);
+  TGR_REQUIRE(tables && calls && uniq && n_unique_dev && arr_out, "null argument");
+  TGR_REQUIRE(n_calls > 0 && n_calls <= TGR_MAX_CALLS, "bad n_calls");
+  ArrSegs a{};
+  int ns = 0, total = 0;
+  for (int c = 0; c < n_calls; ++c) {
+    const tgr_call_t& cl = calls[c];
+    for (int i = 0; i < cl.n_slots; ++i) {
+      const tgr_slot_t& s = cl.slots[i];
+      if (s.kind != TGR_KIND_ARRAY) continue;
+      TGR_REQUIRE(s.src >= 0 && s.src < cl.n_arrays && s.src < TGR_MAX_ARRAYS, "call %d slot %d: bad array index", c, i);
+      if (cl.arr_nnz[s.src] <= 0) continue;
+      TGR_REQUIRE(s.table >= 0 && s.table < n_tables, "call %d slot %d: bad table", c, i);
+      TGR_REQUIRE(cl.arr_val && arr_out[c], "call %d: array pointers NULL", c);
+      a.vals[ns] = cl.arr_val + cl.arr_begin[s.src];
+      a.out[ns] = arr_out[c] + cl.arr_begin[s.src];
+      a.first[ns] = total;
+      a.key_base[ns] = (uint32_t)tables[s.table].key_base;
+      a.rows[ns] = (int32_t)tables[s.table].rows;
+      total += cl.arr_nnz[s.src];
+      ++ns;
+    }
+  }
+  a.first[ns] = total;
+  a.n_seg = ns;
+  if (total == 0) return 0;
+  int blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  remap_arrays_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, uniq, n_unique_dev, perm);
+  return check_launch("remap_arrays");
 }

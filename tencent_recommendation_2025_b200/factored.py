@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 from ._lib import Call, Dnn, check, make_adam
-from .engine import EmbeddingEngine, _stream
+from .engine import _DEBUG, EmbeddingEngine, _stream
 from .layout import KIND_ARRAY, KIND_MM, KIND_SINGLE, SIDE_ITEM, FeatureLayout
 from .packed import PackedBatch
 
@@ -32,26 +32,52 @@ SUPPORTED_H = (32, 64, 128)
 
 
 class FactGroup:
-    """Everything the calls prepared together share; owns its buffers until the row update has run."""
+    """The calls prepared together: the C-side group descriptor + the arena every buffer of the group is carved from
+    (sorted pairs, unique keys, remapped ids, projected rows P, masks, dZ, row gradients G). Lives until the row update."""
 
     def __init__(self, pbs: Sequence[PackedBatch]):
         self.pbs = list(pbs)
         self.index = {id(pb): i for i, pb in enumerate(self.pbs)}
+        self.c = _lib.FactGroup()
+        self.arena: Optional[torch.Tensor] = None
         self.n = 0
-        self.pairs = None          # keeps the sorted (key, src) storage alive
-        self.keys = self.srcs = 0  # device pointers into ``pairs``
-        self.uniq = self.seg_of = self.n_unique = None
-        self.cap = 1
-        self.ids_u: List[torch.Tensor] = []
-        self.arr_u: List[torch.Tensor] = []
-        self.P: Optional[torch.Tensor] = None
-        self.fold: Dict[str, tuple] = {}
         self.n_fwd = 0             # forwards that will get a gradient
         self.n_bwd = 0
-        self.dz: Dict[int, tuple] = {}
-        self.acc: Optional[dict] = None   # dW_item, dW_user, db_item, db_user, dWmm{}, dbmm{}
-        self.g_rows: Optional[torch.Tensor] = None
+        self.acc: Optional[dict] = None   # dW_item, dW_user, db_item, db_user, dWmm{}, dbmm{} + the C struct
         self.done = False
+        self.pool: Optional[list] = None  # the engine's free-arena list; the arena goes back when the group dies
+
+    def release(self):
+        """Hand the arena back for the next group (all work is stream-ordered, so reuse needs no event)."""
+        if self.arena is not None and self.pool is not None:
+            self.pool.append(self.arena)
+        self.arena = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    # -- views for tests / the slow merge path (no copies) -------------------------------------------
+    def _view(self, ptr: int, shape, dtype) -> torch.Tensor:
+        off = ptr - self.arena.data_ptr()
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return self.arena[off:off + nbytes].view(dtype).view(shape)
+
+    @property
+    def n_unique(self) -> torch.Tensor:
+        return self._view(self.c.n_unique, (1,), torch.int32)
+
+    @property
+    def uniq(self) -> torch.Tensor:
+        return self._view(self.c.uniq, (self.c.cap,), torch.int32)
+
+    def rows(self, which: str = "G") -> torch.Tensor:
+        return self._view(getattr(self.c, which), (self.c.cap, self.c.H), torch.float32)
 
 
 class FactoredEngine(EmbeddingEngine):
@@ -67,7 +93,7 @@ class FactoredEngine(EmbeddingEngine):
         self.current: Optional[FactGroup] = None   # group made by prefetch(), consumed by the next forwards
         self.ready: List[FactGroup] = []           # groups whose row gradients wait for fused_step
         full = layout.calls[True]
-        self._dnn_struct = Dnn()
+        self._prm = _lib.FactParams()
         seen = set()
         for s in full.slots:
             if s.kind == KIND_MM:
@@ -75,94 +101,123 @@ class FactoredEngine(EmbeddingEngine):
             if s.table in seen:
                 raise ValueError("a table feeding two slots cannot be factored")
             seen.add(s.table)
-            self._dnn_struct.table_side[s.table] = s.side
-            self._dnn_struct.table_col[s.table] = s.col
+            self._prm.dnn.table_side[s.table] = s.side
+            self._prm.dnn.table_col[s.table] = s.col
         self._mm_slots = [s for s in full.slots if s.kind == KIND_MM]
-        # call templates with every slot at column 0 of its side: the "concat gradient" of the reduction is dZ [T, H]
-        self._call0: Dict[bool, Call] = {}
-        for inc in (True, False):
-            c = Call()
-            C.memmove(C.addressof(c), C.addressof(self._structs._call_tmpl[inc]), C.sizeof(Call))
-            for i in range(c.n_slots):
-                c.slots[i].col = 0
-            self._call0[inc] = c
+        if len(self._mm_slots) > _lib.MAX_MM:
+            raise ValueError(f"at most {_lib.MAX_MM} mm features")
+        self._prm.n_mm = len(self._mm_slots)
+        for f, s in enumerate(self._mm_slots):
+            self._prm.mm[f].mm_dim, self._prm.mm[f].col = s.mm_dim, s.col
+        self._prm_key = None
+        self._prm_fresh = False
+        self._tab_memo: Dict[bool, object] = {}
+        self._arena_pool: List[torch.Tensor] = []
 
-    # ------------------------------------------------------------------ structs
-    def _dnn(self) -> Dnn:
-        d = self._dnn_struct
-        wi = self.dnn["item"].weight.data
-        wu = self.dnn["user"].weight.data
-        for w in (wi, wu):
+    # ------------------------------------------------------------------ structs: pointers are re-read once per group
+    def _table_array(self, state: bool = False, grads=None):
+        """Parameter pointers are re-validated when a group is prepared (and at the row update), not on each of the
+        ~8 C calls of a step: reading 24 ``.data_ptr()`` per call was 0.2 ms of host time per step."""
+        if grads is not None:
+            return super()._table_array(state, grads)
+        hit = self._tab_memo.get(state)
+        if hit is None:
+            hit = self._tab_memo[state] = super()._table_array(state)
+        return hit
+
+    def _params(self) -> "_lib.FactParams":
+        if self._prm_fresh:
+            return self._prm
+        self._prm_fresh = True
+        p = self._prm
+        wi, wu = self.dnn["item"].weight.data, self.dnn["user"].weight.data
+        bi, bu = self.dnn["item"].bias.data, self.dnn["user"].bias.data
+        key = (wi.data_ptr(), wu.data_ptr(), bi.data_ptr(), bu.data_ptr()) + tuple(
+            self.mm[s.name].weight.data.data_ptr() for s in self._mm_slots)
+        if key == self._prm_key:
+            return p
+        for w in (wi, wu, bi, bu):
             if w.dtype != torch.float32 or not w.is_contiguous():
-                raise TypeError("itemdnn / userdnn weights must be contiguous float32")
-        d.w_item, d.item_ld = wi.data_ptr(), wi.stride(0)
-        d.w_user, d.user_ld = wu.data_ptr(), wu.stride(0)
-        return d
-
-    def _dz_call(self, pb: PackedBatch, dz_item: torch.Tensor, dz_user: Optional[torch.Tensor], out: Call) -> Call:
-        C.memmove(C.addressof(out), C.addressof(self._call0[pb.include_user]), C.sizeof(Call))
-        out.T = pb.T
-        out.item_cat, out.item_ld = dz_item.data_ptr(), self.layout.H
-        if dz_user is not None:
-            out.user_cat, out.user_ld = dz_user.data_ptr(), self.layout.H
-        out.cat_dtype = _lib.DTYPE_F32
-        return out
+                raise TypeError("itemdnn / userdnn parameters must be contiguous float32")
+        p.dnn.w_item, p.dnn.item_ld = wi.data_ptr(), wi.stride(0)
+        p.dnn.w_user, p.dnn.user_ld = wu.data_ptr(), wu.stride(0)
+        p.b_item, p.b_user = bi.data_ptr(), bu.data_ptr()
+        for f, s in enumerate(self._mm_slots):
+            lin = self.mm[s.name]
+            w = lin.weight.data
+            if w.dtype != torch.float32 or not w.is_contiguous():
+                raise TypeError("emb_transform weight must be contiguous float32")
+            p.mm[f].w = w.data_ptr()
+            p.mm[f].b = None if lin.bias is None else lin.bias.data.data_ptr()
+        self._prm_key = key
+        return p
 
     # ------------------------------------------------------------------ group preparation (value independent)
     def prepare(self, pbs: Sequence[PackedBatch]) -> FactGroup:
-        """keys -> sort -> dedup -> id remap for the calls of one group. Independent of table VALUES."""
+        """keys -> sort -> dedup -> id remap for the calls of one group (ONE C call). Independent of table VALUES."""
         self._require_cuda()
+        self._tab_memo.clear()       # re-read the parameter pointers for this group
+        self._prm_fresh = False
         lay, dev = self.layout, self._device()
         g = FactGroup(pbs)
         if len(g.pbs) > _lib.MAX_CALLS:
             raise ValueError(f"at most {_lib.MAX_CALLS} calls per group")
-        calls = []
-        for pb in g.pbs:
-            cl = lay.calls[pb.include_user]
-            di = torch.empty((0, cl.item_dim), device=dev)
-            du = torch.empty((0, max(cl.user_dim, 1)), device=dev) if pb.include_user else None
-            calls.append((pb, di, du))
-        structs, g.keys, g.srcs, g.n, _ = self._sorted_pairs(calls)
-        g.pairs = self._ws.pop("pairs")
-        n = g.n
-        g.cap = cap = max(n, 1)
-        g.uniq = torch.empty(cap, dtype=torch.int32, device=dev)
-        seg_off = torch.empty(cap + 1, dtype=torch.int32, device=dev)
-        g.seg_of = torch.empty(cap, dtype=torch.int32, device=dev)
-        g.n_unique = torch.zeros(1, dtype=torch.int32, device=dev)
-        ws = self._buf("dedup_ws", self.lib.tgr_dedup_workspace_bytes(n), dev)
-        e0 = self._t0()
-        check(self.lib.tgr_dedup(g.keys, n, g.uniq.data_ptr(), seg_off.data_ptr(), g.seg_of.data_ptr(),
-                                 g.n_unique.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "tgr_dedup")
-        self._t1("dedup", e0)
-        self.launches += 4
-        # ids -> 1 + unique index: one scatter over the sorted pairs for every SINGLE slot of every call
-        e0 = self._t0()
-        ptrs = (C.c_void_p * len(g.pbs))()
+        c = g.c
+        c.n_calls, c.H, c.key_bits, c.n_mm = len(g.pbs), lay.H, lay.key_bits, len(self._mm_slots)
+        g.n = c.n = sum(pb.n_valid for pb in g.pbs)
+        x_dt = None
+        for f, s in enumerate(self._mm_slots):
+            c.mm_dim[f] = s.mm_dim
         for i, pb in enumerate(g.pbs):
-            o = torch.zeros_like(pb.ids)
-            g.ids_u.append(o)
-            ptrs[i] = o.data_ptr()
-        if n:
-            check(self.lib.tgr_remap_scatter(g.srcs, g.seg_of.data_ptr(), n, None, structs, len(g.pbs), ptrs, _stream()),
-                  "tgr_remap_scatter")
-            self.launches += 1
-        for pb in g.pbs:   # array values (a token may hold several): searching remap, they are few
             cl = lay.calls[pb.include_user]
-            arr_r = torch.zeros_like(pb.arr_val)
-            for s in cl.slots:
-                if s.kind != KIND_ARRAY or pb.arr_nnz[s.src] == 0:
-                    continue
-                kb1 = (C.c_uint32 * 1)(lay.tables[s.table].key_base)
-                rw1 = (C.c_int32 * 1)(lay.tables[s.table].rows)
-                off = 4 * pb.arr_begin[s.src]
-                check(self.lib.tgr_remap_ids(pb.arr_val.data_ptr() + off, pb.arr_nnz[s.src], 1, kb1, rw1, g.uniq.data_ptr(),
-                                             g.n_unique.data_ptr(), None, arr_r.data_ptr() + off, _stream()),
-                      "tgr_remap_ids(array)")
-                self.launches += 1
-            g.arr_u.append(arr_r)
-        self._t1("remap", e0)
+            if pb.ids.dtype != torch.int32 or not pb.ids.is_contiguous() or tuple(pb.ids.shape) != (pb.T, cl.n_single):
+                raise TypeError("PackedBatch.ids must be contiguous int32 [T, n_single]")
+            self._structs.call(pb, pb.ids, None, _lib.DTYPE_F32, None, out=c.calls[i])
+            c.calls[i].item_cat = None
+            for f, s in enumerate(self._mm_slots):
+                x = pb.mm_x[s.src]
+                if not x.is_contiguous() or tuple(x.shape) != (pb.T, s.mm_dim):
+                    raise TypeError(f"mm input {s.name} must be contiguous [T, {s.mm_dim}]")
+                if x_dt is None:
+                    x_dt = x.dtype
+                elif x.dtype != x_dt:
+                    raise TypeError("all mm inputs of a group must share one dtype")
+                c.mm_x[i][f] = x.data_ptr()
+        c.mm_x_dtype = _lib.DTYPE_F32 if x_dt is None else self._dt_code(x_dt)
+        nt = len(self.tables)
+        nbytes = self.lib.tgr_fact_group_bytes(C.byref(c), nt)
+        if nbytes == 0:
+            check(-1, "tgr_fact_group_bytes")
+        g.arena = self._take_arena(nbytes, dev)
+        g.pool = self._arena_pool
+        e0 = self._t0()
+        check(self.lib.tgr_fact_prepare(self._table_array(), nt, C.byref(c), g.arena.data_ptr(), nbytes, _stream()),
+              "tgr_fact_prepare")
+        self._t1("fact_prepare", e0)
+        self.launches += 13 + 2 * len(g.pbs) + sum(1 for pb in g.pbs for z in pb.arr_nnz if z)
+        if _DEBUG:
+            got = int(g._view(c.n_valid, (1,), torch.int32).item())
+            if got != g.n:
+                raise _lib.TgrError(f"PackedBatch.n_valid mismatch: host {g.n}, device {got}")
         return g
+
+    def _take_arena(self, nbytes: int, dev) -> torch.Tensor:
+        """Arenas (~1.7 GB at C2) are recycled instead of going through the allocator every step."""
+        pool = self._arena_pool
+        best = None
+        for i, a in enumerate(pool):
+            if a.numel() >= nbytes and a.device == dev and (best is None or a.numel() < pool[best].numel()):
+                best = i
+        if best is not None:
+            return pool.pop(best)
+        if len(pool) >= 4:          # too-small leftovers: let the allocator have them back
+            pool.clear()
+        return torch.empty(int(nbytes * 1.15) + 4096, dtype=torch.uint8, device=dev)
+
+    @staticmethod
+    def _dt_code(dt: torch.dtype) -> int:
+        from .engine import _dtype_code
+        return _dtype_code(dt)
 
     def prefetch(self, pbs: Sequence[PackedBatch]) -> FactGroup:
         self.current = self.prepare(pbs)
@@ -174,174 +229,77 @@ class FactoredEngine(EmbeddingEngine):
             return g
         return self.prepare([pb])
 
-    # ------------------------------------------------------------------ value dependent: projection + mm fold
-    def _project(self, g: FactGroup):
-        lay, dev, H = self.layout, self._device(), self.layout.H
-        g.P = torch.empty((g.cap, H), dtype=torch.float32, device=dev)
-        tabs = self._table_array()
-        e0 = self._t0()
-        check(self.lib.tgr_fact_project_rows(tabs, len(self.tables), H, C.byref(self._dnn()), g.uniq.data_ptr(),
-                                             g.n_unique.data_ptr(), g.cap, g.P.data_ptr(), _stream()),
-              "tgr_fact_project_rows")
-        self._t1("fact_project_rows", e0)
-        self.launches += 1
-        wi = self.dnn["item"].weight.data
-        for s in self._mm_slots:
-            lin = self.mm[s.name]
-            w = lin.weight.data
-            b = lin.bias.data if lin.bias is not None else None
-            if w.dtype != torch.float32 or not w.is_contiguous():
-                raise TypeError("emb_transform weight must be contiguous float32")
-            M = torch.empty((H, s.mm_dim), dtype=torch.float32, device=dev)
-            c = torch.empty((H,), dtype=torch.float32, device=dev)
-            check(self.lib.tgr_fact_mm_fold(wi.data_ptr() + 4 * s.col, wi.stride(0), w.data_ptr(),
-                                            None if b is None else b.data_ptr(), H, s.mm_dim, M.data_ptr(), c.data_ptr(),
-                                            _stream()), "tgr_fact_mm_fold")
-            self.launches += 1
-            g.fold[s.name] = (M, c)
-
     # ------------------------------------------------------------------ forward of one call
-    def fact_forward(self, g: FactGroup, pb: PackedBatch):
-        """-> (out [T, H] fp32, mask [T, H/4] uint8)."""
-        lay, dev, H = self.layout, self._device(), self.layout.H
-        if g.P is None:
-            self._project(g)
-        i = g.index[id(pb)]
-        T = pb.T
-        cl = lay.calls[pb.include_user]
-        out = torch.empty((T, H), dtype=torch.float32, device=dev)
-        mask = torch.empty((T, H // 4), dtype=torch.uint8, device=dev)
-        mmz = []
-        for s in cl.slots:
-            if s.kind != KIND_MM:
-                continue
-            x = pb.mm_x[s.src]
-            if not x.is_contiguous() or x.shape != (T, s.mm_dim):
-                raise TypeError(f"mm input {s.name} must be contiguous [T, {s.mm_dim}]")
-            M, c = g.fold[s.name]
-            z = torch.empty((T, H), dtype=torch.float32, device=dev)
-            e0 = self._t0()
-            check(self.lib.tgr_mm_proj_fwd(x.data_ptr(), self._dt(x), T, s.mm_dim, M.data_ptr(), c.data_ptr(), H, z.data_ptr(),
-                                           H, _lib.DTYPE_F32, _stream()), "tgr_mm_proj_fwd")
-            self._t1("mm_proj_fwd", e0)
-            self.launches += 1
-            mmz.append(z)
-        mm_ptrs = (C.c_void_p * max(len(mmz), 1))(*[z.data_ptr() for z in mmz])
-        call = self._structs.call(pb, out, None, _lib.DTYPE_F32, None)
-        bi = self.dnn["item"].bias.data
-        bu = self.dnn["user"].bias.data if pb.include_user else None
+    def fact_forward(self, g: FactGroup, pb: PackedBatch) -> torch.Tensor:
+        """-> out [T, H] fp32 (the ReLU masks stay in the group's arena for the backward)."""
+        H = self.layout.H
+        out = torch.empty((pb.T, H), dtype=torch.float32, device=self._device())
+        n_kern = 1 + len(self._mm_slots) + (0 if g.c.projected else 1 + len(self._mm_slots))
         e0 = self._t0()
-        check(self.lib.tgr_fact_forward(C.byref(call), H, g.ids_u[i].data_ptr(),
-                                        g.arr_u[i].data_ptr() if g.arr_u[i].numel() else None, g.P.data_ptr(), mm_ptrs,
-                                        len(mmz), bi.data_ptr(), None if bu is None else bu.data_ptr(), out.data_ptr(),
-                                        mask.data_ptr(), _stream()), "tgr_fact_forward")
-        self._t1("fact_forward", e0)
-        self.launches += 1
-        return out, mask
-
-    @staticmethod
-    def _dt(x: torch.Tensor) -> int:
-        from .engine import _dtype_code
-        return _dtype_code(x.dtype)
+        check(self.lib.tgr_fact_call_forward(self._table_array(), len(self.tables), C.byref(self._params()), C.byref(g.c),
+                                             g.index[id(pb)], out.data_ptr(), _stream()), "tgr_fact_call_forward")
+        self._t1("fact_call_forward", e0)
+        self.launches += n_kern
+        return out
 
     # ------------------------------------------------------------------ backward of one call
     def _acc(self, g: FactGroup) -> dict:
+        """Zero-initialised gradient accumulators of the group's dense parameters: ONE flat buffer, viewed."""
         if g.acc is None:
             dev = self._device()
-            a = {"dW_item": torch.zeros_like(self.dnn["item"].weight.data),
-                 "db_item": torch.zeros_like(self.dnn["item"].bias.data),
-                 "dW_user": None, "db_user": None, "dWmm": {}, "dbmm": {}}
+            shapes = [("dW_item", self.dnn["item"].weight.shape), ("db_item", self.dnn["item"].bias.shape)]
             if any(pb.include_user for pb in g.pbs):
-                a["dW_user"] = torch.zeros_like(self.dnn["user"].weight.data)
-                a["db_user"] = torch.zeros_like(self.dnn["user"].bias.data)
+                shapes += [("dW_user", self.dnn["user"].weight.shape), ("db_user", self.dnn["user"].bias.shape)]
             for s in self._mm_slots:
                 lin = self.mm[s.name]
-                a["dWmm"][s.name] = torch.zeros_like(lin.weight.data)
-                a["dbmm"][s.name] = torch.zeros_like(lin.bias.data) if lin.bias is not None else None
+                shapes.append((f"dWmm/{s.name}", lin.weight.shape))
+                if lin.bias is not None:
+                    shapes.append((f"dbmm/{s.name}", lin.bias.shape))
+            sizes = [(k, sh, (sh.numel() + 63) // 64 * 64) for k, sh in shapes]
+            flat = torch.zeros(sum(z for _, _, z in sizes), dtype=torch.float32, device=dev)
+            a, o = {"dW_user": None, "db_user": None}, 0
+            for k, sh, z in sizes:
+                a[k] = flat[o:o + sh.numel()].view(sh)
+                o += z
+            cg = _lib.FactGrads()
+            cg.dW_item, cg.db_item = a["dW_item"].data_ptr(), a["db_item"].data_ptr()
+            if a["dW_user"] is not None:
+                cg.dW_user, cg.db_user = a["dW_user"].data_ptr(), a["db_user"].data_ptr()
+            for f, s in enumerate(self._mm_slots):
+                cg.dW_mm[f] = a[f"dWmm/{s.name}"].data_ptr()
+                b = a.get(f"dbmm/{s.name}")
+                cg.db_mm[f] = None if b is None else b.data_ptr()
+            a["c"] = cg
             g.acc = a
         return g.acc
 
-    def fact_backward(self, g: FactGroup, pb: PackedBatch, mask: torch.Tensor, d_out: torch.Tensor) -> bool:
-        """dZ + bias / mm gradients of one call; True when the group is now complete (group_backward may run)."""
-        lay, dev, H = self.layout, self._device(), self.layout.H
-        i = g.index[id(pb)]
-        T = pb.T
+    def fact_backward(self, g: FactGroup, pb: PackedBatch, d_out: torch.Tensor) -> bool:
+        """dZ + bias / mm gradients of one call; with the group's last gradient also the segmented reduce, the row
+        gradients and the DNN weight gradients (ONE C call). True when the group is complete."""
+        H = self.layout.H
         a = self._acc(g)
-        d_out = d_out.reshape(T, H)
+        d_out = d_out.reshape(pb.T, H)
         if d_out.dtype != torch.float32:
             d_out = d_out.float()
         if not d_out.is_contiguous():
             d_out = d_out.contiguous()
-        dz_item = torch.empty((T, H), dtype=torch.float32, device=dev)
-        dz_user = torch.empty((T, H), dtype=torch.float32, device=dev) if pb.include_user else None
-        ws = self._buf("relu_ws", self.lib.tgr_fact_relu_mask_workspace_bytes(T, H), dev)
-        e0 = self._t0()
-        check(self.lib.tgr_fact_relu_mask(d_out.data_ptr(), mask.data_ptr(), T, H, dz_item.data_ptr(),
-                                          None if dz_user is None else dz_user.data_ptr(), a["db_item"].data_ptr(),
-                                          None if dz_user is None else a["db_user"].data_ptr(), ws.data_ptr(), ws.numel(),
-                                          _stream()), "tgr_fact_relu_mask")
-        self._t1("fact_relu_mask", e0)
-        self.launches += 2
-        wi = self.dnn["item"].weight.data
-        for s in lay.calls[pb.include_user].slots:
-            if s.kind != KIND_MM:
-                continue
-            x = pb.mm_x[s.src]
-            lin = self.mm[s.name]
-            A = torch.empty((H, s.mm_dim), dtype=torch.float32, device=dev)
-            sv = torch.empty((H,), dtype=torch.float32, device=dev)
-            mws = self._buf("mm_bwd", self.lib.tgr_mm_proj_bwd_workspace_bytes(T, s.mm_dim, H), dev)
-            e0 = self._t0()
-            check(self.lib.tgr_mm_proj_bwd(x.data_ptr(), self._dt(x), T, s.mm_dim, dz_item.data_ptr(), H, _lib.DTYPE_F32, H,
-                                           A.data_ptr(), sv.data_ptr(), 0, mws.data_ptr(), mws.numel(), _stream()),
-                  "tgr_mm_proj_bwd")
-            dbm = a["dbmm"][s.name]
-            check(self.lib.tgr_fact_mm_chain_bwd(wi.data_ptr() + 4 * s.col, wi.stride(0), lin.weight.data.data_ptr(),
-                                                 None if lin.bias is None else lin.bias.data.data_ptr(), A.data_ptr(),
-                                                 sv.data_ptr(), H, s.mm_dim, a["dWmm"][s.name].data_ptr(),
-                                                 None if dbm is None else dbm.data_ptr(),
-                                                 a["dW_item"].data_ptr() + 4 * s.col, a["dW_item"].stride(0), _stream()),
-                  "tgr_fact_mm_chain_bwd")
-            self._t1("mm_proj_bwd", e0)
-            self.launches += 3
-        g.dz[i] = (dz_item, dz_user)
         g.n_bwd += 1
-        return g.n_bwd == g.n_fwd
-
-    def group_backward(self, g: FactGroup):
-        """Segmented sum of dZ rows per unique key, row gradients and DNN weight gradients of the whole group."""
-        lay, dev, H = self.layout, self._device(), self.layout.H
-        if len(g.dz) != len(g.pbs):
+        finish = g.n_bwd == g.n_fwd
+        if finish and g.n_bwd != len(g.pbs):
             raise RuntimeError("a prefetched group needs the gradient of every one of its calls "
-                               f"({len(g.dz)} of {len(g.pbs)} arrived); prefetch only the calls that reach the loss")
-        a = self._acc(g)
-        n = g.n
-        G = torch.empty((g.cap, H), dtype=torch.float32, device=dev)
-        if n:
-            structs = (Call * len(g.pbs))()
-            for i, pb in enumerate(g.pbs):
-                self._dz_call(pb, g.dz[i][0], g.dz[i][1], structs[i])
-            rws = self._buf("reduce_ws", self.lib.tgr_reduce_workspace_bytes(n, H), dev)
-            tabs = self._table_array()
-            e0 = self._t0()
-            check(self.lib.tgr_bwd_reduce(tabs, len(self.tables), H, structs, len(g.pbs), g.keys, g.srcs, n, 0,
-                                          g.seg_of.data_ptr(), G.data_ptr(), None, rws.data_ptr(), rws.numel(), _stream()),
-                  "tgr_bwd_reduce")
-            self._t1("bwd_reduce", e0)
-            self.launches += 2
-            fws = self._buf("fact_bwd_ws", self.lib.tgr_fact_backward_workspace_bytes(len(self.tables), H), dev)
-            e0 = self._t0()
-            check(self.lib.tgr_fact_unique_backward(tabs, len(self.tables), H, C.byref(self._dnn()), g.uniq.data_ptr(),
-                                                    g.n_unique.data_ptr(), g.cap, G.data_ptr(), a["dW_item"].data_ptr(),
-                                                    None if a["dW_user"] is None else a["dW_user"].data_ptr(),
-                                                    fws.data_ptr(), fws.numel(), _stream()), "tgr_fact_unique_backward")
-            self._t1("fact_unique_backward", e0)
-            self.launches += 2
-        g.g_rows = G
-        g.dz.clear()
-        g.done = True
-        if self.current is g:
-            self.current = None
+                               f"({g.n_bwd} of {len(g.pbs)} arrived); prefetch only the calls that reach the loss")
+        n_mm = len(self._mm_slots)
+        e0 = self._t0()
+        check(self.lib.tgr_fact_call_backward(self._table_array(), len(self.tables), C.byref(self._params()), C.byref(g.c),
+                                              g.index[id(pb)], d_out.data_ptr(), C.byref(a["c"]), 1 if finish else 0,
+                                              _stream()), "tgr_fact_call_backward")
+        self._t1("fact_call_backward", e0)
+        self.launches += 2 + 3 * n_mm + (4 if finish and g.n else 0)
+        if finish:
+            g.done = True
+            if self.current is g:
+                self.current = None
+        return finish
 
     def dense_from_rows(self, g: FactGroup) -> List[Optional[torch.Tensor]]:
         """Parity mode: dense [rows, H] gradients of the tables the group's calls index."""
@@ -352,8 +310,8 @@ class FactoredEngine(EmbeddingEngine):
             grads[t] = torch.zeros_like(self.tables[t].data)
         if g.n:
             tabs = self._table_array(grads=grads)
-            check(self.lib.tgr_scatter_rows(tabs, len(self.tables), lay.H, g.uniq.data_ptr(), g.g_rows.data_ptr(),
-                                            g.n_unique.data_ptr(), g.cap, _stream()), "tgr_scatter_rows")
+            check(self.lib.tgr_scatter_rows(tabs, len(self.tables), lay.H, g.c.uniq, g.c.G, g.c.n_unique, g.c.cap, _stream()),
+                  "tgr_scatter_rows")
             self.launches += 1
         return grads
 
@@ -365,6 +323,7 @@ class FactoredEngine(EmbeddingEngine):
             return 0
         self._require_cuda()
         self.ensure_state()
+        self._tab_memo.pop(True, None)
         self.step += 1
         H, dev = self.layout.H, self._device()
         adam = make_adam(lr, betas[0], betas[1], eps, weight_decay, self.step, grad_scale)
@@ -373,10 +332,11 @@ class FactoredEngine(EmbeddingEngine):
             g = groups[0]
             if g.n:
                 e0 = self._t0()
-                check(self.lib.tgr_adam_rows(tabs, len(self.tables), H, g.uniq.data_ptr(), g.g_rows.data_ptr(),
-                                             g.n_unique.data_ptr(), g.cap, C.byref(adam), _stream()), "tgr_adam_rows")
+                check(self.lib.tgr_adam_rows(tabs, len(self.tables), H, g.c.uniq, g.c.G, g.c.n_unique, g.c.cap, C.byref(adam),
+                                             _stream()), "tgr_adam_rows")
                 self._t1("adam_rows", e0)
                 self.launches += 1
+            g.release()
             return g.n
         # several groups touched the step (per-call protocol): merge their (key, row gradient) lists in group order,
         # then ONE update per row. Slow path: one host read of the unique counts.
@@ -397,11 +357,13 @@ class FactoredEngine(EmbeddingEngine):
             cs = structs[i]
             cs.T, cs.n_slots, cs.n_single = max(c, 1), 1, 1
             cs.slots[0].kind, cs.slots[0].side, cs.slots[0].col, cs.slots[0].table, cs.slots[0].src = 0, 0, 0, 0, 0
-            cs.item_cat, cs.item_ld, cs.cat_dtype = g.g_rows.data_ptr(), H, _lib.DTYPE_F32
+            cs.item_cat, cs.item_ld, cs.cat_dtype = g.c.G, H, _lib.DTYPE_F32
         rws = self._buf("reduce_ws", self.lib.tgr_reduce_workspace_bytes(R, H), dev)
         check(self.lib.tgr_bwd_reduce(tabs, len(self.tables), H, structs, len(groups), keys_o.data_ptr(), srcs_o.data_ptr(), R,
                                       1, None, None, C.byref(adam), rws.data_ptr(), rws.numel(), _stream()), "tgr_bwd_reduce")
         self.launches += 8
+        for g in groups:
+            g.release()
         return R
 
 
@@ -412,8 +374,8 @@ class FactoredFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine: FactoredEngine, pb: PackedBatch, needs_grad: bool, *params):
         g = engine._group_of(pb)
-        out, mask = engine.fact_forward(g, pb)
-        ctx.engine, ctx.pb, ctx.group, ctx.mask = engine, pb, g, mask
+        out = engine.fact_forward(g, pb)
+        ctx.engine, ctx.pb, ctx.group = engine, pb, g
         ctx.n_params = len(params)
         if needs_grad:      # (grad mode is always off inside Function.forward: the caller tells)
             g.n_fwd += 1
@@ -423,9 +385,8 @@ class FactoredFn(torch.autograd.Function):
     def backward(ctx, d_out):
         eng, pb, g = ctx.engine, ctx.pb, ctx.group
         grads: List[Optional[torch.Tensor]] = [None] * ctx.n_params
-        if not eng.fact_backward(g, pb, ctx.mask, d_out):
+        if not eng.fact_backward(g, pb, d_out):
             return (None, None, None, *grads)
-        eng.group_backward(g)
         a = g.acc
         n_t = len(eng.tables)
         names = list(eng.layout.item_emb_feat)
@@ -436,9 +397,10 @@ class FactoredFn(torch.autograd.Function):
             for i in range(n_t):
                 if ctx.needs_input_grad[3 + i]:
                     grads[i] = dense[i]
+            g.release()
         for j, k in enumerate(names):
-            grads[n_t + 2 * j] = a["dWmm"][k]
-            grads[n_t + 2 * j + 1] = a["dbmm"][k]
+            grads[n_t + 2 * j] = a[f"dWmm/{k}"]
+            grads[n_t + 2 * j + 1] = a.get(f"dbmm/{k}")
         o = n_t + 2 * len(names)
         grads[o], grads[o + 1] = a["dW_item"], a["db_item"]
         grads[o + 2], grads[o + 3] = a["dW_user"], a["db_user"]

@@ -198,6 +198,68 @@ def stage_pinned(layout: FeatureLayout, pc: PackedCall, mm_dtype: torch.dtype = 
     return HostPacked(pc.B, pc.L, pc.include_user, ints, offs, sizes, pc.ids.shape[1], n_arr, begins, nnz, mm, pc.n_valid)
 
 
+class HostPrefetcher:
+    """Double-buffered host -> device feed (what a pin_memory DataLoader + a copy stream give a training loop):
+    ``submit(host_calls)`` enqueues the H2D copies of one step's pinned ``HostPacked`` calls on a side stream into
+    PERSISTENT device staging slots (no allocator traffic in the loop), ``take()`` makes the compute stream wait for
+    the oldest submitted step and returns its ``PackedBatch`` list (views of the slot). Submitting step k+1 before
+    running step k overlaps its copies with step k's kernels. A slot is rewritten only after the step that read it
+    has finished on the compute stream (event recorded at the following ``take``)."""
+
+    def __init__(self, device, slots: int = 3):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [{"ints": [], "mm": [], "done": None} for _ in range(slots)]
+        self.next = 0
+        self.queue = []
+        self.last = None
+
+    @staticmethod
+    def _fit(lst, i, n, dtype, device):
+        while len(lst) <= i:
+            lst.append(None)
+        if lst[i] is None or lst[i].numel() < n or lst[i].dtype != dtype:
+            lst[i] = torch.empty(int(n * 1.1) + 64, dtype=dtype, device=device)
+        return lst[i]
+
+    def submit(self, host_calls: Sequence["HostPacked"]):
+        slot = self.slots[self.next]
+        self.next = (self.next + 1) % len(self.slots)
+        if slot["done"] is not None:
+            slot["done"].synchronize()          # the step that read this slot is long finished (slots - 1 steps ago)
+        pbs = []
+        with torch.cuda.stream(self.stream):
+            j = 0
+            for i, hp in enumerate(host_calls):
+                n = hp.ints.numel()
+                dev = self._fit(slot["ints"], i, n, torch.int32, self.device)[:n]
+                dev.copy_(hp.ints, non_blocking=True)
+                o, s, T = hp.offs, hp.sizes, hp.T
+                mm = []
+                for x in hp.mm_x:
+                    d = self._fit(slot["mm"], j, x.numel(), x.dtype, self.device)[:x.numel()].view(x.shape)
+                    d.copy_(x, non_blocking=True)
+                    mm.append(d)
+                    j += 1
+                pbs.append(PackedBatch(hp.B, hp.L, hp.include_user, dev[o[0]:o[0] + s[0]].view(T, hp.n_single),
+                                       dev[o[1]:o[1] + s[1]].view(hp.n_arr, T + 1), dev[o[2]:o[2] + s[2]],
+                                       dev[o[3]:o[3] + s[3]], hp.arr_begin, hp.arr_nnz, mm, hp.n_valid, hp.nbytes))
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.queue.append((pbs, ev, slot))
+
+    def take(self) -> List[PackedBatch]:
+        cur = torch.cuda.current_stream(self.device)
+        if self.last is not None:               # everything that read the previous slot is enqueued by now
+            done = torch.cuda.Event()
+            done.record(cur)
+            self.last["done"] = done
+        pbs, ev, slot = self.queue.pop(0)
+        cur.wait_event(ev)
+        self.last = slot
+        return pbs
+
+
 class _PinnedPool:
     """Reusable pinned staging buffers. cudaHostAlloc costs milliseconds, so buffers are recycled; a buffer is
     handed out again only after the event recorded behind its last H2D copy has completed."""

@@ -49,6 +49,29 @@ def test_struct_layouts_match_header(lib):
     assert ctypes.sizeof(_lib.Call) == 16 + 640 + 8 + 64 + 64 + 32 + 32 + 8 + 8 + 8 + 8 + 8 + 8 + 8
 
 
+def test_ctypes_structs_match_the_c_compiler(lib, tmp_path):
+    """sizeof / key offsets of every struct in include/tgr_embed.h as gcc lays them out == the ctypes mirrors."""
+    import subprocess
+    names = {"tgr_table_t": _lib.Table, "tgr_slot_t": _lib.Slot, "tgr_call_t": _lib.Call, "tgr_adam_t": _lib.Adam,
+             "tgr_dnn_t": _lib.Dnn, "tgr_mm_feat_t": _lib.MmFeat, "tgr_fact_params_t": _lib.FactParams,
+             "tgr_fact_grads_t": _lib.FactGrads, "tgr_fact_group_t": _lib.FactGroup}
+    offs = [("tgr_fact_group_t", "calls"), ("tgr_fact_group_t", "mm_x"), ("tgr_fact_group_t", "cap"),
+            ("tgr_fact_group_t", "P"), ("tgr_fact_group_t", "mmz"), ("tgr_fact_group_t", "ws_bytes"),
+            ("tgr_fact_group_t", "n_backward"), ("tgr_fact_params_t", "b_item"), ("tgr_fact_params_t", "n_mm"),
+            ("tgr_call_t", "err_flag"), ("tgr_dnn_t", "table_col")]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "tgr_embed.h"', 'int main(void) {']
+    src += [f'printf("%zu\\n", sizeof({n}));' for n in names]
+    src += [f'printf("%zu\\n", offsetof({n}, {f}));' for n, f in offs]
+    src += ['return 0; }']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(t) for t in names.values()] + [getattr(names[n], f).offset for n, f in offs]
+    assert got == want, list(zip(list(names) + offs, got, want))
+
+
 def test_size_queries_work_without_gpu(lib):
     assert lib.tgr_build_keys_workspace_bytes(1 << 20) > 0
     assert lib.tgr_dedup_workspace_bytes(1 << 20) > 0
