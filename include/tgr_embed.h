@@ -247,7 +247,7 @@ int tgr_fact_forward(const tgr_call_t* call, int H, const int32_t* ids_u, const 
 
 /* dz_item = d_out * mask_item, dz_user = d_out * mask_user (NULL without users); db_* += column sums
  * (autograd of relu + the Linear bias, model.py:303-307). Optional fused mm statistics for ONE 32-wide mm feature
- * ('81'): mm_A [H, 32] = dz_item^T . mm_x and mm_s [H] = colsum(dz_item), from the same pass (mm_x NULL = off). */
+ * ('81'): mm_A [H, 32] += dz_item^T . mm_x and mm_s [H] += colsum(dz_item), from the same pass (mm_x NULL = off). */
 size_t tgr_fact_relu_mask_workspace_bytes(int64_t T, int H);
 int tgr_fact_relu_mask(const float* d_out, const uint8_t* mask, int64_t T, int H, float* dz_item, float* dz_user,
                        float* db_item, float* db_user, const void* mm_x, int mm_x_dtype, int mm_dim, float* mm_A,

@@ -103,7 +103,7 @@ static int check_group(const tgr_fact_group_t* g) {
   TGR_REQUIRE(g != nullptr, "group is NULL");
   TGR_REQUIRE(g->n_calls > 0 && g->n_calls <= TGR_MAX_CALLS, "n_calls=%d out of range", g->n_calls);
   TGR_REQUIRE(g->H == 32 || g->H == 64 || g->H == 128, "the factored path supports H in {32, 64, 128} (H=%d)", g->H);
-  TGR_REQUIRE(g->n >= 0 && g->n < (1ll << 31), "n out of range");
+  TGR_REQUIRE(g->n >= 0 && g->n < (1ll << 31) && g->n * (g->H / 4) < (1ll << 31), "n out of range");
   TGR_REQUIRE(g->n_mm >= 0 && g->n_mm <= TGR_MAX_MM, "n_mm out of range");
   return 0;
 }
@@ -124,6 +124,10 @@ extern "C" int tgr_fact_prepare(const tgr_table_t* tables, int n_tables, tgr_fac
   g->projected = 0;
   g->n_backward = 0;
   cudaStream_t st = (cudaStream_t)stream;
+  for (int f = 0; f < g->n_mm; ++f) {   // A = dz^T x and s = colsum(dz) accumulate over the group's calls
+    cudaMemsetAsync(g->mm_A[f], 0, (size_t)g->H * g->mm_dim[f] * sizeof(float), st);
+    cudaMemsetAsync(g->mm_s[f], 0, (size_t)g->H * sizeof(float), st);
+  }
   if (int rc = tgr_bwd_build_keys(tables, n_tables, g->calls, g->n_calls, g->keys_in, g->srcs_in, g->n_valid, g->ws,
                                   g->ws_bytes, stream)) return rc;
   if (int rc = tgr_sort_pairs(g->keys_in, g->srcs_in, g->keys, g->srcs, g->n, g->key_bits, g->ws, g->ws_bytes, stream))
@@ -188,19 +192,23 @@ extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, c
                                     fused >= 0 ? 32 : 0, fused >= 0 ? g->mm_A[fused] : nullptr,
                                     fused >= 0 ? g->mm_s[fused] : nullptr, g->ws, g->ws_bytes, stream)) return rc;
     for (int f = 0; f < g->n_mm; ++f) {
-      const tgr_mm_feat_t& m = prm->mm[f];
-      if (gr->dW_mm[f] == nullptr) continue;
-      if (f != fused)
-        if (int rc = tgr_mm_proj_bwd(g->mm_x[c][f], g->mm_x_dtype, cl.T, m.mm_dim, g->dz_item[c], H, TGR_DTYPE_F32, H,
-                                     g->mm_A[f], g->mm_s[f], 0, g->ws, g->ws_bytes, stream)) return rc;
-      TGR_REQUIRE(gr->dW_item != nullptr, "dW_item is NULL");
-      if (int rc = tgr_fact_mm_chain_bwd(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, g->mm_A[f], g->mm_s[f], H,
-                                         m.mm_dim, gr->dW_mm[f], gr->db_mm[f], gr->dW_item + m.col, prm->dnn.item_ld,
-                                         stream)) return rc;
+      if (gr->dW_mm[f] == nullptr || f == fused) continue;
+      if (int rc = tgr_mm_proj_bwd(g->mm_x[c][f], g->mm_x_dtype, cl.T, prm->mm[f].mm_dim, g->dz_item[c], H, TGR_DTYPE_F32,
+                                   H, g->mm_A[f], g->mm_s[f], 1, g->ws, g->ws_bytes, stream)) return rc;
     }
     g->n_backward++;
   }
-  if (!finish || g->n == 0) return 0;
+  if (!finish) return 0;
+  // the chain rule through emb_transform / the item-DNN block is linear in (A, s): ONCE per group on the sums
+  for (int f = 0; f < g->n_mm; ++f) {
+    const tgr_mm_feat_t& m = prm->mm[f];
+    if (gr->dW_mm[f] == nullptr) continue;
+    TGR_REQUIRE(gr->dW_item != nullptr, "dW_item is NULL");
+    if (int rc = tgr_fact_mm_chain_bwd(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, g->mm_A[f], g->mm_s[f], H,
+                                       m.mm_dim, gr->dW_mm[f], gr->db_mm[f], gr->dW_item + m.col, prm->dnn.item_ld,
+                                       stream)) return rc;
+  }
+  if (g->n == 0) return 0;
   // "concat gradient" of the reduction = dZ [T, H]: every slot at column 0 of its side, row pitch H
   tgr_call_t calls[TGR_MAX_CALLS];
   for (int i = 0; i < g->n_calls; ++i) {

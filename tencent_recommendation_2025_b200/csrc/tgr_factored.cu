@@ -26,9 +26,8 @@
 namespace tgr {
 
 constexpr int kFT = 256;          // threads per CTA
-constexpr int kRT = 64;           // unique rows per tile
-constexpr int kRowsGridFwd = 4 * kNumSMs;   // 35 KB smem, 64 regs: 4 CTAs / SM (H = 64)
-constexpr int kRowsGridBwd = 3 * kNumSMs;   // 52 KB smem, 80 regs: 3 CTAs / SM
+constexpr int kRowsGridFwd = 6 * kNumSMs;   // H = 64: 35 KB smem, 64 threads x 163 regs -> 6 CTAs / SM
+constexpr int kRowsGridBwd = 4 * kNumSMs;   // H = 64: 52 KB smem, 64 threads x 225 regs -> 4 CTAs / SM
 
 struct FactParams {
   const float* w[TGR_MAX_TABLES];       // table rows
@@ -40,6 +39,15 @@ struct FactParams {
   int32_t n_tables;
 };
 
+// 16-byte global -> shared copy that bypasses the register file (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ void fma4(float4& a, float x, const float4& w) {
   a.x = fmaf(x, w.x, a.x); a.y = fmaf(x, w.y, a.y); a.z = fmaf(x, w.z, a.z); a.w = fmaf(x, w.w, a.w);
 }
@@ -48,59 +56,78 @@ __device__ __forceinline__ void fma4(float4& a, float x, const float4& w) {
 // MODE 1: PG[u] (holding G[u]) <- G[u] . W_s  in place, and the CTA's split-K partial of dW_s = sum_u G[u]^T row[u]
 // Persistent: CTA b owns the contiguous tile range [b*tpc, (b+1)*tpc) of the sorted unique list, so the rows of one
 // table are consecutive and its H x H weight block / dW accumulator stay on chip across tiles.
+// fp32 FFMA with 8 x 8 register tiles: 4 LDS.128 feed 64 FMAs, which balances the shared-memory pipe against the
+// FMA pipe (the first version used 4 x 4 tiles and was LDS-bound at ~30 % of the FFMA rate, profiles/README.md).
+// threads = (H/8) column groups x (RT/8) row groups over an RT-row tile; the dW GEMM uses (H/8)^2 8x8 tiles and
+// RG interleaved row groups whose partials are combined in fixed order by fact_dw_reduce_kernel. Measured on
+// B200 (tools/rows_bench.py, 227 k rows): 67 us forward / 130 us backward; with the loads or the GEMMs disabled the
+// phases take 25 / 43 us — the GEMM loop runs at ~55 % of the FFMA rate with the LDS and FMA pipes both saturated.
+template <int H>
+struct RowsCfg {
+  static constexpr int RT = H == 64 ? 64 : 128;   // unique rows per tile (64-row tiles: more, smaller CTAs per SM in
+                                                  // different load / compute phases)
+  static constexpr int TXN = H / 8;               // column groups
+  static constexpr int TYN = RT / 8;              // row groups
+  static constexpr int NT = TXN * TYN;            // threads
+  static constexpr int DT = (H / 8) * (H / 8);
+  static constexpr int RG = NT / DT;
+  static constexpr int LD = H + 4;
+  static_assert(NT % DT == 0 && RG >= 1, "tile shape");
+};
+
 template <int H, int MODE>
-__global__ void __launch_bounds__(kFT) fact_rows_kernel(const __grid_constant__ FactParams p,
-                                                        const uint32_t* __restrict__ uniq,
-                                                        const int32_t* __restrict__ n_unique_dev,
-                                                        float* __restrict__ PG, float* __restrict__ dw_part) {
-  constexpr int NV = H > 64 ? H / 64 : 1;   // float4 column groups per thread
-  constexpr int TXN = H / (4 * NV);         // threads along the output columns
-  constexpr int TYN = kFT / TXN;
-  constexpr int RPT = kRT / TYN;            // rows per thread of the [kRT, H] row GEMM
-  constexpr int HPT = H / TYN;              // dW rows per thread
-  constexpr int LD = H + 4;
-  static_assert(RPT >= 1 && HPT >= 1, "tile shape");
+__global__ void __launch_bounds__(RowsCfg<H>::NT) fact_rows_kernel(const __grid_constant__ FactParams p,
+                                                          const uint32_t* __restrict__ uniq,
+                                                          const int32_t* __restrict__ n_unique_dev,
+                                                          float* __restrict__ PG, float* __restrict__ dw_part) {
+  using Cfg = RowsCfg<H>;
+  constexpr int NT = Cfg::NT, TXN = Cfg::TXN, TYN = Cfg::TYN, DT = Cfg::DT, RG = Cfg::RG, LD = Cfg::LD, HH = H / 2;
+  constexpr int kRT = Cfg::RT;
   extern __shared__ __align__(16) float sm[];
   float* Ws = sm;              // [H][LD]   MODE 0: Ws[k][h] = W[h][col+k]   MODE 1: Ws[h][k] = W[h][col+k]
   float* Xs = Ws + H * LD;     // [kRT][LD] MODE 0: table rows               MODE 1: G rows
   float* Rs = Xs + kRT * LD;   // [kRT][LD] MODE 1: table rows
   __shared__ uint32_t s_key[kRT];
-  const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
+  const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;          // row GEMM: rows ty + TYN i, cols tx*4 (+ H/2)
+  const int hx = tid % TXN, hy = (tid % DT) / TXN, rg = tid / DT;        // dW GEMM: h = hy*4 (+H/2), k = hx*4 (+H/2)
   const int U = *n_unique_dev;
   const int n_tiles = (U + kRT - 1) / kRT;
   const int tpc = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tile_a = blockIdx.x * tpc, tile_b = min(n_tiles, tile_a + tpc);
   int cur_t = -1;
-  float4 dw[HPT][NV];
+  float4 dw[8][2];
 #pragma unroll
-  for (int i = 0; i < HPT; ++i)
-#pragma unroll
-    for (int v = 0; v < NV; ++v) dw[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < 8; ++i) dw[i][0] = dw[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   auto flush_dw = [&](int t) {
-    float* dst = dw_part + (size_t)(blockIdx.x + t) * H * H;   // (cta, table) pairs are monotone => unique slots
+    float* dst = dw_part + ((size_t)(blockIdx.x + t) * RG + rg) * H * H;   // (cta, table) pairs are monotone => unique slots
 #pragma unroll
-    for (int i = 0; i < HPT; ++i)
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        *reinterpret_cast<float4*>(dst + (ty * HPT + i) * H + tx * 4 + 64 * v) = dw[i][v];
-        dw[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+    for (int i = 0; i < 8; ++i) {
+      const int h = (i < 4 ? 0 : HH) + hy * 4 + (i & 3);
+      *reinterpret_cast<float4*>(dst + h * H + hx * 4) = dw[i][0];
+      *reinterpret_cast<float4*>(dst + h * H + HH + hx * 4) = dw[i][1];
+      dw[i][0] = dw[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   };
 
   for (int tile = tile_a; tile < tile_b; ++tile) {
     const int r0 = tile * kRT;
     const int nr = min(kRT, U - r0);
     __syncthreads();
-    if (tid < kRT) s_key[tid] = tid < nr ? __ldg(uniq + r0 + tid) : 0xFFFFFFFFu;
+    for (int i = tid; i < kRT; i += NT) s_key[i] = i < nr ? __ldg(uniq + r0 + i) : 0xFFFFFFFFu;
     __syncthreads();
     int seg_a = 0;
     while (seg_a < nr) {
       const int t = find_table(p.key_base, p.n_tables, s_key[seg_a]);
       const uint32_t kend = p.key_base[t + 1];
-      int seg_b = seg_a + 1;
-      if (s_key[nr - 1] < kend) seg_b = nr;
-      else while (s_key[seg_b] < kend) ++seg_b;   // uniform across the CTA (shared-memory broadcast reads)
+      int seg_b;
+      if (s_key[nr - 1] < kend) {
+        seg_b = nr;
+      } else {   // first row of the next table, by bisection (uniform across the CTA: shared-memory broadcast reads)
+        int lo = seg_a + 1, hi = nr - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] < kend) lo = mid + 1; else hi = mid; }
+        seg_b = lo;
+      }
       const int ns = seg_b - seg_a;
       __syncthreads();   // previous segment's readers of Xs / Rs / Ws are done
       if (t != cur_t) {
@@ -108,7 +135,7 @@ __global__ void __launch_bounds__(kFT) fact_rows_kernel(const __grid_constant__ 
         const float* W = p.dnn_w[p.side[t]];
         const int64_t ld = p.dnn_ld[p.side[t]];
         const int col = p.col[t];
-        for (int i = tid; i < H * H; i += kFT) {
+        for (int i = tid; i < H * H; i += NT) {
           const int h = i / H, k = i - h * H;
           const float wv = __ldg(W + (size_t)h * ld + col + k);
           if (MODE == 1) Ws[h * LD + k] = wv; else Ws[k * LD + h] = wv;
@@ -117,77 +144,69 @@ __global__ void __launch_bounds__(kFT) fact_rows_kernel(const __grid_constant__ 
       }
       const float* tab = p.w[t];
       const uint32_t kb = p.key_base[t];
-      for (int i = tid; i < kRT * (H / 4); i += kFT) {
+      // all of the tile's 16-byte pieces go global -> shared asynchronously (every copy in flight at once: the rows
+      // are scattered 256 B reads out of HBM, so one latency round instead of one per register-staged batch)
+      for (int i = tid; i < kRT * (H / 4); i += NT) {
         const int r = i / (H / 4), c = i - r * (H / 4);
-        float4 row = make_float4(0.f, 0.f, 0.f, 0.f), g = row;
-        if (r < ns) {
-          row = __ldg(reinterpret_cast<const float4*>(tab + (size_t)(s_key[seg_a + r] - kb) * H) + c);
-          if (MODE == 1) g = *reinterpret_cast<const float4*>(PG + (size_t)(r0 + seg_a + r) * H + c * 4);
-        }
+        const bool ok = r < ns;
+        const float* rsrc = ok ? tab + (size_t)(s_key[seg_a + r] - kb) * H + c * 4 : tab;
         if (MODE == 1) {
-          *reinterpret_cast<float4*>(Rs + r * LD + c * 4) = row;
-          *reinterpret_cast<float4*>(Xs + r * LD + c * 4) = g;
+          cp_async16(Rs + r * LD + c * 4, rsrc, ok ? 16 : 0);
+          cp_async16(Xs + r * LD + c * 4, ok ? PG + (size_t)(r0 + seg_a + r) * H + c * 4 : PG, ok ? 16 : 0);
         } else {
-          *reinterpret_cast<float4*>(Xs + r * LD + c * 4) = row;
+          cp_async16(Xs + r * LD + c * 4, rsrc, ok ? 16 : 0);
         }
       }
+      cp_async_wait_all();
       __syncthreads();
-      // ---- row GEMM: out[r][j] = sum_q Xs[r][q] * Ws[q][j]
-      {
-        float4 acc[RPT][NV];
+      // ---- row GEMM: out[r][j] = sum_q Xs[r][q] * Ws[q][j];  r = ty + TYN i, j in {tx*4.., H/2 + tx*4..}
+      if (ty < ns) {   // (rows are interleaved by TYN: a row group with no valid row at all only exists in short tails)
+        float4 acc[8][2];
 #pragma unroll
-        for (int i = 0; i < RPT; ++i)
-#pragma unroll
-          for (int v = 0; v < NV; ++v) acc[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
+        for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
         for (int q = 0; q < H; q += 4) {
-          float4 xv[RPT];
+          float4 xv[8];
 #pragma unroll
-          for (int i = 0; i < RPT; ++i) xv[i] = *reinterpret_cast<const float4*>(Xs + (ty + TYN * i) * LD + q);
+          for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(Xs + (ty + TYN * i) * LD + q);
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
-            float4 wv[NV];
+            const float4 w0 = *reinterpret_cast<const float4*>(Ws + (q + qq) * LD + tx * 4);
+            const float4 w1 = *reinterpret_cast<const float4*>(Ws + (q + qq) * LD + HH + tx * 4);
 #pragma unroll
-            for (int v = 0; v < NV; ++v) wv[v] = *reinterpret_cast<const float4*>(Ws + (q + qq) * LD + tx * 4 + 64 * v);
-#pragma unroll
-            for (int i = 0; i < RPT; ++i) {
+            for (int i = 0; i < 8; ++i) {
               const float x = qq == 0 ? xv[i].x : (qq == 1 ? xv[i].y : (qq == 2 ? xv[i].z : xv[i].w));
-#pragma unroll
-              for (int v = 0; v < NV; ++v) fma4(acc[i][v], x, wv[v]);
+              fma4(acc[i][0], x, w0);
+              fma4(acc[i][1], x, w1);
             }
           }
         }
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const int r = ty + TYN * i;
           if (r < ns) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v)
-              *reinterpret_cast<float4*>(PG + (size_t)(r0 + seg_a + r) * H + tx * 4 + 64 * v) = acc[i][v];
+            float* dst = PG + (size_t)(r0 + seg_a + r) * H;
+            *reinterpret_cast<float4*>(dst + tx * 4) = acc[i][0];
+            *reinterpret_cast<float4*>(dst + HH + tx * 4) = acc[i][1];
           }
         }
       }
-      // ---- dW GEMM: dw[h][k] += sum_r G[r][h] * R[r][k], rows in sorted order
+      // ---- dW GEMM: dw[h][k] += sum_r G[r][h] * R[r][k]; row group rg takes rows rg, rg + RG, ... in order
       if (MODE == 1) {
-        for (int r = 0; r < ns; ++r) {
-          float4 rv[NV];
-#pragma unroll
-          for (int v = 0; v < NV; ++v) rv[v] = *reinterpret_cast<const float4*>(Rs + r * LD + tx * 4 + 64 * v);
-          float gv[HPT];
-          if constexpr (HPT % 4 == 0) {
-#pragma unroll
-            for (int i = 0; i < HPT; i += 4) {
-              const float4 g4 = *reinterpret_cast<const float4*>(Xs + r * LD + ty * HPT + i);
-              gv[i] = g4.x; gv[i + 1] = g4.y; gv[i + 2] = g4.z; gv[i + 3] = g4.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < HPT; ++i) gv[i] = Xs[r * LD + ty * HPT + i];
-          }
-#pragma unroll
-          for (int i = 0; i < HPT; ++i)
-#pragma unroll
-            for (int v = 0; v < NV; ++v) fma4(dw[i][v], gv[i], rv[v]);
+#pragma unroll 2
+        for (int r = rg; r < ns; r += RG) {
+          const float4 k0 = *reinterpret_cast<const float4*>(Rs + r * LD + hx * 4);
+          const float4 k1 = *reinterpret_cast<const float4*>(Rs + r * LD + HH + hx * 4);
+          const float4 g0 = *reinterpret_cast<const float4*>(Xs + r * LD + hy * 4);
+          const float4 g1 = *reinterpret_cast<const float4*>(Xs + r * LD + HH + hy * 4);
+          fma4(dw[0][0], g0.x, k0); fma4(dw[0][1], g0.x, k1);
+          fma4(dw[1][0], g0.y, k0); fma4(dw[1][1], g0.y, k1);
+          fma4(dw[2][0], g0.z, k0); fma4(dw[2][1], g0.z, k1);
+          fma4(dw[3][0], g0.w, k0); fma4(dw[3][1], g0.w, k1);
+          fma4(dw[4][0], g1.x, k0); fma4(dw[4][1], g1.x, k1);
+          fma4(dw[5][0], g1.y, k0); fma4(dw[5][1], g1.y, k1);
+          fma4(dw[6][0], g1.z, k0); fma4(dw[6][1], g1.z, k1);
+          fma4(dw[7][0], g1.w, k0); fma4(dw[7][1], g1.w, k1);
         }
       }
       seg_a = seg_b;
@@ -196,13 +215,15 @@ __global__ void __launch_bounds__(kFT) fact_rows_kernel(const __grid_constant__ 
   if (MODE == 1 && cur_t >= 0) flush_dw(cur_t);
 }
 
-// dW[:, col(t) : col(t)+H] (+)= sum of table t's split-K partials in CTA order. grid = (n_tables, H*H/256).
+// dW[:, col(t) : col(t)+H] (+)= sum of table t's split-K partials in CTA order. grid = (n_tables, H*H/64);
+// 4 strided lanes per output element (ascending inside a lane, unrolled loads), combined in fixed order.
 template <int H>
 __global__ void __launch_bounds__(kFT) fact_dw_reduce_kernel(const __grid_constant__ FactParams p,
                                                              const uint32_t* __restrict__ uniq,
                                                              const int32_t* __restrict__ n_unique_dev,
                                                              const float* __restrict__ dw_part, int rows_grid,
                                                              float* dW_item, float* dW_user) {
+  __shared__ float s_p[4][64];
   const int t = blockIdx.x;
   const int U = *n_unique_dev;
   int lo = 0, hi = U;   // unique-row range [a, b) of table t by binary search on the sorted keys
@@ -215,13 +236,28 @@ __global__ void __launch_bounds__(kFT) fact_dw_reduce_kernel(const __grid_consta
   float* dW = p.side[t] == 0 ? dW_item : dW_user;
   if (dW == nullptr) return;
   const int64_t ld = p.dnn_ld[p.side[t]];
+  constexpr int kRT = RowsCfg<H>::RT;
   const int n_tiles = (U + kRT - 1) / kRT;
   const int tpc = (n_tiles + rows_grid - 1) / rows_grid;
   const int cta_a = (a / kRT) / tpc, cta_b = ((b - 1) / kRT) / tpc;
-  const int i = blockIdx.y * kFT + threadIdx.x;
-  if (i >= H * H) return;
+  const int ol = threadIdx.x % 64, pl = threadIdx.x / 64;
+  const int i = blockIdx.y * 64 + ol;
+  // partial slots of table t: ((cta + t) * RG + rg), cta in [cta_a, cta_b], rg in [0, RG)  => one contiguous run
+  constexpr int RG = RowsCfg<H>::RG;
+  const float* src = dw_part + (size_t)t * RG * H * H + i;
+  const int ca = cta_a * RG, cb = cta_b * RG + RG - 1;
   float s = 0.f;
-  for (int c = cta_a; c <= cta_b; ++c) s = __fadd_rn(s, dw_part[(size_t)(c + t) * H * H + i]);
+  int c = ca + pl;
+  for (; c + 12 <= cb; c += 16) {
+    const float v0 = src[(size_t)c * H * H], v1 = src[(size_t)(c + 4) * H * H];
+    const float v2 = src[(size_t)(c + 8) * H * H], v3 = src[(size_t)(c + 12) * H * H];
+    s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, v0), v1), v2), v3);
+  }
+  for (; c <= cb; c += 4) s = __fadd_rn(s, src[(size_t)c * H * H]);
+  s_p[pl][ol] = s;
+  __syncthreads();
+  if (pl != 0) return;
+  s = __fadd_rn(__fadd_rn(s_p[0][ol], s_p[1][ol]), __fadd_rn(s_p[2][ol], s_p[3][ol]));
   const int h = i / H, k = i - h * H;
   float* d = dW + (size_t)h * ld + p.col[t] + k;
   *d = __fadd_rn(*d, s);
@@ -284,7 +320,29 @@ __device__ __forceinline__ float4 relu4(const float4& z) {
   return make_float4(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f), fmaxf(z.z, 0.f), fmaxf(z.w, 0.f));
 }
 
-template <int LANES>
+// N compile-time consecutive id columns starting at idr[0]: no bounds checks, no column indirection
+template <int N>
+__device__ __forceinline__ void gather_sum_fixed(float4& z, const int32_t* idr, const float4* __restrict__ P4, int H4, int c) {
+#pragma unroll
+  for (int s0 = 0; s0 < N; s0 += kFU) {
+    float4 v[kFU];
+#pragma unroll
+    for (int u = 0; u < kFU; ++u) {
+      if (s0 + u < N) {
+        const int r = idr[s0 + u];
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r) v[u] = __ldg(P4 + (uint32_t)((r - 1) * H4 + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kFU; ++u)
+      if (s0 + u < N) z = f4_add(z, v[u]);   // slot order
+  }
+}
+
+// NSI / NSU > 0: the call's SINGLE slots are ids columns [0, NSI) (item side) and [NSI, NSI + NSU) (user side) — the
+// reference's default feature lists (dataset.py:191-212) give (15, 0) and (15, 5); NSI < 0: counts / columns at run time.
+template <int LANES, int NSI, int NSU>
 __global__ void __launch_bounds__(kFT) fact_forward_kernel(const __grid_constant__ FwdFactParams p) {
   extern __shared__ int32_t s_ids[];   // [kFTok * n_single]
   constexpr int G = kFT / LANES;
@@ -305,20 +363,23 @@ __global__ void __launch_bounds__(kFT) fact_forward_kernel(const __grid_constant
   const float4* P4 = reinterpret_cast<const float4*>(p.P);
   const int ns_i = p.n_item_single, ns = ns_i + p.n_user_single;
   const int na_i = p.n_item_array, na = na_i + p.n_user_array;
+  const bool user = NSI >= 0 ? NSU > 0 : p.include_user != 0;
   for (int tl = grp; tl < nt; tl += G) {
     const int t = t0 + tl;
     const int32_t* idr = s_ids + tl * p.n_single;
     for (int c = lane; c < H4; c += LANES) {
       float4 zi = __ldg(reinterpret_cast<const float4*>(p.bias[0]) + c);
-      gather_sum(zi, idr, p.s_col, 0, ns_i, P4, H4, c);
+      if constexpr (NSI >= 0) gather_sum_fixed<NSI>(zi, idr, P4, H4, c);
+      else gather_sum(zi, idr, p.s_col, 0, ns_i, P4, H4, c);
       array_sum(zi, p, 0, na_i, t, P4, H4, c);
       for (int f = 0; f < p.n_mm; ++f)
         zi = f4_add(zi, ld_stream(reinterpret_cast<const float4*>(p.mmz[f]) + (size_t)t * H4 + c));
       unsigned bits = pos_bits(zi);
       float4 o = relu4(zi);
-      if (p.include_user) {
+      if (user) {
         float4 zu = __ldg(reinterpret_cast<const float4*>(p.bias[1]) + c);
-        gather_sum(zu, idr, p.s_col, ns_i, ns, P4, H4, c);
+        if constexpr (NSI >= 0) gather_sum_fixed<(NSU > 0 ? NSU : 1)>(zu, idr + NSI, P4, H4, c);
+        else gather_sum(zu, idr, p.s_col, ns_i, ns, P4, H4, c);
         array_sum(zu, p, na_i, na, t, P4, H4, c);
         bits |= pos_bits(zu) << 4;
         o = f4_add(o, relu4(zu));
@@ -424,27 +485,37 @@ __global__ void __launch_bounds__(kFT) fact_dz_kernel(const float4* __restrict__
   }
 }
 
-// Ordered sum of the per-CTA partial vectors: output o = sum_b part[b][o], b ascending within each of 4 strided
-// lanes, lanes combined in fixed order. o < H: db_item += , mm_s = ; o < 2H: db_user += ; else mm_A = .
+// Ordered sum of the per-CTA partial vectors: output o = sum_b part[b][o]; 16 strided lanes per output (b ascending
+// inside a lane, 4 independent loads in flight), lanes combined in fixed order.
+// o < H: db_item += , mm_s += ; o < 2H: db_user += ; else mm_A += .
 __global__ void __launch_bounds__(256) fact_dz_finish_kernel(const float* __restrict__ part, int n_part, int part_ld, int H,
                                                              float* db_item, float* db_user, float* mm_A, float* mm_s) {
-  __shared__ float s_p[4][64];
-  const int ol = threadIdx.x % 64, pl = threadIdx.x / 64;
-  const int o = blockIdx.x * 64 + ol;
+  __shared__ float s_p[16][17];
+  const int ol = threadIdx.x % 16, pl = threadIdx.x / 16;
+  const int o = blockIdx.x * 16 + ol;
   float s = 0.f;
-  if (o < part_ld)
-    for (int b = pl; b < n_part; b += 4) s = __fadd_rn(s, part[(size_t)b * part_ld + o]);
+  if (o < part_ld) {
+    int b = pl;
+    for (; b + 48 < n_part; b += 64) {
+      const float v0 = part[(size_t)b * part_ld + o], v1 = part[(size_t)(b + 16) * part_ld + o];
+      const float v2 = part[(size_t)(b + 32) * part_ld + o], v3 = part[(size_t)(b + 48) * part_ld + o];
+      s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s, v0), v1), v2), v3);
+    }
+    for (; b < n_part; b += 16) s = __fadd_rn(s, part[(size_t)b * part_ld + o]);
+  }
   s_p[pl][ol] = s;
   __syncthreads();
   if (pl != 0 || o >= part_ld) return;
-  s = __fadd_rn(__fadd_rn(s_p[0][ol], s_p[1][ol]), __fadd_rn(s_p[2][ol], s_p[3][ol]));
+  s = s_p[0][ol];
+#pragma unroll
+  for (int l = 1; l < 16; ++l) s = __fadd_rn(s, s_p[l][ol]);
   if (o < H) {
     if (db_item) db_item[o] = __fadd_rn(db_item[o], s);
-    if (mm_s) mm_s[o] = s;
+    if (mm_s) mm_s[o] = __fadd_rn(mm_s[o], s);
   } else if (o < 2 * H) {
     if (db_user) db_user[o - H] = __fadd_rn(db_user[o - H], s);
   } else if (mm_A) {
-    mm_A[o - 2 * H] = s;
+    mm_A[o - 2 * H] = __fadd_rn(mm_A[o - 2 * H], s);
   }
 }
 
@@ -457,6 +528,7 @@ __global__ void __launch_bounds__(256) fact_mm_fold_kernel(const float* __restri
   if (i < H * mm_dim) {
     const int h = i / mm_dim, j = i - h * mm_dim;
     float s = 0.f;
+#pragma unroll 8
     for (int q = 0; q < H; ++q) s = fmaf(__ldg(Ws + (size_t)h * ld + q), __ldg(Wmm + (size_t)q * mm_dim + j), s);
     M[i] = s;
   } else if (i < H * mm_dim + H) {
@@ -479,6 +551,7 @@ __global__ void __launch_bounds__(256) fact_mm_chain_kernel(const float* __restr
   if (i < n1) {
     const int q = i / mm_dim, j = i - q * mm_dim;
     float a = 0.f;
+#pragma unroll 8
     for (int h = 0; h < H; ++h) a = fmaf(__ldg(Ws + (size_t)h * ld + q), __ldg(A + (size_t)h * mm_dim + j), a);
     dWmm[i] = __fadd_rn(dWmm[i], a);
   } else if (i < n2) {
@@ -492,6 +565,7 @@ __global__ void __launch_bounds__(256) fact_mm_chain_kernel(const float* __restr
     const int e = i - n2;
     const int h = e / H, q = e - h * H;
     float a = 0.f;
+#pragma unroll 8
     for (int j = 0; j < mm_dim; ++j) a = fmaf(__ldg(A + (size_t)h * mm_dim + j), __ldg(Wmm + (size_t)q * mm_dim + j), a);
     if (bmm != nullptr) a = fmaf(__ldg(s + h), __ldg(bmm + q), a);
     float* d = dWs + (size_t)h * dld + q;
@@ -521,14 +595,16 @@ static int fill_fact(FactParams& p, const tgr_table_t* tables, int n_tables, int
   return 0;
 }
 
-static size_t fact_smem(int H, bool bwd) { return (size_t)(H * (H + 4) + (bwd ? 2 : 1) * kRT * (H + 4)) * sizeof(float); }
+static int rows_rt(int H) { return H == 64 ? 64 : 128; }
+static size_t fact_smem(int H, bool bwd) { return (size_t)(H * (H + 4) + (bwd ? 2 : 1) * rows_rt(H) * (H + 4)) * sizeof(float); }
+static int rows_rg(int H) { return (H / 8) * (rows_rt(H) / 8) / ((H / 8) * (H / 8)); }
 
 template <int H, int MODE>
 static int launch_rows(const FactParams& p, const uint32_t* uniq, const int32_t* n_unique_dev, float* PG, float* dw_part,
                        cudaStream_t st) {
   const size_t smem = fact_smem(H, MODE == 1);
   { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_rows_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
-  fact_rows_kernel<H, MODE><<<MODE ? kRowsGridBwd : kRowsGridFwd, kFT, smem, st>>>(p, uniq, n_unique_dev, PG, dw_part);
+  fact_rows_kernel<H, MODE><<<MODE ? kRowsGridBwd : kRowsGridFwd, RowsCfg<H>::NT, smem, st>>>(p, uniq, n_unique_dev, PG, dw_part);
   return check_launch(MODE ? "fact_unique_backward" : "fact_project_rows");
 }
 
@@ -551,7 +627,7 @@ extern "C" int tgr_fact_project_rows(const tgr_table_t* tables, int n_tables, in
 }
 
 extern "C" size_t tgr_fact_backward_workspace_bytes(int n_tables, int H) {
-  return (size_t)(kRowsGridBwd + n_tables + 1) * H * H * sizeof(float);
+  return (size_t)(kRowsGridBwd + n_tables + 1) * rows_rg(H) * H * H * sizeof(float);
 }
 
 extern "C" int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn,
@@ -572,7 +648,7 @@ extern "C" int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables,
   else rc = launch_rows<128, 1>(p, uniq, n_unique_dev, G, part, st);
   if (rc) return rc;
   if (dW_item == nullptr && dW_user == nullptr) return 0;
-  const dim3 grid(n_tables, (H * H + kFT - 1) / kFT);
+  const dim3 grid(n_tables, H * H / 64);
   if (H == 32) fact_dw_reduce_kernel<32><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
   else if (H == 64) fact_dw_reduce_kernel<64><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
   else fact_dw_reduce_kernel<128><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
@@ -622,9 +698,20 @@ extern "C" int tgr_fact_forward(const tgr_call_t* call, int H, const int32_t* id
   const int grid = (call->T + kFTok - 1) / kFTok;
   const size_t smem = (size_t)kFTok * (p.n_single > 0 ? p.n_single : 1) * sizeof(int32_t);
   cudaStream_t st = (cudaStream_t)stream;
-  if (H == 32) fact_forward_kernel<8><<<grid, kFT, smem, st>>>(p);
-  else if (H == 64) fact_forward_kernel<16><<<grid, kFT, smem, st>>>(p);
-  else fact_forward_kernel<32><<<grid, kFT, smem, st>>>(p);
+  // identity column layout with the reference's default slot counts -> fully unrolled gather loops
+  bool ident = true;   // (the fixed variant indexes P with 32-bit float4 offsets: unique rows * H/4 < 2^31)
+  for (int i = 0; i < ns; ++i) ident = ident && p.s_col[i] == i;
+  const int nsi = p.n_item_single, nsu = p.n_user_single;
+#define TGR_FWD(L)                                                                                         \
+  do {                                                                                                     \
+    if (ident && nsi == 15 && nsu == 0) fact_forward_kernel<L, 15, 0><<<grid, kFT, smem, st>>>(p);        \
+    else if (ident && nsi == 15 && nsu == 5) fact_forward_kernel<L, 15, 5><<<grid, kFT, smem, st>>>(p);   \
+    else fact_forward_kernel<L, -1, 0><<<grid, kFT, smem, st>>>(p);                                       \
+  } while (0)
+  if (H == 32) TGR_FWD(8);
+  else if (H == 64) TGR_FWD(16);
+  else TGR_FWD(32);
+#undef TGR_FWD
   return check_launch("fact_forward");
 }
 
@@ -684,7 +771,7 @@ extern "C" int tgr_fact_relu_mask(const float* d_out, const uint8_t* mask, int64
   if (rc) return rc;
   if (db_item == nullptr && db_user == nullptr && mm_x == nullptr) return 0;
   const int part_ld = 2 * H + (mm_x ? H * kDzMM : 0);
-  fact_dz_finish_kernel<<<(part_ld + 63) / 64, 256, 0, st>>>(part, grid, part_ld, H, db_item, dz_user ? db_user : nullptr,
+  fact_dz_finish_kernel<<<(part_ld + 15) / 16, 256, 0, st>>>(part, grid, part_ld, H, db_item, dz_user ? db_user : nullptr,
                                                            mm_x ? mm_A : nullptr, mm_x ? mm_s : nullptr);
   return check_launch("fact_dz_finish");
 }
