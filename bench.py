@@ -357,6 +357,7 @@ def run_gpu(args):
         pbs = feeder.take()                                        # waits (on the stream) for this step's H2D copies
         feeder.submit(host_steps[(i + 1) % n_batches])             # next step's copies overlap this step's kernels
         outs = one_step(pbs, dev_steps[k][1])
+        feeder.retire()
         with torch.no_grad():
             loss = sum(o.detach().sum() for o in outs)
         slot = i & 1
@@ -377,6 +378,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     feeder.take()   # drain the look-ahead submission
+    feeder.retire()
     e2e = {"value": rows_e2e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps,
            "d2h_bytes_per_step": d2h // e2e_steps, "ms_per_step": round(t_e2e / e2e_steps * 1e3, 3),
            "entry": "BaselineEmbedding.prefetch + feat2emb_packed x3 + backward + fused_step from pinned host packed "
@@ -495,6 +497,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="sharded path: per-call exchange instead of step prefetch")
     ap.add_argument("--no-lookahead", action="store_true", help="sharded path: no one-step-ahead key processing")
+    ap.add_argument("--no-p2p", action="store_true", help="sharded factored path: fetch rows with the NCCL all-to-all "
+                    "instead of reading the owners' shards in place over NVLink peer memory")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks (debug)")
     ap.add_argument("--no-kernel-timing", action="store_true", help="no per-kernel CUDA events (debug)")
     ap.add_argument("--clock-period-ms", type=int, default=20)

@@ -30,7 +30,8 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     lay = worldgen.layout
     margs = types.SimpleNamespace(device=str(dev), hidden_units=cfg.H)
     torch.manual_seed(0)                                   # identical dense parameters on every rank
-    m = ShardedBaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), margs, rank, world)
+    m = ShardedBaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), margs, rank, world,
+                                 path=args.path, p2p=not args.no_p2p)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     with torch.no_grad():
         for p in m.parameters():
@@ -41,7 +42,7 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
             if t.key_base % world == rank:
                 m.local_table[t.key_base // world].zero_()
     dense = [p for p in m.parameters() if p is not m.local_table]
-    dense_opt = torch.optim.AdamW(dense, lr=1e-3, betas=(0.9, 0.98))
+    dense_opt = torch.optim.AdamW(dense, lr=1e-3, betas=(0.9, 0.98), fused=True)
     n_batches = max(1, min(args.batches, args.steps + args.warmup))
     steps_np = [worldgen.make_step(1000 * rank + s) for s in range(n_batches)]
     dev_steps = [([to_device(lay, pc, dev) for pc in st.calls], [torch.from_numpy(r).to(dev) for r in st.upstream])
@@ -60,10 +61,12 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
         flat_grad.zero_()
         if not args.no_prefetch:
             m.prefetch(pbs)                      # one dedup + one exchange for the step's three calls
+        if next_pbs is not None and not args.no_lookahead:
+            # next step's key processing (value independent) is enqueued EARLY: its per-owner counts reach the host
+            # long before finish_prepare needs them, so the step never waits on a device->host copy
+            m.prepare_next(next_pbs)
         outs = [m.feat2emb_packed(pb) for pb in pbs]
         torch.autograd.backward(outs, ups)
-        if next_pbs is not None and not args.no_lookahead:
-            m.prepare_next(next_pbs)             # next step's key processing overlaps this step's tail
         dist.all_reduce(flat_grad)
         flat_grad.div_(world)
         dense_opt.step()
@@ -72,25 +75,29 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
             m.finish_prepare()
         return outs
 
-    eng = m.ops._eng
+    from tencent_recommendation_2025_b200 import _lib
+    from tencent_recommendation_2025_b200.packed import HostPrefetcher, stage_pinned
     clocks = bench.ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
-    for i in range(args.warmup):
+    nw = max(args.warmup, 3)
+    for i in range(nw):
         one_step(*dev_steps[i % n_batches], next_pbs=dev_steps[(i + 1) % n_batches][0])
     torch.cuda.synchronize()
     dist.barrier()
-    eng.timing = {}
-    m.ops.timing = eng.timing
     if clocks:
         clocks.mark()
-    l0 = m.ops.launches
+
+    def n_launch():
+        return m.ops.launches + (m.ops.feng.launches if hasattr(m.ops, "feng") else 0)
+
+    l0 = n_launch()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
     rows = 0
     for i in range(args.steps):
-        k = (args.warmup + i) % n_batches
+        k = (nw + i) % n_batches
         one_step(*dev_steps[k], next_pbs=dev_steps[(k + 1) % n_batches][0])   # the data loader is one batch ahead
         rows += lookups[k]
     ev1.record()
@@ -98,6 +105,7 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     dist.barrier()
     clk = clocks.stop() if clocks else None
     ms_local = ev0.elapsed_time(ev1)
+    launches = n_launch() - l0
     t = torch.tensor([ms_local, float(rows)], dtype=torch.float64, device=dev)
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -105,36 +113,61 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
     ms = float(tmax[0])
     total_rows = float(tsum[1])
-    kern_ms = eng.timing_summary()
-    eng.timing = None
-    launches = m.ops.launches - l0
 
-    # ---- e2e from host buffers ----
-    from tencent_recommendation_2025_b200.packed import stage_pinned
+    # ---- per-entry CUDA-event timing inside the library: a second pass over the same steps (all ranks in lockstep) ----
+    used = [(nw + i) % n_batches for i in range(args.steps)]
+    _lib.timing_enable(True)
+    for k in used:
+        one_step(*dev_steps[k], next_pbs=dev_steps[(k + 1) % n_batches][0])
+    torch.cuda.synchronize()
+    kern_ms = _lib.timing_collect()
+    _lib.timing_enable(False)
+    dist.barrier()
+
+    # ---- e2e from pinned host buffers: copy stream two steps ahead (the look-ahead key processing needs step k+1's
+    #      ids on the device during step k), loss of every step copied back and read on the host ----
     host_steps = [[stage_pinned(lay, pc) for pc in st.calls] for st in steps_np]   # as a pin_memory DataLoader would
-    e2e_steps = max(3, min(args.steps, 10))
-    t_e2e = 0.0
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_warm = n_batches + 1
+    feeder = HostPrefetcher(dev, slots=5)
+    m.rank_state.prep = None
+    loss_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+    loss_ev = [None, None]
+    losses = []
     rows_e2e = 0
     h2d = 0
-    nxt = None
-    m.rank_state.prep = None
-    for i in range(e2e_steps + 1):
+    feeder.submit(host_steps[0])
+    feeder.submit(host_steps[1 % n_batches])
+    cur = feeder.take()
+    t0 = None
+    for i in range(e2e_warm + e2e_steps):
         k = i % n_batches
-        st = steps_np[k]
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        pbs = nxt if nxt is not None else [hp.upload(dev) for hp in host_steps[k]]
-        nxt = [hp.upload(dev) for hp in host_steps[(k + 1) % n_batches]]     # next batch's H2D, also inside the timed region
-        outs = one_step(pbs, dev_steps[k][1], next_pbs=nxt)
-        _ = float(sum(o.sum() for o in outs).item())
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if i == 0:
-            continue
-        t_e2e += dt
-        rows_e2e += lookups[k]
-        h2d += sum(pb.h2d_bytes for pb in pbs)
+        if i == e2e_warm:
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+        nxt = feeder.take()
+        feeder.submit(host_steps[(i + 2) % n_batches])
+        outs = one_step(cur, dev_steps[k][1], next_pbs=nxt)
+        feeder.retire()
+        with torch.no_grad():
+            loss = sum(o.detach().sum() for o in outs)
+        slot = i & 1
+        if loss_ev[slot] is not None:
+            loss_ev[slot].synchronize()
+            losses.append(float(loss_host[slot]))
+        loss_host[slot:slot + 1].copy_(loss.reshape(1), non_blocking=True)
+        loss_ev[slot] = torch.cuda.Event()
+        loss_ev[slot].record()
+        if i >= e2e_warm:
+            rows_e2e += lookups[k]
+            h2d += sum(pb.h2d_bytes for pb in cur)
+        cur = nxt
+    for ev in loss_ev:
+        if ev is not None:
+            ev.synchronize()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e, float(rows_e2e)], dtype=torch.float64, device=dev)
     te_max = te.clone()
     dist.all_reduce(te_max, op=dist.ReduceOp.MAX)
@@ -142,23 +175,30 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     dist.all_reduce(te_sum, op=dist.ReduceOp.SUM)
 
     if rank == 0:
-        H = lay.H
-        # rank 0's dominant embedding kernel, against its algorithmic bytes
-        used = [(args.warmup + i) % n_batches for i in range(args.steps)]
-        kb = {"fwd_gather_pool_concat": 0.0}
+        # rank 0's kernels against their compulsory bytes (rank 0's batches)
+        kbytes = {}
         for k in used:
             st = steps_np[k]
             pu, su = bench.unique_counts(lay, st.calls)
-            for pc, U in zip(st.calls, pu):
-                cl = lay.calls[pc.include_user]
-                d_tab = cl.item_dim + cl.user_dim - H * cl.n_mm
-                kb["fwd_gather_pool_concat"] += 4 * (pc.ids.size + pc.arr_val.size + pc.arr_off.size) + U * H * 4 + pc.T * d_tab * 4
-        dom = "fwd_gather_pool_concat"
-        dom_ms, dom_n = kern_ms.get(dom, (0.0, 0))
-        achieved = kb[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": dom + " (rank 0)", "achieved": round(achieved, 1), "peak": hbm_peak,
-                    "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
-                    "kernels_ms_per_step": {n: round(v[0] / args.steps, 4) for n, v in kern_ms.items()}}
+            for name, v in bench.kernel_bytes_step(lay, st, dev_steps[k][0], pu, su, args.path).items():
+                kbytes[name] = kbytes.get(name, 0) + v
+        if args.path == "factored":
+            kbytes.pop("adam_rows", None)          # the owner-side update is bwd_reduce (mode 1) over received rows
+            kbytes.pop("bwd_reduce", None)         # two different launches share this entry name on the sharded path
+        table = {}
+        for name, (t_ms, cnt) in kern_ms.items():
+            e = {"ms_per_step": round(t_ms / args.steps, 4), "launches_per_step": round(cnt / args.steps, 2)}
+            if name in kbytes and t_ms > 0:
+                gbs = kbytes[name] / (t_ms * 1e-3) / 1e9
+                e.update({"alg_MB_per_step": round(kbytes[name] / args.steps / 1e6, 1), "GBs": round(gbs, 1),
+                          "frac": round(gbs / hbm_peak, 4)})
+            table[name] = e
+        cand = [n_ for n_ in table if "GBs" in table[n_]]
+        dom = max(cand, key=lambda n_: table[n_]["ms_per_step"]) if cand else None
+        roofline = {"bound": "hbm", "kernel": (dom or "") + " (rank 0)", "achieved": table[dom]["GBs"] if dom else 0.0,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": table[dom]["frac"] if dom else 0.0,
+                    "traffic": bench.load_traffic(dom), "peak_source": peak_src, "kernels": table,
+                    "kernels_ms_per_step_sum": round(sum(v["ms_per_step"] for v in table.values()), 4)}
         line = {"metric": bench.METRIC, "value": total_rows / (ms * 1e-3), "unit": bench.UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -166,13 +206,18 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
                            "(owner = key mod W), dedup-then-all-to-all of ids/rows/grad rows over NCCL",
                            "batch_per_gpu": cfg.B, "seq_len": cfg.L, "hidden": cfg.H, "item_rows": cfg.item_num + 1,
                            "user_rows": cfg.user_num + 1, "zipf_alpha": cfg.alpha, "mm_features": list(cfg.mm_ids),
-                           "row_update": "fused sparse AdamW on the owner", "dnn_matmul": args.dnn_matmul,
+                           "row_update": "fused sparse AdamW on the owner", "path": args.path,
+                           "row_fetch": ("in place from the owners' shards over NVLink peer memory, fused into the projection kernel"
+                                         if getattr(m.ops, "peers", None) is not None else "NCCL all-to-all of deduplicated rows"),
                            "rows_per_step": int(total_rows // args.steps),
                            "l2": "per-step working set >> 126 MB L2; distinct batches cycled"},
                 "roofline": roofline, "cpu_baseline": None,
                 "e2e": {"value": float(te_sum[1]) / float(te_max[0]), "unit": bench.UNIT,
                         "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": 4 + 8 * world * 4,
-                        "ms_per_step": round(float(te_max[0]) / e2e_steps * 1e3, 3)},
+                        "ms_per_step": round(float(te_max[0]) / e2e_steps * 1e3, 3),
+                        "entry": "prefetch + feat2emb_packed x3 + backward + all-reduce + fused_step per rank from pinned "
+                                 "host buffers (copy stream two steps ahead), loss read back every step; wall clock, max over ranks",
+                        "loss_finite": bool(np.all(np.isfinite(losses)))},
                 "gpu_launches": launches, "clocks": clk}
         print(json.dumps(line))
     dist.barrier()

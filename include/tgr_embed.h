@@ -34,6 +34,7 @@ extern "C" {
 #define TGR_MAX_SLOTS 32
 #define TGR_MAX_ARRAYS 8
 #define TGR_MAX_CALLS 4
+#define TGR_MAX_PEERS 16
 
 /* slot kinds */
 #define TGR_KIND_SINGLE 0 /* one id per token: copy one table row            (model.py:242-247,275) */
@@ -234,9 +235,26 @@ typedef struct tgr_dnn {
   int32_t table_col[TGR_MAX_TABLES];  /* first DNN-input column of that slot */
 } tgr_dnn_t;
 
+/* Where the factored kernels read table rows from. All NULL / 0 (or src == NULL): tables[].weight.
+ *   fetched_rows [+ fetched_perm]: row-sharded tables, the step's rows already fetched from their owners (all-to-all):
+ *       row(uniq[u]) = fetched_rows[fetched_perm[u]] (fetched_perm NULL: fetched_rows[u]);
+ *   peer_rows[0..n_peers): row-sharded tables read IN PLACE over NVLink peer memory (one kernel does the fetch and the
+ *       projection: no gather kernel, no row all-to-all): row(key) = peer_rows[key % n_peers][key / n_peers];
+ *   save_rows: tgr_fact_project_rows also stores the raw rows there, [n_unique, H] (the backward needs them again).
+ * With a non-table source the table weights may be NULL (key bases / rows are still read). */
+typedef struct tgr_row_source {
+  const float* fetched_rows;
+  const int32_t* fetched_perm;
+  const float* peer_rows[TGR_MAX_PEERS];
+  int32_t n_peers;
+  int32_t reserved;
+  float* save_rows;
+} tgr_row_source_t;
+
 /* P[u, :] = W_side[:, col : col+H] . row(uniq[u]) for u < *n_unique_dev (uniq sorted ascending). */
 int tgr_fact_project_rows(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn, const uint32_t* uniq,
-                          const int32_t* n_unique_dev, int64_t max_unique, float* P, void* stream);
+                          const int32_t* n_unique_dev, int64_t max_unique, const tgr_row_source_t* src, float* P,
+                          void* stream);
 
 /* One feat2emb call from the projected rows: out[t] = relu(b_item + sum P[ids_u[t, item slots]-1] + sum_f mmz[f][t])
  * + relu(b_user + sum P[ids_u[t, user slots]-1]); arrays via call->arr_off and arr_u (remapped arr_val). ids 0 add
@@ -257,8 +275,8 @@ int tgr_fact_relu_mask(const float* d_out, const uint8_t* mask, int64_t T, int H
  * dW_item / dW_user [H, ld] += sum_u G[u]^T (x) row[u] in the slot's columns (autograd of the Linear weight). */
 size_t tgr_fact_backward_workspace_bytes(int n_tables, int H);
 int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn, const uint32_t* uniq,
-                             const int32_t* n_unique_dev, int64_t max_unique, float* G, float* dW_item, float* dW_user,
-                             void* workspace, size_t workspace_bytes, void* stream);
+                             const int32_t* n_unique_dev, int64_t max_unique, const tgr_row_source_t* src, float* G,
+                             float* dW_item, float* dW_user, void* workspace, size_t workspace_bytes, void* stream);
 
 /* mm feature folded through its item-DNN block: M = W_slot . W_mm [H, mm_dim], c = W_slot . b_mm [H]
  * (emb_transform then itemdnn, model.py:297-303); x . M^T + c is then produced by tgr_mm_proj_fwd. */
@@ -310,12 +328,15 @@ typedef struct tgr_fact_group {
   int32_t reserved;
   tgr_call_t calls[TGR_MAX_CALLS];     /* ids / arrays of every call; item_cat / user_cat unused */
   const void* mm_x[TGR_MAX_CALLS][TGR_MAX_MM]; /* [T, mm_dim] inputs of every call */
+  tgr_row_source_t src;                /* row-sharded tables: set BEFORE the first forward (fetched rows or peer
+                                          shards; src.save_rows is carved by the driver); all zero = own tables */
   /* ---- carved from the arena by tgr_fact_prepare (device pointers; read-only for the caller) ---- */
   int64_t cap;                         /* rows of uniq / P / G (= max(n, 1)) */
   uint32_t *keys_in, *srcs_in, *keys, *srcs; /* unsorted / stably sorted (key, src) pairs [n] */
   uint32_t* uniq;                      /* sorted unique keys [*n_unique] */
   int32_t *seg_off, *seg_of, *n_unique, *n_valid;
   float* P;                            /* projected rows [*n_unique, H] */
+  float* rows_local;                   /* peer source only: raw rows kept for the backward [*n_unique, H] */
   float* G;                            /* after the finishing backward: row gradients [*n_unique, H] */
   int32_t* ids_u[TGR_MAX_CALLS];
   int32_t* arr_u[TGR_MAX_CALLS];

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(PKG, "libtgr_embed.so")
 
 TGR_ABI_VERSION = 1
 MAX_TABLES, MAX_SLOTS, MAX_ARRAYS, MAX_CALLS = 64, 32, 8, 4
+MAX_PEERS = 16
 KIND_SINGLE, KIND_ARRAY, KIND_MM = 0, 1, 2
 DTYPE_F32, DTYPE_BF16 = 0, 1
 
@@ -49,6 +50,11 @@ class Dnn(C.Structure):
 MAX_MM = 6
 
 
+class RowSource(C.Structure):
+    _fields_ = [("fetched_rows", C.c_void_p), ("fetched_perm", C.c_void_p), ("peer_rows", C.c_void_p * MAX_PEERS),
+                ("n_peers", C.c_int32), ("reserved", C.c_int32), ("save_rows", C.c_void_p)]
+
+
 class MmFeat(C.Structure):
     _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("mm_dim", C.c_int32), ("col", C.c_int32)]
 
@@ -67,11 +73,12 @@ class FactGroup(C.Structure):
     _fields_ = [("n_calls", C.c_int32), ("H", C.c_int32), ("key_bits", C.c_int32), ("n_mm", C.c_int32),
                 ("n", C.c_int64), ("mm_dim", C.c_int32 * MAX_MM), ("mm_x_dtype", C.c_int32), ("reserved", C.c_int32),
                 ("calls", Call * MAX_CALLS), ("mm_x", (C.c_void_p * MAX_MM) * MAX_CALLS),
+                ("src", RowSource),
                 ("cap", C.c_int64),
                 ("keys_in", C.c_void_p), ("srcs_in", C.c_void_p), ("keys", C.c_void_p), ("srcs", C.c_void_p),
                 ("uniq", C.c_void_p),
                 ("seg_off", C.c_void_p), ("seg_of", C.c_void_p), ("n_unique", C.c_void_p), ("n_valid", C.c_void_p),
-                ("P", C.c_void_p), ("G", C.c_void_p),
+                ("P", C.c_void_p), ("rows_local", C.c_void_p), ("G", C.c_void_p),
                 ("ids_u", C.c_void_p * MAX_CALLS), ("arr_u", C.c_void_p * MAX_CALLS), ("mask", C.c_void_p * MAX_CALLS),
                 ("dz_item", C.c_void_p * MAX_CALLS), ("dz_user", C.c_void_p * MAX_CALLS),
                 ("mmz", (C.c_void_p * MAX_MM) * MAX_CALLS),
@@ -139,7 +146,7 @@ SIGNATURES = {
     "tgr_permute_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "tgr_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "tgr_fact_project_rows": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Dnn), C.c_void_p, C.c_void_p,
-                                        C.c_int64, C.c_void_p, C.c_void_p]),
+                                        C.c_int64, C.POINTER(RowSource), C.c_void_p, C.c_void_p]),
     "tgr_fact_forward": (C.c_int, [C.POINTER(Call), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_fact_relu_mask_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
@@ -148,8 +155,8 @@ SIGNATURES = {
                                      C.c_size_t, C.c_void_p]),
     "tgr_fact_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "tgr_fact_unique_backward": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Dnn), C.c_void_p, C.c_void_p,
-                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
-                                           C.c_void_p]),
+                                           C.c_int64, C.POINTER(RowSource), C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_size_t, C.c_void_p]),
     "tgr_fact_mm_fold": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     "tgr_fact_group_bytes": (C.c_size_t, [C.POINTER(FactGroup), C.c_int]),

@@ -63,6 +63,7 @@ static size_t carve(tgr_fact_group_t* g, void* arena, int n_tables) {
   g->n_unique = cv.take<int32_t>(4);
   g->n_valid = cv.take<int32_t>(4);
   g->P = cv.take<float>(cap * H);
+  g->rows_local = cv.take<float>(cap * H);
   g->G = cv.take<float>(cap * H);
   size_t ws = 0;
   int64_t max_entries = 0;
@@ -154,7 +155,9 @@ extern "C" int tgr_fact_call_forward(const tgr_table_t* tables, int n_tables, co
   TGR_REQUIRE(prm->n_mm == g->n_mm, "n_mm mismatch");
   const int H = g->H;
   if (!g->projected) {
-    if (int rc = tgr_fact_project_rows(tables, n_tables, H, &prm->dnn, g->uniq, g->n_unique, g->n, g->P, stream)) return rc;
+    tgr_row_source_t src = g->src;
+    if (src.n_peers > 0) src.save_rows = g->rows_local;   // read the owners' shards once; the backward uses the copy
+    if (int rc = tgr_fact_project_rows(tables, n_tables, H, &prm->dnn, g->uniq, g->n_unique, g->n, &src, g->P, stream)) return rc;
     for (int f = 0; f < g->n_mm; ++f) {
       const tgr_mm_feat_t& m = prm->mm[f];
       TGR_REQUIRE(m.mm_dim == g->mm_dim[f], "mm_dim mismatch");
@@ -222,6 +225,11 @@ extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, c
   }
   if (int rc = tgr_bwd_reduce(tables, n_tables, H, calls, g->n_calls, g->keys, g->srcs, g->n, 0, g->seg_of, g->G, nullptr,
                               g->ws, g->ws_bytes, stream)) return rc;
-  return tgr_fact_unique_backward(tables, n_tables, H, &prm->dnn, g->uniq, g->n_unique, g->n, g->G, gr->dW_item,
+  tgr_row_source_t src = g->src;
+  if (src.n_peers > 0) {   // the rows were copied out of the peers' shards by the forward projection
+    src = tgr_row_source_t{};
+    src.fetched_rows = g->rows_local;
+  }
+  return tgr_fact_unique_backward(tables, n_tables, H, &prm->dnn, g->uniq, g->n_unique, g->n, &src, g->G, gr->dW_item,
                                   gr->dW_user, g->ws, g->ws_bytes, stream);
 }

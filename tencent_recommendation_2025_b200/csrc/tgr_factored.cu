@@ -36,6 +36,11 @@ struct FactParams {
   int8_t side[TGR_MAX_TABLES];          // which DNN the table's slot feeds
   const float* dnn_w[2];                // itemdnn.weight [H, item_dim], userdnn.weight [H, user_dim]
   int64_t dnn_ld[2];
+  const float* fetched;                 // row-sharded tables: rows of this step fetched from their owners, or NULL
+  const int32_t* fetched_perm;          // row of unique key u = fetched[fetched_perm[u]] (NULL: fetched[u])
+  const float* peer[TGR_MAX_PEERS];     // row-sharded tables read in place over NVLink: shard of owner r (peer memory)
+  int32_t n_peers;                      // > 0: row(key) = peer[key % n_peers][key / n_peers]
+  float* save_rows;                     // MODE 0: also keep the raw rows, [U, H] (the backward's dW needs them again)
   int32_t n_tables;
 };
 
@@ -88,6 +93,7 @@ __global__ void __launch_bounds__(RowsCfg<H>::NT) fact_rows_kernel(const __grid_
   float* Xs = Ws + H * LD;     // [kRT][LD] MODE 0: table rows               MODE 1: G rows
   float* Rs = Xs + kRT * LD;   // [kRT][LD] MODE 1: table rows
   __shared__ uint32_t s_key[kRT];
+  __shared__ int32_t s_perm[kRT];
   const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;          // row GEMM: rows ty + TYN i, cols tx*4 (+ H/2)
   const int hx = tid % TXN, hy = (tid % DT) / TXN, rg = tid / DT;        // dW GEMM: h = hy*4 (+H/2), k = hx*4 (+H/2)
   const int U = *n_unique_dev;
@@ -114,7 +120,10 @@ __global__ void __launch_bounds__(RowsCfg<H>::NT) fact_rows_kernel(const __grid_
     const int r0 = tile * kRT;
     const int nr = min(kRT, U - r0);
     __syncthreads();
-    for (int i = tid; i < kRT; i += NT) s_key[i] = i < nr ? __ldg(uniq + r0 + i) : 0xFFFFFFFFu;
+    for (int i = tid; i < kRT; i += NT) {
+      s_key[i] = i < nr ? __ldg(uniq + r0 + i) : 0xFFFFFFFFu;
+      if (p.fetched != nullptr) s_perm[i] = i >= nr ? 0 : (p.fetched_perm ? __ldg(p.fetched_perm + r0 + i) : r0 + i);
+    }
     __syncthreads();
     int seg_a = 0;
     while (seg_a < nr) {
@@ -149,7 +158,15 @@ __global__ void __launch_bounds__(RowsCfg<H>::NT) fact_rows_kernel(const __grid_
       for (int i = tid; i < kRT * (H / 4); i += NT) {
         const int r = i / (H / 4), c = i - r * (H / 4);
         const bool ok = r < ns;
-        const float* rsrc = ok ? tab + (size_t)(s_key[seg_a + r] - kb) * H + c * 4 : tab;
+        const float* rsrc;
+        if (p.n_peers > 0) {          // the owner's shard, read in place through NVLink peer memory
+          const uint32_t key = ok ? s_key[seg_a + r] : 0u;
+          rsrc = p.peer[key % (uint32_t)p.n_peers] + (size_t)(key / (uint32_t)p.n_peers) * H + c * 4;
+        } else if (p.fetched != nullptr) {
+          rsrc = ok ? p.fetched + (size_t)s_perm[seg_a + r] * H + c * 4 : p.fetched;
+        } else {
+          rsrc = ok ? tab + (size_t)(s_key[seg_a + r] - kb) * H + c * 4 : tab;
+        }
         if (MODE == 1) {
           cp_async16(Rs + r * LD + c * 4, rsrc, ok ? 16 : 0);
           cp_async16(Xs + r * LD + c * 4, ok ? PG + (size_t)(r0 + seg_a + r) * H + c * 4 : PG, ok ? 16 : 0);
@@ -159,6 +176,13 @@ __global__ void __launch_bounds__(RowsCfg<H>::NT) fact_rows_kernel(const __grid_
       }
       cp_async_wait_all();
       __syncthreads();
+      if (MODE == 0 && p.save_rows != nullptr) {
+        for (int i = tid; i < ns * (H / 4); i += NT) {
+          const int r = i / (H / 4), c = i - r * (H / 4);
+          st_stream(reinterpret_cast<float4*>(p.save_rows + (size_t)(r0 + seg_a + r) * H) + c,
+                    *reinterpret_cast<const float4*>(Xs + r * LD + c * 4));
+        }
+      }
       // ---- row GEMM: out[r][j] = sum_q Xs[r][q] * Ws[q][j];  r = ty + TYN i, j in {tx*4.., H/2 + tx*4..}
       if (ty < ns) {   // (rows are interleaved by TYN: a row group with no valid row at all only exists in short tails)
         float4 acc[8][2];
@@ -573,14 +597,26 @@ __global__ void __launch_bounds__(256) fact_mm_chain_kernel(const float* __restr
   }
 }
 
-static int fill_fact(FactParams& p, const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn) {
+static int fill_fact(FactParams& p, const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn,
+                     const tgr_row_source_t* src) {
+  const float* fetched = src ? src->fetched_rows : nullptr;
+  const int32_t* fetched_perm = src ? src->fetched_perm : nullptr;
+  const int n_peers = src ? src->n_peers : 0;
+  TGR_REQUIRE(n_peers >= 0 && n_peers <= TGR_MAX_PEERS, "n_peers out of range");
+  TGR_REQUIRE(!(n_peers > 0 && fetched), "row source: peers and fetched rows are exclusive");
+  p.n_peers = n_peers;
+  for (int r = 0; r < n_peers; ++r) {
+    TGR_REQUIRE(src->peer_rows[r] != nullptr, "peer %d: shard pointer is NULL", r);
+    p.peer[r] = src->peer_rows[r];
+  }
+  p.save_rows = src ? src->save_rows : nullptr;
   TGR_REQUIRE(tables && n_tables > 0 && n_tables <= TGR_MAX_TABLES, "bad table array");
   TGR_REQUIRE(H == 32 || H == 64 || H == 128, "the factored path supports H in {32, 64, 128} (H=%d)", H);
   TGR_REQUIRE(dnn && dnn->w_item, "dnn / itemdnn weight is NULL");
   p.n_tables = n_tables;
   for (int t = 0; t < n_tables; ++t) {
     p.w[t] = tables[t].weight;
-    TGR_REQUIRE(p.w[t] != nullptr, "table %d: weight NULL", t);
+    TGR_REQUIRE(p.w[t] != nullptr || fetched != nullptr || n_peers > 0, "table %d: weight NULL", t);
     p.key_base[t] = (uint32_t)tables[t].key_base;
     p.side[t] = (int8_t)dnn->table_side[t];
     p.col[t] = dnn->table_col[t];
@@ -590,6 +626,9 @@ static int fill_fact(FactParams& p, const tgr_table_t* tables, int n_tables, int
     if (t) TGR_REQUIRE(tables[t].key_base == tables[t - 1].key_base + tables[t - 1].rows, "key bases must be cumulative");
   }
   p.key_base[n_tables] = (uint32_t)(tables[n_tables - 1].key_base + tables[n_tables - 1].rows);
+  TGR_REQUIRE(fetched != nullptr || fetched_perm == nullptr, "a permutation without fetched rows");
+  p.fetched = fetched;
+  p.fetched_perm = fetched_perm;
   p.dnn_w[0] = dnn->w_item; p.dnn_ld[0] = dnn->item_ld;
   p.dnn_w[1] = dnn->w_user; p.dnn_ld[1] = dnn->user_ld;
   return 0;
@@ -613,11 +652,11 @@ static int launch_rows(const FactParams& p, const uint32_t* uniq, const int32_t*
 using namespace tgr;
 
 extern "C" int tgr_fact_project_rows(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn,
-                                     const uint32_t* uniq, const int32_t* n_unique_dev, int64_t max_unique, float* P,
-                                     void* stream) {
+                                     const uint32_t* uniq, const int32_t* n_unique_dev, int64_t max_unique,
+                                     const tgr_row_source_t* src, float* P, void* stream) {
   tgr::TimedScope tgr_timed_("fact_project_rows", stream);
   FactParams p{};
-  if (int rc = fill_fact(p, tables, n_tables, H, dnn)) return rc;
+  if (int rc = fill_fact(p, tables, n_tables, H, dnn, src)) return rc;
   TGR_REQUIRE(uniq && n_unique_dev && P, "null argument");
   if (max_unique <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -631,12 +670,12 @@ extern "C" size_t tgr_fact_backward_workspace_bytes(int n_tables, int H) {
 }
 
 extern "C" int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables, int H, const tgr_dnn_t* dnn,
-                                        const uint32_t* uniq, const int32_t* n_unique_dev, int64_t max_unique, float* G,
-                                        float* dW_item, float* dW_user, void* workspace, size_t workspace_bytes,
-                                        void* stream) {
+                                        const uint32_t* uniq, const int32_t* n_unique_dev, int64_t max_unique,
+                                        const tgr_row_source_t* src, float* G, float* dW_item, float* dW_user,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
   tgr::TimedScope tgr_timed_("fact_unique_backward", stream);
   FactParams p{};
-  if (int rc = fill_fact(p, tables, n_tables, H, dnn)) return rc;
+  if (int rc = fill_fact(p, tables, n_tables, H, dnn, src)) return rc;
   TGR_REQUIRE(uniq && n_unique_dev && G && workspace, "null argument");
   TGR_REQUIRE(workspace_bytes >= tgr_fact_backward_workspace_bytes(n_tables, H), "workspace too small");
   if (max_unique <= 0) return 0;

@@ -236,7 +236,10 @@ __global__ void __launch_bounds__(kRedThreads) reduce_fixup_kernel(const __grid_
   TGR_FOR_COLS(j, c) dst[c] = acc[j];
 }
 
-// mode 1, second phase: AdamW on every finished row. One CTA per region, two rows in flight per group.
+// mode 1, second phase: AdamW on every finished row. grid = (regions, kAdamSplit): a region holds up to TILE finished rows
+// (all of them when every key occurs once, as on the owner side of the sharded exchange), so its rows are split over
+// kAdamSplit CTAs; two rows in flight per group.
+constexpr int kAdamSplit = 4;
 template <int LANES, int NJ>
 __global__ void __launch_bounds__(kRedThreads) adam_regions_kernel(const __grid_constant__ RowParams rp,
                                                                    const uint32_t* __restrict__ row_keys,
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(kRedThreads) adam_regions_kernel(const __grid_
   const int H4 = rp.H4;
   const int cnt = row_cnt[blockIdx.x];
   const size_t base = (size_t)blockIdx.x * TILE;
-  for (int j0 = grp; j0 < cnt; j0 += 2 * G) {
+  for (int j0 = grp + 2 * G * blockIdx.y; j0 < cnt; j0 += 2 * G * kAdamSplit) {
     float4 g[2][NJ], w[2][NJ], m[2][NJ], v[2][NJ];
     float4 *wp[2], *mp[2], *vp[2];
 #pragma unroll
@@ -304,7 +307,7 @@ static int launch_reduce(RedParams& p, const RowParams* rp, bool bf16, int n_cta
     if (int rc = check_launch("reduce_fixup")) return rc;
   }
   if (p.mode == 1) {
-    adam_regions_kernel<LANES, NJ><<<n_cta, kRedThreads, 0, st>>>(*rp, p.row_keys, p.row_buf, p.row_cnt);
+    adam_regions_kernel<LANES, NJ><<<dim3(n_cta, kAdamSplit), kRedThreads, 0, st>>>(*rp, p.row_keys, p.row_buf, p.row_cnt);
     return check_launch("adam_regions");
   }
   return 0;

@@ -16,6 +16,10 @@ __global__ void __launch_bounds__(kRouteBlock) route_count_kernel(const uint32_t
                                                                   const int32_t* __restrict__ n_dev, int W, int nb,
                                                                   int32_t* __restrict__ cnt /*[W][nb]*/) {
   const int n = *n_dev;
+  if ((int)blockIdx.x * kRouteBlock >= n) {   // the grid covers the capacity bound; blocks past *n_dev just report zeros
+    if (threadIdx.x < W) cnt[threadIdx.x * nb + blockIdx.x] = 0;
+    return;
+  }
   const int i = blockIdx.x * kRouteBlock + threadIdx.x;
   const int owner = i < n ? (int)(__ldg(uniq + i) % (uint32_t)W) : -1;
   for (int w = 0; w < W; ++w) {
@@ -76,6 +80,7 @@ __global__ void __launch_bounds__(kRouteBlock) route_emit_kernel(const uint32_t*
                                                                  int32_t* __restrict__ perm) {
   __shared__ int32_t warp_cnt[32];
   const int n = *n_dev;
+  if ((int)blockIdx.x * kRouteBlock >= n) return;
   const int i = blockIdx.x * kRouteBlock + threadIdx.x;
   const uint32_t key = i < n ? __ldg(uniq + i) : 0u;
   const int owner = i < n ? (int)(key % (uint32_t)W) : -1;

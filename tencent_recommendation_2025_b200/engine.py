@@ -49,7 +49,7 @@ class EmbeddingEngine:
     """
 
     def __init__(self, layout: FeatureLayout, tables: Sequence[torch.nn.Parameter], mm: Dict[str, torch.nn.Linear],
-                 mode: str = "parity"):
+                 mode: str = "parity", check_shapes: bool = True):
         if mode not in ("parity", "fused"):
             raise ValueError("mode must be 'parity' or 'fused'")
         self.lib = _lib.load()
@@ -57,7 +57,7 @@ class EmbeddingEngine:
         self.tables = list(tables)
         assert len(self.tables) == len(layout.tables)
         for p, t in zip(self.tables, layout.tables):
-            if tuple(p.shape) != (t.rows, layout.H):
+            if check_shapes and tuple(p.shape) != (t.rows, layout.H):
                 raise ValueError(f"table {t.name}: shape {tuple(p.shape)} != {(t.rows, layout.H)}")
         self.mm = mm
         self.mode = mode

@@ -84,8 +84,9 @@ class FactoredEngine(EmbeddingEngine):
     """EmbeddingEngine whose forward/backward run the factored kernels. ``dnn``: {'item': nn.Linear, 'user': nn.Linear}
     (itemdnn / userdnn, model.py:150-151) — borrowed like the tables."""
 
-    def __init__(self, layout: FeatureLayout, tables, mm, dnn: Dict[str, torch.nn.Linear], mode: str = "fused"):
-        super().__init__(layout, tables, mm, mode)
+    def __init__(self, layout: FeatureLayout, tables, mm, dnn: Dict[str, torch.nn.Linear], mode: str = "fused",
+                 check_shapes: bool = True):
+        super().__init__(layout, tables, mm, mode, check_shapes)
         if layout.H not in SUPPORTED_H:
             raise ValueError(f"the factored path supports hidden_units in {SUPPORTED_H}, got {layout.H}")
         self.dnn = dnn

@@ -202,17 +202,17 @@ class HostPrefetcher:
     """Double-buffered host -> device feed (what a pin_memory DataLoader + a copy stream give a training loop):
     ``submit(host_calls)`` enqueues the H2D copies of one step's pinned ``HostPacked`` calls on a side stream into
     PERSISTENT device staging slots (no allocator traffic in the loop), ``take()`` makes the compute stream wait for
-    the oldest submitted step and returns its ``PackedBatch`` list (views of the slot). Submitting step k+1 before
-    running step k overlaps its copies with step k's kernels. A slot is rewritten only after the step that read it
-    has finished on the compute stream (event recorded at the following ``take``)."""
+    the oldest submitted step and returns its ``PackedBatch`` list (views of the slot); ``retire()`` — called once
+    the step that consumed the oldest taken batch is fully enqueued — records the event after which its slot may be
+    rewritten. Submitting step k+1 before running step k overlaps its copies with step k's kernels."""
 
-    def __init__(self, device, slots: int = 3):
+    def __init__(self, device, slots: int = 4):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.slots = [{"ints": [], "mm": [], "done": None} for _ in range(slots)]
         self.next = 0
         self.queue = []
-        self.last = None
+        self.taken = []
 
     @staticmethod
     def _fit(lst, i, n, dtype, device):
@@ -225,8 +225,10 @@ class HostPrefetcher:
     def submit(self, host_calls: Sequence["HostPacked"]):
         slot = self.slots[self.next]
         self.next = (self.next + 1) % len(self.slots)
+        if any(slot is t for t in self.taken):
+            raise RuntimeError("HostPrefetcher: every slot is still in use (retire() consumed batches, or add slots)")
         if slot["done"] is not None:
-            slot["done"].synchronize()          # the step that read this slot is long finished (slots - 1 steps ago)
+            slot["done"].synchronize()          # the step that read this slot finished slots - 1 steps ago
         pbs = []
         with torch.cuda.stream(self.stream):
             j = 0
@@ -249,15 +251,18 @@ class HostPrefetcher:
         self.queue.append((pbs, ev, slot))
 
     def take(self) -> List[PackedBatch]:
-        cur = torch.cuda.current_stream(self.device)
-        if self.last is not None:               # everything that read the previous slot is enqueued by now
-            done = torch.cuda.Event()
-            done.record(cur)
-            self.last["done"] = done
         pbs, ev, slot = self.queue.pop(0)
-        cur.wait_event(ev)
-        self.last = slot
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        slot["done"] = None
+        self.taken.append(slot)
         return pbs
+
+    def retire(self):
+        """Everything that reads the oldest taken batch has been enqueued on the current stream."""
+        slot = self.taken.pop(0)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        slot["done"] = done
 
 
 class _PinnedPool:

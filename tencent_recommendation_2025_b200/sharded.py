@@ -119,7 +119,7 @@ class CudaShardOps:
         dev = self.local.device
         out = torch.empty((n, self.layout.H), dtype=torch.float32, device=dev)
         if n:
-            n_dev = torch.tensor([n], dtype=torch.int32, device=dev)
+            n_dev = torch.full((1,), n, dtype=torch.int32, device=dev)   # a fill kernel: no pageable H2D copy / sync
             check(self.lib.tgr_gather_rows(self.local.data_ptr(), self.layout.H, rows.data_ptr(), n_dev.data_ptr(), n,
                                            out.data_ptr(), _stream()), "tgr_gather_rows")
             self.launches += 1
@@ -348,6 +348,62 @@ class CudaShardOps:
         self.launches += 2
 
 
+class FactShardOps(CudaShardOps):
+    """Sharded path with the FACTORED kernels (factored.py): the exchange protocol, routing, owner-side gather and
+    AdamW are CudaShardOps'; the per-rank forward / backward run on the rows fetched from their owners — projected
+    once per unique row through the (replicated) itemdnn / userdnn blocks, gather-summed per token — so no rank ever
+    builds a concat buffer. Needs the step-level prefetch protocol (one group per step)."""
+
+    fetched_rows_direct = True
+
+    def __init__(self, layout: FeatureLayout, local_table: torch.Tensor, mm, dnn, W: int):
+        super().__init__(layout, local_table, mm, W)
+        from .factored import FactoredEngine
+        # device pointers of EVERY rank's shard in this process' address space (NVLink peer memory / the other emulated
+        # ranks' tensors), own shard included. When set, the projection kernel reads the rows in place from their owners
+        # — no owner-side gather, no row all-to-all; the exchange protocol only synchronises (one barrier per step).
+        self.peers: Optional[List[int]] = None
+        self._bar = torch.zeros(1, device=local_table.device)
+        dev = local_table.device
+        dummy = [torch.nn.Parameter(torch.zeros((1, layout.H), device=dev), requires_grad=False) for _ in layout.tables]
+        self.feng = FactoredEngine(layout, dummy, mm, dnn, mode="fused", check_shapes=False)
+
+    def prepare(self, pbs: List[PackedBatch]):
+        g = self.feng.prepare(pbs)
+        return {"group": g, "n": g.n, "uniq": g.uniq, "n_unique": g.n_unique, "cap": int(g.c.cap), "pbs": list(pbs)}
+
+    def remap_all(self, pf, perm):
+        return   # ids already address the sorted unique list; the permutation is applied when the rows are projected
+
+    def forward_prefetched(self, pb: PackedBatch, st, out_dtype=None):
+        g = st["pf"]["group"]
+        if not g.c.projected:
+            if self.peers is not None:
+                if len(self.peers) != self.W or self.W > _lib.MAX_PEERS:
+                    raise ValueError("peer shard pointers do not match the world size")
+                g.c.src.n_peers = self.W
+                for r, ptr in enumerate(self.peers):
+                    g.c.src.peer_rows[r] = ptr
+            else:
+                g.c.src.fetched_rows = st["rows_buf"].data_ptr()
+                g.c.src.fetched_perm = st["perm"].data_ptr()
+                g.keep = (st["rows_buf"], st["perm"])
+        return self.feng.fact_forward(g, pb)
+
+    def reduce_cached(self, pf, calls):
+        g = pf["group"]
+        if not g.done:
+            raise RuntimeError("fused_step before the backward of every prefetched call")
+        return g.rows("G")
+
+    def release(self, pf):
+        pf["group"].release()
+
+    @property
+    def total_launches(self):
+        return self.launches + self.feng.launches
+
+
 class _KeyEngine(EmbeddingEngine):
     """EmbeddingEngine plumbing (key build / sort / dedup / reduce) without owning real tables: the global
     key space comes from the layout, table pointers are never dereferenced by those kernels."""
@@ -418,10 +474,15 @@ class ShardedRank:
     #   C  prefetch_gen       : owner gathers rows -> all-to-all rows back -> rows_buf
     # The backward then sends gradient rows only (the owner already knows which rows each source asked for,
     # in which order): no ids, no counts, no host sync.
-    @staticmethod
-    def _to_host_async(t: torch.Tensor):
+    def _to_host_async(self, t: torch.Tensor):
         if t.is_cuda:
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            ring = self.__dict__.setdefault("_pin_ring", [])
+            if len(ring) < 4 or ring[0].shape != t.shape or ring[0].dtype != t.dtype:
+                ring.insert(0, torch.empty(t.shape, dtype=t.dtype, pin_memory=True))   # pinned buffers are recycled
+                del ring[4:]
+            else:
+                ring.insert(0, ring.pop())
+            h = ring[0]
             h.copy_(t, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
@@ -465,9 +526,22 @@ class ShardedRank:
         if p["stage"] == 1:
             yield from self.finish_prepare_gen()
         self.prep = None
-        served = ops.gather(p["recv_rows"], p["R"])
-        back = yield ("a2a_v", served, p["recv_counts"], p["send_counts"])
-        rows_buf = torch.cat([torch.zeros((1, self.layout.H), dtype=back.dtype, device=back.device), back], dim=0)
+        if getattr(ops, "peers", None) is not None:
+            # rows are read in place from the owners' shards by the projection kernel: all that is left of the forward
+            # exchange is ordering — every owner's previous row update must be complete before anybody reads. The
+            # local-row id all-to-all of this step was enqueued AFTER that update on every rank and completes here
+            # only once every peer's part has arrived, so it already is that barrier — unless some pair of ranks
+            # exchanged nothing, in which case an explicit one is issued.
+            if min(p["send_counts"]) == 0 or min(p["recv_counts"]) == 0:
+                yield ("barrier", ops._bar)
+            back = None
+        else:
+            served = ops.gather(p["recv_rows"], p["R"])
+            back = yield ("a2a_v", served, p["recv_counts"], p["send_counts"])
+        if back is None or getattr(ops, "fetched_rows_direct", False):
+            rows_buf = back          # the factored kernels index the received rows through the permutation
+        else:
+            rows_buf = torch.cat([torch.zeros((1, self.layout.H), dtype=back.dtype, device=back.device), back], dim=0)
         self.pf = {"pbs": list(pbs), "pf": p["pf"], "perm": p["perm"], "rows_buf": rows_buf, "send_counts": p["send_counts"],
                    "recv_counts": p["recv_counts"], "U": p["U"], "R": p["R"], "owner": p["owner"]}
         self.last_fwd = {"U": p["U"], "R": p["R"], "send_counts": p["send_counts"], "recv_counts": p["recv_counts"]}
@@ -477,6 +551,8 @@ class ShardedRank:
         ops, W = self.ops, self.W
         st = getattr(self, "pf", None)
         if st is not None and any(pb is q for q in st["pbs"]):
+            if hasattr(ops, "forward_prefetched"):
+                return ops.forward_prefetched(pb, st, out_dtype)
             rm = st["pf"].get("remapped")
             if rm is not None:
                 return ops.forward_from_rows(pb, st["pf"]["uniq"], st["pf"]["n_unique"], st["perm"], st["rows_buf"],
@@ -513,6 +589,8 @@ class ShardedRank:
             gb = ops.permute(grads, st["perm"], st["pf"]["n_unique"], st["pf"]["cap"])
             recv_grads = yield ("a2a_v", gb[:st["U"]], st["send_counts"], st["recv_counts"])
             ops.apply_cached(st["owner"], recv_grads, st["R"], hyper)
+            if hasattr(ops, "release"):
+                ops.release(st["pf"])
             self.last_step = {"U": st["U"], "R": st["R"], "send_counts": st["send_counts"], "recv_counts": st["recv_counts"]}
             return st["U"]
         if pend:
@@ -538,17 +616,23 @@ class ShardedRank:
 def run_distributed(gen: Generator, group=None):
     """Drive one rank's generator with torch.distributed collectives (NCCL on GPUs, gloo on CPU)."""
     import torch.distributed as dist
+    pg = group if group is not None else dist.group.WORLD
     try:
         req = next(gen)
         while True:
-            if req[0] == "a2a_equal":
+            # straight to the ProcessGroup (the torch.distributed wrappers cost 50-75 us of host time per call);
+            # wait() only orders the current stream behind the collective, the host does not block
+            if req[0] == "barrier":
+                pg.allreduce([req[1]]).wait()
+                out = None
+            elif req[0] == "a2a_equal":
                 out = torch.empty_like(req[1])
-                dist.all_to_all_single(out, req[1].contiguous(), group=group)
+                pg.alltoall_base(out, req[1].contiguous(), [], []).wait()
             else:
                 _, t, ss, rs = req
                 t = t.contiguous()
                 out = torch.empty((sum(rs),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-                dist.all_to_all_single(out, t, output_split_sizes=rs, input_split_sizes=ss, group=group)
+                pg.alltoall_base(out, t, list(rs), list(ss)).wait()
             req = gen.send(out)
     except StopIteration as e:
         return e.value
@@ -571,7 +655,9 @@ def run_emulated(gens: List[Generator]):
         kind = reqs[0][0]
         assert all(r[0] == kind for r in reqs), "ranks diverged"
         outs = []
-        if kind == "a2a_equal":
+        if kind == "barrier":
+            outs = [None] * W
+        elif kind == "a2a_equal":
             for r in range(W):
                 outs.append(torch.stack([reqs[s][1][r] for s in range(W)]))
         else:
@@ -622,27 +708,94 @@ class ShardedGatherConcatFn(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+class ShardedFactoredFn(torch.autograd.Function):
+    """Factored flavour: forward returns feat2emb's output itself; the replicated DNN / emb_transform gradients come
+    back from the backward of the step's last call (they are the caller's to all-reduce), row gradients stay queued
+    for fused_step's exchange with the owners."""
+
+    @staticmethod
+    def forward(ctx, mod, pb, needs_grad, *params):
+        st = getattr(mod.rank_state, "pf", None)
+        if st is None or not any(pb is q for q in st["pbs"]):
+            raise RuntimeError("the factored sharded path needs prefetch(all calls of the step) before feat2emb_packed")
+        out = mod._run(mod.rank_state.forward_gen(pb))
+        g = st["pf"]["group"]
+        ctx.mod, ctx.pb, ctx.group = mod, pb, g
+        ctx.n_params = len(params)
+        if needs_grad:
+            g.n_fwd += 1
+        return out.view(pb.B, pb.L, -1)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        mod, pb, g = ctx.mod, ctx.pb, ctx.group
+        grads = [None] * ctx.n_params
+        mod.rank_state.queue(pb, None, None)
+        if not mod.ops.feng.fact_backward(g, pb, d_out):
+            return (None, None, None, *grads)
+        a = g.acc
+        names = list(mod.layout.item_emb_feat)
+        for j, k in enumerate(names):
+            grads[2 * j] = a[f"dWmm/{k}"]
+            grads[2 * j + 1] = a.get(f"dbmm/{k}")
+        o = 2 * len(names)
+        grads[o], grads[o + 1] = a["dW_item"], a["db_item"]
+        grads[o + 2], grads[o + 3] = a["dW_user"], a["db_user"]
+        return (None, None, None, *grads)
+
+
 class ShardedBaselineEmbedding(torch.nn.Module):
     """Row-sharded variant of ``BaselineEmbedding``: this rank's slice of the flat table lives in
     ``local_table``; emb_transform / itemdnn / userdnn are replicated (their gradients are the caller's
     to all-reduce, as in any data-parallel run). Row updates are always fused (``fused_step``)."""
 
-    def __init__(self, user_num, item_num, feat_statistics, feat_types, args, rank: int, world_size: int, group=None):
+    def __init__(self, user_num, item_num, feat_statistics, feat_types, args, rank: int, world_size: int, group=None,
+                 path: str = "concat", p2p: bool = True):
         super().__init__()
+        if path not in ("concat", "factored"):
+            raise ValueError("path must be 'concat' or 'factored'")
+        self.path = path
         H = args.hidden_units
         lay = FeatureLayout(user_num, item_num, feat_statistics, feat_types, H)
         self.layout = lay
         self.rank, self.W, self.group = rank, world_size, group
         self.dev = args.device
         n_local = shard_rows(lay.total_rows, world_size)
-        self.local_table = torch.nn.Parameter(torch.zeros((n_local, H), device=args.device), requires_grad=False)
+        local, self._symm = self._alloc_shard(n_local, H, args.device, world_size, group, path == "factored" and p2p)
+        self.local_table = torch.nn.Parameter(local, requires_grad=False)
         self.emb_transform = torch.nn.ModuleDict({k: torch.nn.Linear(d, H) for k, d in lay.item_emb_feat.items()})
         self.userdnn = torch.nn.Linear(lay.user_dim, H)
         self.itemdnn = torch.nn.Linear(lay.item_dim, H)
         self.to(args.device)
-        self.ops = CudaShardOps(lay, self.local_table.data, dict(self.emb_transform.items()), world_size)
+        if path == "factored":
+            self.ops = FactShardOps(lay, self.local_table.data, dict(self.emb_transform.items()),
+                                    {"item": self.itemdnn, "user": self.userdnn}, world_size)
+        else:
+            self.ops = CudaShardOps(lay, self.local_table.data, dict(self.emb_transform.items()), world_size)
+        if self._symm is not None:
+            # every rank's shard mapped into this process (CUDA VMM handles exchanged at the rendezvous)
+            self._peer_views = [self._symm.get_buffer(r, (n_local, H), torch.float32) for r in range(world_size)]
+            self.ops.peers = [t.data_ptr() for t in self._peer_views]
         self.rank_state = ShardedRank(lay, self.ops, rank, world_size)
         self._run = lambda gen: run_distributed(gen, self.group)
+
+    @staticmethod
+    def _alloc_shard(n_local: int, H: int, device, world_size: int, group, want_p2p: bool):
+        """The rank's slice of the flat table. With p2p (factored path, W > 1, NCCL group up) it is allocated as torch
+        symmetric memory so the other ranks' kernels can read its rows over NVLink; (tensor, handle | None)."""
+        import torch.distributed as dist
+        dev = torch.device(device)
+        if want_p2p and world_size > 1 and dev.type == "cuda" and dist.is_available() and dist.is_initialized():
+            try:
+                import torch.distributed._symmetric_memory as symm
+                t = symm.empty((n_local, H), dtype=torch.float32, device=dev)
+                hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+                t.zero_()
+                return t, hdl
+            except Exception as e:     # no VMM / fabric support on this box: the NCCL exchange still works
+                import warnings
+                warnings.warn(f"symmetric memory unavailable ({e}); rows go through the NCCL all-to-all")
+        return torch.zeros((n_local, H), device=device), None
 
     def load_full_tables(self, tables: Sequence[torch.Tensor]):
         """Take this rank's slice out of full per-table tensors (layout order) — e.g. a reference checkpoint."""
@@ -654,6 +807,11 @@ class ShardedBaselineEmbedding(torch.nn.Module):
         params = []
         for k in self.layout.item_emb_feat:
             params += [self.emb_transform[k].weight, self.emb_transform[k].bias]
+        if self.path == "factored":
+            params += [self.itemdnn.weight, self.itemdnn.bias, self.userdnn.weight, self.userdnn.bias]
+            needs = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+            out = ShardedFactoredFn.apply(self, pb, needs, *params)
+            return out.to(torch.bfloat16) if _concat_dtype() == torch.bfloat16 else out
         item_cat, user_cat = ShardedGatherConcatFn.apply(self, pb, _concat_dtype(), *params)
         B, L = pb.B, pb.L
         out = torch.relu(self.itemdnn(item_cat.view(B, L, -1)))

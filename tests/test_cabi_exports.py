@@ -54,8 +54,10 @@ def test_ctypes_structs_match_the_c_compiler(lib, tmp_path):
     import subprocess
     names = {"tgr_table_t": _lib.Table, "tgr_slot_t": _lib.Slot, "tgr_call_t": _lib.Call, "tgr_adam_t": _lib.Adam,
              "tgr_dnn_t": _lib.Dnn, "tgr_mm_feat_t": _lib.MmFeat, "tgr_fact_params_t": _lib.FactParams,
-             "tgr_fact_grads_t": _lib.FactGrads, "tgr_fact_group_t": _lib.FactGroup}
-    offs = [("tgr_fact_group_t", "calls"), ("tgr_fact_group_t", "mm_x"), ("tgr_fact_group_t", "cap"),
+             "tgr_fact_grads_t": _lib.FactGrads, "tgr_fact_group_t": _lib.FactGroup,
+             "tgr_row_source_t": _lib.RowSource}
+    offs = [("tgr_fact_group_t", "calls"), ("tgr_fact_group_t", "mm_x"), ("tgr_fact_group_t", "src"), ("tgr_fact_group_t", "cap"), ("tgr_fact_group_t", "rows_local"),
+            ("tgr_row_source_t", "save_rows"),
             ("tgr_fact_group_t", "P"), ("tgr_fact_group_t", "mmz"), ("tgr_fact_group_t", "ws_bytes"),
             ("tgr_fact_group_t", "n_backward"), ("tgr_fact_params_t", "b_item"), ("tgr_fact_params_t", "n_mm"),
             ("tgr_call_t", "err_flag"), ("tgr_dnn_t", "table_col")]

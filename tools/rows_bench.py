@@ -19,9 +19,9 @@ dW = torch.zeros(H, 1024, device=dev)
 ws = torch.empty(lib.tgr_fact_backward_workspace_bytes(1, H), dtype=torch.uint8, device=dev)
 def run(which):
     if which == "fwd":
-        _lib.check(lib.tgr_fact_project_rows(tabs, 1, H, C.byref(dnn), uniq.data_ptr(), nU.data_ptr(), U, P.data_ptr(), st))
+        _lib.check(lib.tgr_fact_project_rows(tabs, 1, H, C.byref(dnn), uniq.data_ptr(), nU.data_ptr(), U, None, P.data_ptr(), st))
     else:
-        _lib.check(lib.tgr_fact_unique_backward(tabs, 1, H, C.byref(dnn), uniq.data_ptr(), nU.data_ptr(), U, P.data_ptr(), dW.data_ptr(), None, ws.data_ptr(), ws.numel(), st))
+        _lib.check(lib.tgr_fact_unique_backward(tabs, 1, H, C.byref(dnn), uniq.data_ptr(), nU.data_ptr(), U, None, P.data_ptr(), dW.data_ptr(), None, ws.data_ptr(), ws.numel(), st))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for which in ("fwd", "bwd"):
     for _ in range(3): run(which)
