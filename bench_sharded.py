@@ -29,9 +29,17 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     worldgen = synth.SynthWorld(cfg, 0)
     lay = worldgen.layout
     margs = types.SimpleNamespace(device=str(dev), hidden_units=cfg.H)
+    n_batches = max(1, min(args.batches, args.steps + args.warmup))
+    steps_np = [worldgen.make_step(1000 * rank + s) for s in range(n_batches)]
+    # gradient window (symmetric memory, same size on every rank): half the largest step's lookup count bounds the
+    # unique rows of this workload with a wide margin; a step that does not fit falls back to the NCCL all-to-all
+    from tencent_recommendation_2025_b200.packed import count_valid
+    n_max = torch.tensor([max(sum(count_valid(lay, pc) for pc in st.calls) for st in steps_np)], device=dev)
+    dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
+    win_rows = max(1 << 20, int(n_max.item()) // 2)
     torch.manual_seed(0)                                   # identical dense parameters on every rank
     m = ShardedBaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), margs, rank, world,
-                                 path=args.path, p2p=not args.no_p2p)
+                                 path=args.path, p2p=not args.no_p2p, grad_window_rows=win_rows)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     with torch.no_grad():
         for p in m.parameters():
@@ -43,8 +51,6 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
                 m.local_table[t.key_base // world].zero_()
     dense = [p for p in m.parameters() if p is not m.local_table]
     dense_opt = torch.optim.AdamW(dense, lr=1e-3, betas=(0.9, 0.98), fused=True)
-    n_batches = max(1, min(args.batches, args.steps + args.warmup))
-    steps_np = [worldgen.make_step(1000 * rank + s) for s in range(n_batches)]
     dev_steps = [([to_device(lay, pc, dev) for pc in st.calls], [torch.from_numpy(r).to(dev) for r in st.upstream])
                  for st in steps_np]
     hyper = dict(lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
@@ -209,6 +215,9 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
                            "row_update": "fused sparse AdamW on the owner", "path": args.path,
                            "row_fetch": ("in place from the owners' shards over NVLink peer memory, fused into the projection kernel"
                                          if getattr(m.ops, "peers", None) is not None else "NCCL all-to-all of deduplicated rows"),
+                           "grad_exchange": ("owners pull the bucketed gradient rows in place over NVLink peer memory inside the "
+                                             "segmented reduce (+ one barrier)" if getattr(m.ops, "grad_peers", None) is not None
+                                             else "NCCL all-to-all of locally reduced gradient rows"),
                            "rows_per_step": int(total_rows // args.steps),
                            "l2": "per-step working set >> 126 MB L2; distinct batches cycled"},
                 "roofline": roofline, "cpu_baseline": None,

@@ -173,6 +173,14 @@ int tgr_bwd_reduce(const tgr_table_t* tables, int n_tables, int H, const tgr_cal
                    const int32_t* seg_of_entry, float* grads_out, const tgr_adam_t* adam, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* The same fixed-tile reduction + AdamW (mode 1) over rows of up to 32 flat buffers instead of concat gradients:
+ * src = b << 24 | row, contribution = row_bases[b][row, 0:H]. Used by the owner side of the row-sharded exchange with
+ * row_bases[b] pointing INTO rank b's bucketed gradient buffer (NVLink peer memory): the reduction pulls the rows in
+ * place, there is no gradient all-to-all. row_bases is a HOST array of device pointers. */
+int tgr_bwd_reduce_rows(const tgr_table_t* tables, int n_tables, int H, const float* const* row_bases, int n_bases,
+                        const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n, const tgr_adam_t* adam,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* AdamW row update from already-reduced rows: for u < *n_unique_dev: row(uniq[u]) <- adamw(row, grads[u]). */
 int tgr_adam_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
                   const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam, void* stream);
@@ -202,6 +210,12 @@ int tgr_remap_ids(const int32_t* ids, int64_t n, int n_cols, const uint32_t* col
  * zero-filled by the caller (padding ids stay 0). ids_out is a HOST array of device pointers. */
 int tgr_remap_scatter(const uint32_t* srcs_sorted, const int32_t* seg_of_entry, int64_t n, const int32_t* perm,
                       const tgr_call_t* calls, int n_calls, int32_t* const* ids_out, void* stream);
+
+/* out[u, :] = peer_rows[uniq[u] % n_peers][uniq[u] / n_peers, :] for u < *n_unique_dev: this step's rows copied in
+ * place out of their owners' shards over NVLink peer memory (replaces owner-side gather + row all-to-all). A latency-
+ * bound copy: meant for a side stream next to value-independent work. peer_rows is a HOST array of device pointers. */
+int tgr_fetch_peer_rows(const float* const* peer_rows, int n_peers, int H, const uint32_t* uniq, const int32_t* n_unique_dev,
+                        int64_t max_unique, float* out, void* stream);
 
 /* The same remap for the values of every ARRAY slot of up to 4 calls in one launch (searching: a token may hold
  * several values, so the pairs' (call, slot, token) code does not address them). arr_out[c] is indexed like

@@ -130,6 +130,8 @@ SIGNATURES = {
     "tgr_bwd_reduce": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Call), C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Adam), C.c_void_p, C.c_size_t,
                                  C.c_void_p]),
+    "tgr_bwd_reduce_rows": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.POINTER(Adam), C.c_void_p, C.c_size_t, C.c_void_p]),
     "tgr_adam_rows": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.POINTER(Adam), C.c_void_p]),
     "tgr_scatter_rows": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
@@ -141,6 +143,8 @@ SIGNATURES = {
                                 C.c_void_p]),
     "tgr_remap_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Call), C.c_int,
                                     C.POINTER(C.c_void_p), C.c_void_p]),
+    "tgr_fetch_peer_rows": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p]),
     "tgr_remap_arrays": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(Call), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_void_p), C.c_void_p]),
     "tgr_permute_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),

@@ -395,3 +395,49 @@ extern "C" int tgr_bwd_reduce(const tgr_table_t* tables, int n_tables, int H, co
   if (H4 <= 64) return launch_reduce<32, 2>(p, &rp, bf16, n_cta, st);
   return launch_reduce<32, 4>(p, &rp, bf16, n_cta, st);
 }
+
+// Owner side of the row-sharded exchange without the gradient all-to-all: the contributions of source rank b are
+// rows of that rank's bucketed gradient buffer, read IN PLACE over NVLink peer memory by the same fixed-tile
+// segmented reduction (+ AdamW) — src = b << 24 | row inside row_bases[b].
+extern "C" int tgr_bwd_reduce_rows(const tgr_table_t* tables, int n_tables, int H, const float* const* row_bases,
+                                   int n_bases, const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n,
+                                   const tgr_adam_t* adam, void* workspace, size_t workspace_bytes, void* stream) {
+  tgr::TimedScope tgr_timed_("bwd_reduce_rows", stream);
+  TGR_REQUIRE(H > 0 && H % 4 == 0 && H <= 512, "H=%d unsupported (multiple of 4, <= 512)", H);
+  TGR_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
+  TGR_REQUIRE(n_bases > 0 && n_bases <= TGR_MAX_SLOTS && row_bases, "n_bases out of range");
+  if (n == 0) return 0;
+  TGR_REQUIRE(keys_sorted && srcs_sorted && workspace && adam, "null argument");
+  TGR_REQUIRE(workspace_bytes >= tgr_reduce_workspace_bytes(n, H), "workspace too small");
+  RedParams p{};
+  RowParams rp{};
+  for (int b = 0; b < n_bases; ++b) {
+    TGR_REQUIRE(row_bases[b] != nullptr, "row base %d is NULL", b);
+    p.chunk_base[0][b] = (const char*)row_bases[b];     // call field 0, slot field = source rank
+    p.ld_bytes[0][b] = (int64_t)H * 4;
+  }
+  p.keys = keys_sorted;
+  p.srcs = srcs_sorted;
+  p.n = n;
+  p.H4 = H / 4;
+  p.mode = 1;
+  const int tile = red_tile(p.H4);
+  const int n_cta = (int)((n + tile - 1) / tile);
+  const size_t part = align_up((size_t)(n_cta + 1) * H * sizeof(float));
+  char* ws = (char*)workspace;
+  p.cta_head = (float*)ws;
+  p.cta_tail = (float*)(ws + part);
+  if (int rc = fill_row_params(rp, tables, n_tables, H)) return rc;
+  for (int t = 0; t < n_tables; ++t) TGR_REQUIRE(rp.w[t] && rp.m[t] && rp.v[t], "table %d: weight/exp_avg/exp_avg_sq NULL", t);
+  rp.adam = *adam;
+  p.row_buf = (float*)(ws + 2 * part);
+  p.row_keys = (uint32_t*)(ws + 2 * part + align_up((size_t)n_cta * tile * H * sizeof(float)));
+  p.row_cnt = (int32_t*)((char*)p.row_keys + align_up((size_t)n_cta * tile * 4));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H4 = p.H4;
+  if (H4 <= 8) return launch_reduce<8, 1>(p, &rp, false, n_cta, st);
+  if (H4 <= 16) return launch_reduce<16, 1>(p, &rp, false, n_cta, st);
+  if (H4 <= 32) return launch_reduce<32, 1>(p, &rp, false, n_cta, st);
+  if (H4 <= 64) return launch_reduce<32, 2>(p, &rp, false, n_cta, st);
+  return launch_reduce<32, 4>(p, &rp, false, n_cta, st);
+}

@@ -15,17 +15,23 @@ constexpr int kMaxW = 64;
 __global__ void __launch_bounds__(kRouteBlock) route_count_kernel(const uint32_t* __restrict__ uniq,
                                                                   const int32_t* __restrict__ n_dev, int W, int nb,
                                                                   int32_t* __restrict__ cnt /*[W][nb]*/) {
+  __shared__ int32_t s_cnt[kMaxW];
   const int n = *n_dev;
   if ((int)blockIdx.x * kRouteBlock >= n) {   // the grid covers the capacity bound; blocks past *n_dev just report zeros
     if (threadIdx.x < W) cnt[threadIdx.x * nb + blockIdx.x] = 0;
     return;
   }
+  if (threadIdx.x < W) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const int i = blockIdx.x * kRouteBlock + threadIdx.x;
   const int owner = i < n ? (int)(__ldg(uniq + i) % (uint32_t)W) : -1;
-  for (int w = 0; w < W; ++w) {
-    const int c = __syncthreads_count(owner == w);
-    if (threadIdx.x == 0) cnt[w * nb + blockIdx.x] = c;
+  const int lane = threadIdx.x & 31;
+  for (int w = 0; w < W; ++w) {               // warp ballots; integer shared-memory atomics (totals are order independent)
+    const unsigned b = __ballot_sync(0xffffffffu, owner == w);
+    if (lane == 0 && b) atomicAdd(&s_cnt[w], __popc(b));
   }
+  __syncthreads();
+  if (threadIdx.x < W) cnt[threadIdx.x * nb + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
 // exclusive scan over the w-major [W*nb] array (single CTA), then per-owner totals
@@ -78,36 +84,26 @@ __global__ void __launch_bounds__(kRouteBlock) route_emit_kernel(const uint32_t*
                                                                  const int32_t* __restrict__ off /*[W][nb]*/,
                                                                  uint32_t* __restrict__ local_rows,
                                                                  int32_t* __restrict__ perm) {
-  __shared__ int32_t warp_cnt[32];
+  __shared__ uint16_t warp_cnt[kRouteBlock / 32][kMaxW];   // keys of owner w in warp i
   const int n = *n_dev;
   if ((int)blockIdx.x * kRouteBlock >= n) return;
   const int i = blockIdx.x * kRouteBlock + threadIdx.x;
   const uint32_t key = i < n ? __ldg(uniq + i) : 0u;
   const int owner = i < n ? (int)(key % (uint32_t)W) : -1;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int r = 0;                                  // rank among the warp's earlier keys of the same owner
   for (int w = 0; w < W; ++w) {
-    const int v = owner == w;
-    const unsigned b = __ballot_sync(0xffffffffu, v);
-    const int r = __popc(b & ((1u << lane) - 1u));
-    if (lane == 0) warp_cnt[wid] = __popc(b);
-    __syncthreads();
-    if (wid == 0) {
-      int s = warp_cnt[lane];
-      const int orig = s;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += y;
-      }
-      warp_cnt[lane] = s - orig;
-    }
-    __syncthreads();
-    if (v) {
-      const int pos = off[w * nb + blockIdx.x] + warp_cnt[wid] + r;
-      local_rows[pos] = key / (uint32_t)W;
-      perm[i] = pos;
-    }
-    __syncthreads();
+    const unsigned b = __ballot_sync(0xffffffffu, owner == w);
+    if (owner == w) r = __popc(b & ((1u << lane) - 1u));
+    if (lane == 0) warp_cnt[wid][w] = (uint16_t)__popc(b);
+  }
+  __syncthreads();
+  if (owner >= 0) {
+    int before = 0;                           // stable: earlier warps first
+    for (int q = 0; q < wid; ++q) before += warp_cnt[q][owner];
+    const int pos = off[owner * nb + blockIdx.x] + before + r;
+    local_rows[pos] = key / (uint32_t)W;
+    perm[i] = pos;
   }
 }
 
@@ -331,4 +327,59 @@ extern "C" int tgr_remap_arrays(const tgr_table_t* tables, int n_tables, const t
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   remap_arrays_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, uniq, n_unique_dev, perm);
   return check_launch("remap_arrays");
+}
+
+// ---- rows of this step's unique keys fetched in place from their owners' shards (NVLink peer memory) -----------------
+// out[u, :] = peer[key % W][key / W, :]. A pure latency-hiding kernel (remote reads take ~2 us and bypass the local L2):
+// one H/4-lane group per row, 4 rows in flight per lane, so it is launched on a side stream next to value-independent
+// work instead of stalling the projection GEMM behind the fabric.
+namespace tgr {
+struct PeerPtrs { const float* p[TGR_MAX_PEERS]; };
+template <int LANES>
+__global__ void __launch_bounds__(256) fetch_peer_rows_kernel(const __grid_constant__ PeerPtrs peers, int W, int H4,
+                                                              const uint32_t* __restrict__ uniq,
+                                                              const int32_t* __restrict__ n_dev, float* __restrict__ out) {
+  constexpr int G = 256 / LANES, UN = 4;
+  const int n = *n_dev;
+  const int lane = threadIdx.x % LANES, grp = threadIdx.x / LANES;
+  for (int u0 = (blockIdx.x * G + grp) * UN; u0 < n; u0 += gridDim.x * G * UN) {
+    for (int c = lane; c < H4; c += LANES) {
+      float4 v[UN];
+#pragma unroll
+      for (int j = 0; j < UN; ++j) {
+        if (u0 + j < n) {
+          const uint32_t key = __ldg(uniq + u0 + j);
+          const float4* src = reinterpret_cast<const float4*>(peers.p[key % (uint32_t)W] + (size_t)(key / (uint32_t)W) * (H4 * 4));
+          v[j] = ld_stream(src + c);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UN; ++j)
+        if (u0 + j < n) reinterpret_cast<float4*>(out)[(size_t)(u0 + j) * H4 + c] = v[j];
+    }
+  }
+}
+}  // namespace tgr
+
+extern "C" int tgr_fetch_peer_rows(const float* const* peer_rows, int n_peers, int H, const uint32_t* uniq,
+                                   const int32_t* n_unique_dev, int64_t max_unique, float* out, void* stream) {
+  tgr::TimedScope tgr_timed_("fetch_peer_rows", stream);
+  TGR_REQUIRE(peer_rows && uniq && n_unique_dev && out, "null argument");
+  TGR_REQUIRE(n_peers > 0 && n_peers <= TGR_MAX_PEERS, "n_peers out of range");
+  TGR_REQUIRE(H > 0 && H % 4 == 0, "bad H");
+  if (max_unique <= 0) return 0;
+  PeerPtrs pp{};
+  for (int r = 0; r < n_peers; ++r) {
+    TGR_REQUIRE(peer_rows[r] != nullptr, "peer %d: shard pointer is NULL", r);
+    pp.p[r] = peer_rows[r];
+  }
+  const int H4 = H / 4;
+  const int lanes = H4 <= 8 ? 8 : (H4 <= 16 ? 16 : 32);
+  int64_t blocks = (max_unique + (256 / lanes) * 4 - 1) / ((256 / lanes) * 4);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lanes == 8) fetch_peer_rows_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(pp, n_peers, H4, uniq, n_unique_dev, out);
+  else if (lanes == 16) fetch_peer_rows_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(pp, n_peers, H4, uniq, n_unique_dev, out);
+  else fetch_peer_rows_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(pp, n_peers, H4, uniq, n_unique_dev, out);
+  return check_launch("fetch_peer_rows");
 }

@@ -363,6 +363,10 @@ class FactShardOps(CudaShardOps):
         # ranks' tensors), own shard included. When set, the projection kernel reads the rows in place from their owners
         # — no owner-side gather, no row all-to-all; the exchange protocol only synchronises (one barrier per step).
         self.peers: Optional[List[int]] = None
+        # gradient window: this rank's bucketed row gradients live in a buffer every owner can read over NVLink, so the
+        # owner-side reduction PULLS its contributions in place — no gradient all-to-all, one barrier instead.
+        self.grad_win: Optional[torch.Tensor] = None     # [rows, H] (symmetric memory)
+        self.grad_peers: Optional[List[int]] = None      # base pointer of every rank's window
         self._bar = torch.zeros(1, device=local_table.device)
         dev = local_table.device
         dummy = [torch.nn.Parameter(torch.zeros((1, layout.H), device=dev), requires_grad=False) for _ in layout.tables]
@@ -375,20 +379,88 @@ class FactShardOps(CudaShardOps):
     def remap_all(self, pf, perm):
         return   # ids already address the sorted unique list; the permutation is applied when the rows are projected
 
+    def fetch_rows_async(self, pf):
+        """Copy this step's unique rows out of their owners' shards (NVLink peer memory) into the group's arena on a
+        SIDE stream: remote reads are latency-bound (~2 us, no local L2), so they run next to whatever value-independent
+        work the caller enqueues now (the next step's key processing) instead of stalling the projection kernel."""
+        g = pf["group"]
+        if len(self.peers) != self.W or self.W > _lib.MAX_PEERS:
+            raise ValueError("peer shard pointers do not match the world size")
+        if g.n == 0:
+            g.fetch_done = None
+            return
+        dev = self.local.device
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(main)                      # behind the id all-to-all, i.e. behind every owner's previous update
+        self._side.wait_event(ready)
+        ptrs = (C.c_void_p * self.W)(*self.peers)
+        check(self.lib.tgr_fetch_peer_rows(ptrs, self.W, self.layout.H, g.c.uniq, g.c.n_unique, g.c.cap, g.c.rows_local,
+                                           self._side.cuda_stream), "tgr_fetch_peer_rows")
+        g.arena.record_stream(self._side)
+        g.fetch_done = torch.cuda.Event()
+        g.fetch_done.record(self._side)
+        self.launches += 1
+
     def forward_prefetched(self, pb: PackedBatch, st, out_dtype=None):
         g = st["pf"]["group"]
         if not g.c.projected:
             if self.peers is not None:
-                if len(self.peers) != self.W or self.W > _lib.MAX_PEERS:
-                    raise ValueError("peer shard pointers do not match the world size")
-                g.c.src.n_peers = self.W
-                for r, ptr in enumerate(self.peers):
-                    g.c.src.peer_rows[r] = ptr
+                done = getattr(g, "fetch_done", None)
+                if done is not None:
+                    torch.cuda.current_stream(self.local.device).wait_event(done)
+                g.c.src.fetched_rows = g.c.rows_local       # sorted unique order: no permutation
             else:
                 g.c.src.fetched_rows = st["rows_buf"].data_ptr()
                 g.c.src.fetched_perm = st["perm"].data_ptr()
                 g.keep = (st["rows_buf"], st["perm"])
         return self.feng.fact_forward(g, pb)
+
+    def prepare_owner(self, recv_rows: torch.Tensor, R: int, counts_dev: Optional[torch.Tensor] = None):
+        """Owner side, done ahead: stable sort of the requested local rows. With the gradient window the payload of
+        an entry is `source rank << 24 | index inside that source's bucket` (where the owner will pull the row from)."""
+        if self.grad_peers is None or counts_dev is None:
+            return super().prepare_owner(recv_rows, R)
+        if R == 0:
+            return None
+        dev = self.local.device
+        cnt = counts_dev.to(torch.int64)
+        src_rank = torch.repeat_interleave(torch.arange(self.W, device=dev), cnt, output_size=R)
+        first = torch.cumsum(cnt, 0) - cnt
+        code = ((src_rank << 24) | (torch.arange(R, device=dev) - first[src_rank])).to(torch.int32)
+        keys_out = torch.empty(R, dtype=torch.int32, device=dev)
+        code_out = torch.empty(R, dtype=torch.int32, device=dev)
+        ws = self._buf("sort", self.lib.tgr_sort_workspace_bytes(R), dev)
+        bits = max(1, int(self.local.shape[0] - 1).bit_length())
+        check(self.lib.tgr_sort_pairs(recv_rows.data_ptr(), code.data_ptr(), keys_out.data_ptr(), code_out.data_ptr(), R, bits,
+                                      ws.data_ptr(), ws.numel(), _stream()), "tgr_sort_pairs")
+        self.launches += 5
+        return keys_out, code_out
+
+    def permute_to_window(self, grads, perm, n_unique, cap):
+        check(self.lib.tgr_permute_rows(grads.data_ptr(), self.layout.H, perm.data_ptr(), n_unique.data_ptr(), cap, 0,
+                                        self.grad_win.data_ptr(), _stream()), "tgr_permute_rows")
+        self.launches += 1
+
+    def apply_from_peers(self, owner_state, starts: List[int], R: int, hyper: dict):
+        """Fixed-order segmented sum of the contributions pulled from every source's window + AdamW on the slice."""
+        self.step += 1
+        if R == 0 or owner_state is None:
+            return
+        keys_out, code_out = owner_state
+        H, dev = self.layout.H, self.local.device
+        bases = (C.c_void_p * self.W)(*[self.grad_peers[s] + 4 * H * starts[s] for s in range(self.W)])
+        tab = (_lib.Table * 1)()
+        tab[0].weight, tab[0].exp_avg, tab[0].exp_avg_sq = self.local.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        tab[0].rows, tab[0].key_base = self.local.shape[0], 0
+        adam = make_adam(hyper["lr"], hyper["betas"][0], hyper["betas"][1], hyper["eps"], hyper["weight_decay"], self.step,
+                         hyper.get("grad_scale", 1.0))
+        rws = self._buf("reduce", self.lib.tgr_reduce_workspace_bytes(R, H), dev)
+        check(self.lib.tgr_bwd_reduce_rows(tab, 1, H, bases, self.W, keys_out.data_ptr(), code_out.data_ptr(), R, C.byref(adam),
+                                           rws.data_ptr(), rws.numel(), _stream()), "tgr_bwd_reduce_rows")
+        self.launches += 3
 
     def reduce_cached(self, pf, calls):
         g = pf["group"]
@@ -493,6 +565,13 @@ class ShardedRank:
         ops = self.ops
         pf = ops.prepare(list(pbs))
         rows_b, perm, counts = ops.route(pf["uniq"], pf["n_unique"], pf["cap"])
+        if getattr(ops, "grad_peers", None) is not None:
+            # the owner will PULL gradient rows out of every source's window: it needs the whole W x W count matrix
+            # (where its bucket starts inside each source's buffer), so the counts are all-gathered
+            M = yield ("allgather", counts)                       # [W, W], M[s, o] = rows rank s sends to owner o
+            host = self._to_host_async(M)
+            self.prep = {"pbs": list(pbs), "pf": pf, "rows_b": rows_b, "perm": perm, "host": host, "stage": 1, "M": M}
+            return None
         recv_counts_t = yield ("a2a_equal", counts)
         host = self._to_host_async(torch.stack([counts, recv_counts_t]))
         self.prep = {"pbs": list(pbs), "pf": pf, "rows_b": rows_b, "perm": perm, "host": host, "stage": 1}
@@ -506,13 +585,25 @@ class ShardedRank:
         h, ev = p["host"]
         if ev is not None:
             ev.synchronize()          # normally long complete: the copy was issued a phase earlier
-        send_counts, recv_counts = h[0].tolist(), h[1].tolist()
+        starts, window = None, False
+        if "M" in p:
+            M = h.tolist()
+            send_counts, recv_counts = M[self.rank], [M[s][self.rank] for s in range(self.W)]
+            starts = [sum(M[s][:self.rank]) for s in range(self.W)]      # my bucket's first row in source s' window
+            # every rank sees the same matrix, so all of them take the same branch
+            window = max(sum(row) for row in M) <= ops.grad_win.shape[0] and max(max(row) for row in M) < (1 << 24)
+        else:
+            send_counts, recv_counts = h[0].tolist(), h[1].tolist()
         U, R = sum(send_counts), sum(recv_counts)
         recv_rows = yield ("a2a_v", p["rows_b"][:U], send_counts, recv_counts)
-        owner_state = ops.prepare_owner(recv_rows, R)
+        if window:
+            owner_state = ops.prepare_owner(recv_rows, R, counts_dev=p["M"][:, self.rank])
+        else:
+            owner_state = ops.prepare_owner(recv_rows, R)
         if hasattr(ops, "remap_all"):
             ops.remap_all(p["pf"], p["perm"])
-        p.update(send_counts=send_counts, recv_counts=recv_counts, U=U, R=R, recv_rows=recv_rows, owner=owner_state, stage=2)
+        p.update(send_counts=send_counts, recv_counts=recv_counts, U=U, R=R, recv_rows=recv_rows, owner=owner_state, stage=2,
+                 starts=starts, window=window)
         return None
 
     def prefetch_gen(self, pbs: List[PackedBatch]) -> Generator:
@@ -534,6 +625,7 @@ class ShardedRank:
             # exchanged nothing, in which case an explicit one is issued.
             if min(p["send_counts"]) == 0 or min(p["recv_counts"]) == 0:
                 yield ("barrier", ops._bar)
+            ops.fetch_rows_async(p["pf"])
             back = None
         else:
             served = ops.gather(p["recv_rows"], p["R"])
@@ -543,7 +635,8 @@ class ShardedRank:
         else:
             rows_buf = torch.cat([torch.zeros((1, self.layout.H), dtype=back.dtype, device=back.device), back], dim=0)
         self.pf = {"pbs": list(pbs), "pf": p["pf"], "perm": p["perm"], "rows_buf": rows_buf, "send_counts": p["send_counts"],
-                   "recv_counts": p["recv_counts"], "U": p["U"], "R": p["R"], "owner": p["owner"]}
+                   "recv_counts": p["recv_counts"], "U": p["U"], "R": p["R"], "owner": p["owner"],
+                   "starts": p.get("starts"), "window": p.get("window", False)}
         self.last_fwd = {"U": p["U"], "R": p["R"], "send_counts": p["send_counts"], "recv_counts": p["recv_counts"]}
         return p["U"]
 
@@ -586,9 +679,17 @@ class ShardedRank:
                 raise RuntimeError("fused_step after prefetch needs the gradient of every prefetched call")
             calls = [by_id[id(pb)] for pb in st["pbs"]]            # source codes carry the prefetch call order
             grads = ops.reduce_cached(st["pf"], calls)
-            gb = ops.permute(grads, st["perm"], st["pf"]["n_unique"], st["pf"]["cap"])
-            recv_grads = yield ("a2a_v", gb[:st["U"]], st["send_counts"], st["recv_counts"])
-            ops.apply_cached(st["owner"], recv_grads, st["R"], hyper)
+            if st.get("window"):
+                # bucketed gradient rows go into this rank's window; once every rank has written (barrier) each owner's
+                # reduction pulls its contributions over NVLink. The window is next written a whole step later, after
+                # the following id all-to-all — which every owner enqueues behind this update.
+                ops.permute_to_window(grads, st["perm"], st["pf"]["n_unique"], st["pf"]["cap"])
+                yield ("barrier", ops._bar)
+                ops.apply_from_peers(st["owner"], st["starts"], st["R"], hyper)
+            else:
+                gb = ops.permute(grads, st["perm"], st["pf"]["n_unique"], st["pf"]["cap"])
+                recv_grads = yield ("a2a_v", gb[:st["U"]], st["send_counts"], st["recv_counts"])
+                ops.apply_cached(st["owner"], recv_grads, st["R"], hyper)
             if hasattr(ops, "release"):
                 ops.release(st["pf"])
             self.last_step = {"U": st["U"], "R": st["R"], "send_counts": st["send_counts"], "recv_counts": st["recv_counts"]}
@@ -625,6 +726,10 @@ def run_distributed(gen: Generator, group=None):
             if req[0] == "barrier":
                 pg.allreduce([req[1]]).wait()
                 out = None
+            elif req[0] == "allgather":
+                t = req[1].contiguous()
+                out = torch.empty((pg.size(),) + tuple(t.shape), dtype=t.dtype, device=t.device)
+                pg._allgather_base(out, t).wait()
             elif req[0] == "a2a_equal":
                 out = torch.empty_like(req[1])
                 pg.alltoall_base(out, req[1].contiguous(), [], []).wait()
@@ -657,6 +762,9 @@ def run_emulated(gens: List[Generator]):
         outs = []
         if kind == "barrier":
             outs = [None] * W
+        elif kind == "allgather":
+            full = torch.stack([reqs[s][1] for s in range(W)])
+            outs = [full.clone() for _ in range(W)]
         elif kind == "a2a_equal":
             for r in range(W):
                 outs.append(torch.stack([reqs[s][1][r] for s in range(W)]))
@@ -750,7 +858,7 @@ class ShardedBaselineEmbedding(torch.nn.Module):
     to all-reduce, as in any data-parallel run). Row updates are always fused (``fused_step``)."""
 
     def __init__(self, user_num, item_num, feat_statistics, feat_types, args, rank: int, world_size: int, group=None,
-                 path: str = "concat", p2p: bool = True):
+                 path: str = "concat", p2p: bool = True, grad_window_rows: int = 1 << 20):
         super().__init__()
         if path not in ("concat", "factored"):
             raise ValueError("path must be 'concat' or 'factored'")
@@ -776,6 +884,12 @@ class ShardedBaselineEmbedding(torch.nn.Module):
             # every rank's shard mapped into this process (CUDA VMM handles exchanged at the rendezvous)
             self._peer_views = [self._symm.get_buffer(r, (n_local, H), torch.float32) for r in range(world_size)]
             self.ops.peers = [t.data_ptr() for t in self._peer_views]
+            # gradient window (same size on every rank): steps whose unique rows exceed it use the NCCL all-to-all
+            win, self._symm_win = self._alloc_shard(int(grad_window_rows), H, args.device, world_size, group, True)
+            if self._symm_win is not None:
+                self._win_views = [self._symm_win.get_buffer(r, tuple(win.shape), torch.float32) for r in range(world_size)]
+                self.ops.grad_win = win
+                self.ops.grad_peers = [t.data_ptr() for t in self._win_views]
         self.rank_state = ShardedRank(lay, self.ops, rank, world_size)
         self._run = lambda gen: run_distributed(gen, self.group)
 

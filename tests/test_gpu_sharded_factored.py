@@ -40,10 +40,13 @@ def setup(W, B=16, L=33, H=64, seed=3, p2p=False):
     for r in range(W):
         ops = FactShardOps(lay, shard_of_tables(tables, r, W), dict(full.emb_transform.items()), dnn, W)
         ranks.append(ShardedRank(lay, ops, r, W))
-    if p2p:   # emulated ranks share one address space: every rank reads the others' shards in place
+    if p2p:   # emulated ranks share one address space: every rank reads the others' shards / gradient windows in place
         ptrs = [rk.ops.local.data_ptr() for rk in ranks]
-        for rk in ranks:
+        wins = [torch.zeros((1 << 14, H), device="cuda") for _ in ranks]
+        for rk, w_ in zip(ranks, wins):
             rk.ops.peers = list(ptrs)
+            rk.ops.grad_win = w_
+            rk.ops.grad_peers = [x.data_ptr() for x in wins]
     steps = [world.make_step(r) for r in range(W)]                       # rank r's data-parallel share
     pbs = [[to_device(lay, pc, "cuda") for pc in st.calls] for st in steps]
     return cfg, full, lay, ranks, steps, pbs
@@ -150,3 +153,38 @@ def test_sharded_factored_step_matches_oracle_and_is_deterministic(W, p2p):
             assert np.abs(s - tot[name]).max() <= 1e-5 * np.abs(tot[name]).max(), name
     for a, b in zip(*results):
         assert torch.equal(a, b), "sharded factored step must be bitwise reproducible"
+
+
+def test_peer_source_projection_equals_table_source():
+    """tgr_row_source_t.peer_rows (rows read in place from W shards inside the projection kernel) and
+    tgr_fetch_peer_rows + fetched_rows give the table-source projection bit for bit."""
+    import ctypes as C
+    from tencent_recommendation_2025_b200 import _lib
+    from tencent_recommendation_2025_b200.engine import _stream
+    from tencent_recommendation_2025_b200.sharded import shard_of_tables
+    W = 4
+    cfg, full, lay, ranks, steps, pbs = setup(1)
+    eng = full.engine
+    g = eng.prepare(pbs[0])
+    lib, H, nt = eng.lib, lay.H, len(eng.tables)
+    cap = int(g.c.cap)
+    shards = [shard_of_tables([p.data for p in eng.tables], r, W) for r in range(W)]
+    outs = []
+    for mode in ("table", "peer", "fetched"):
+        P = torch.zeros((cap, H), device="cuda")
+        src = _lib.RowSource()
+        keep = None
+        if mode == "peer":
+            src.n_peers = W
+            for r in range(W):
+                src.peer_rows[r] = shards[r].data_ptr()
+        elif mode == "fetched":
+            keep = torch.zeros((cap, H), device="cuda")
+            ptrs = (C.c_void_p * W)(*[s.data_ptr() for s in shards])
+            _lib.check(lib.tgr_fetch_peer_rows(ptrs, W, H, g.c.uniq, g.c.n_unique, cap, keep.data_ptr(), _stream()))
+            src.fetched_rows = keep.data_ptr()
+        _lib.check(lib.tgr_fact_project_rows(eng._table_array(), nt, H, C.byref(eng._params().dnn), g.c.uniq, g.c.n_unique, cap,
+                                             C.byref(src), P.data_ptr(), _stream()))
+        torch.cuda.synchronize()
+        outs.append(P[: int(g.n_unique.item())].clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
