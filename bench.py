@@ -323,7 +323,8 @@ def run_gpu(args):
     cand = [n_ for n_ in table if "GBs" in table[n_]]
     dom = max(cand, key=lambda n_: table[n_]["ms_per_step"]) if cand else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": table[dom]["GBs"] if dom else 0.0, "peak": hbm_peak,
-                "unit": "GB/s", "frac": table[dom]["frac"] if dom else 0.0, "traffic": load_traffic(dom),
+                "unit": "GB/s", "frac": table[dom]["frac"] if dom else 0.0,
+                "traffic": load_traffic(dom, table[dom]["launches_per_step"] if dom else 1),
                 "peak_source": peak_src,
                 "kernel_ms_per_step": table[dom]["ms_per_step"] if dom else 0.0,
                 "launches": int(kern_ms[dom][1]) if dom else 0,
@@ -407,13 +408,15 @@ def run_gpu(args):
     print(json.dumps(line))
 
 
-def load_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
+def load_traffic(kernel, launches_per_step=1):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the C-ABI entry `kernel`, from the committed
+    `ncu --set full` capture of one C2 step (profiles/traffic.json holds bytes per STEP per entry), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if kernel is None or not os.path.exists(p):
         return None
     try:
-        return json.load(open(p)).get(kernel)
+        v = json.load(open(p)).get(kernel)
+        return None if v is None else int(v / max(launches_per_step, 1))
     except Exception:
         return None
 

@@ -203,7 +203,7 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
         dom = max(cand, key=lambda n_: table[n_]["ms_per_step"]) if cand else None
         roofline = {"bound": "hbm", "kernel": (dom or "") + " (rank 0)", "achieved": table[dom]["GBs"] if dom else 0.0,
                     "peak": hbm_peak, "unit": "GB/s", "frac": table[dom]["frac"] if dom else 0.0,
-                    "traffic": bench.load_traffic(dom), "peak_source": peak_src, "kernels": table,
+                    "traffic": bench.load_traffic(dom, table[dom]["launches_per_step"] if dom else 1), "peak_source": peak_src, "kernels": table,
                     "kernels_ms_per_step_sum": round(sum(v["ms_per_step"] for v in table.values()), 4)}
         line = {"metric": bench.METRIC, "value": total_rows / (ms * 1e-3), "unit": bench.UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(PKG, "libtgr_embed.so")
-SOURCES = ["tgr_util.cu", "tgr_fwd.cu", "tgr_mm.cu", "tgr_bwd.cu", "tgr_reduce.cu", "tgr_route.cu", "tgr_factored.cu", "tgr_fact_step.cu"]
+SOURCES = ["tgr_util.cu", "tgr_fwd.cu", "tgr_mm.cu", "tgr_bwd.cu", "tgr_sort.cu", "tgr_reduce.cu", "tgr_route.cu", "tgr_factored.cu", "tgr_fact_step.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "-I", INCLUDE, "-I", CSRC, "--expt-relaxed-constexpr", "-Xptxas", "-v"]

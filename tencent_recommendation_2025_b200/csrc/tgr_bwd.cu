@@ -7,7 +7,7 @@
 //
 //   build_keys   (key = table.key_base + id, src = call|slot|token) for every non-padding id of up to 4
 //                calls, compacted in (call, token, slot) order (count -> scan -> emit, no atomics)
-//   sort_pairs   stable LSD radix sort on the key bits only (stability keeps each row's contributions
+//   sort_pairs   (tgr_sort.cu) stable LSD radix sort on the key bits only (stability keeps each row's contributions
 //                in ascending (call, token) order = embedding_dense_backward's per-row order, F16)
 //   dedup        run-length encode -> unique keys / segment offsets / per-entry segment index
 //   reduce       fixed-tile segmented sum of the concat-gradient rows the sources point at; short runs
@@ -17,8 +17,6 @@
 //
 // All kernels are HBM/L2-bound integer/byte movers: 128-bit row accesses, one LANES=H/4 thread
 // group per gradient row, grids sized by the (host-known) entry count.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "tgr_common.cuh"
 #include "tgr_rows.cuh"
 
@@ -420,30 +418,6 @@ extern "C" int tgr_bwd_build_keys(const tgr_table_t* tables, int n_tables, const
   block_scan_kernel<<<1, kScanBlock, 0, st>>>(block_cnt, nb, n_valid_dev);
   keys_block_kernel<true><<<nb, kKT, 0, st>>>(P, block_cnt, keys, srcs);
   return check_launch("build_keys");
-}
-
-extern "C" size_t tgr_sort_workspace_bytes(int64_t n) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)(n > 0 ? n : 1), 0, 32, (cudaStream_t)0);
-  return align_up(bytes);
-}
-
-extern "C" int tgr_sort_pairs(const uint32_t* keys_in, const uint32_t* srcs_in, uint32_t* keys_out, uint32_t* srcs_out,
-                              int64_t n, int key_bits, void* workspace, size_t workspace_bytes, void* stream) {
-  tgr::TimedScope tgr_timed_("sort_pairs", stream);
-  TGR_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
-  TGR_REQUIRE(key_bits > 0 && key_bits <= 32, "key_bits=%d out of range", key_bits);
-  if (n == 0) return 0;
-  TGR_REQUIRE(keys_in && srcs_in && keys_out && srcs_out && workspace, "null argument");
-  size_t bytes = workspace_bytes;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(workspace, bytes, keys_in, keys_out, srcs_in, srcs_out, (int)n, 0,
-                                                  key_bits, (cudaStream_t)stream);
-  if (e != cudaSuccess) {
-    set_error("sort_pairs: %s", cudaGetErrorString(e));
-    return -2;
-  }
-  return check_launch("sort_pairs");
 }
 
 extern "C" size_t tgr_dedup_workspace_bytes(int64_t n) {

@@ -433,3 +433,26 @@ def test_route_bucket_bit_exact(W):
     inv = np.empty(n, np.int64)
     inv[order] = np.arange(n)
     assert np.array_equal(perm[:n].cpu().numpy(), inv)
+
+
+@pytest.mark.parametrize("n,key_bits", [(1, 1), (31, 5), (257, 9), (5000, 12), (70001, 13), (300000, 18), (1 << 20, 24),
+                                        (123457, 24), (99999, 27), (4096, 32)])
+def test_sort_pairs_stable_vs_torch(n, key_bits):
+    """The hand-written 12-bit-digit LSD radix sort (tgr_sort.cu): keys AND payload order bit-exact with a stable
+    sort, for 1 / 2 / 3 pass key widths, Zipf-like duplicate-heavy keys and sizes around the tile boundaries."""
+    from tencent_recommendation_2025_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(n + key_bits)
+    hi = (1 << key_bits) - 1
+    keys = (torch.rand(n, device="cuda", generator=g, dtype=torch.float64) ** 6 * hi).to(torch.int64)   # heavy duplicates
+    keys[::7] = torch.randint(0, hi + 1, (len(keys[::7]),), device="cuda", generator=g)
+    vals = torch.arange(n, device="cuda", dtype=torch.int64)
+    k32, v32 = keys.to(torch.int32), vals.to(torch.int32)          # uint32 payloads in int32 storage
+    ko, vo = torch.empty_like(k32), torch.empty_like(v32)
+    ws = torch.empty(lib.tgr_sort_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.tgr_sort_pairs(k32.data_ptr(), v32.data_ptr(), ko.data_ptr(), vo.data_ptr(), n, key_bits, ws.data_ptr(),
+                                  ws.numel(), torch.cuda.current_stream().cuda_stream), "tgr_sort_pairs")
+    ref_k, order = torch.sort(keys, stable=True)
+    got_k = ko.to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(got_k, ref_k)
+    assert torch.equal(vo.to(torch.int64), vals[order])
