@@ -132,46 +132,6 @@ struct KeyParams {
   int32_t n_seg;
 };
 
-struct KeyFunctor {
-  KeyParams kp;  // ~3 KB, lives in the kernel parameter (constant) bank
-  uint32_t* keys;
-  uint32_t* srcs;
-
-  __device__ __forceinline__ bool decode(int64_t e, uint32_t& key, uint32_t& src) const {
-    const KeyParams* p = &kp;
-    int s = 0;
-    const int ns = p->n_seg;
-    while (s + 1 < ns && e >= p->seg[s + 1].start) ++s;
-    const KeySeg& g = p->seg[s];
-    const uint32_t i = (uint32_t)(e - g.start);   // a segment holds < 2^31 entries: 32-bit index math
-    if (g.n_cols > 0) {
-      const int id = __ldg(g.vals + i);
-      const uint32_t t = i / (uint32_t)g.n_cols;
-      const int c = (int)(i - t * (uint32_t)g.n_cols);
-      if (id <= 0 || id >= p->col_rows[g.call][c]) return false;
-      key = p->col_key_base[g.call][c] + (uint32_t)id;
-      src = ((uint32_t)g.call << TGR_SRC_CALL_SHIFT) | ((uint32_t)p->col_slot[g.call][c] << TGR_SRC_SLOT_SHIFT) | (uint32_t)t;
-    } else {
-      const int id = __ldg(g.vals + i);
-      if (id <= 0 || id >= g.rows) return false;
-      key = g.key_base + (uint32_t)id;
-      src = ((uint32_t)g.call << TGR_SRC_CALL_SHIFT) | ((uint32_t)g.slot << TGR_SRC_SLOT_SHIFT) | (uint32_t)__ldg(g.toks + i);
-    }
-    return true;
-  }
-  __device__ __forceinline__ bool valid(int64_t e) const {
-    uint32_t k, s;
-    return decode(e, k, s);
-  }
-  __device__ __forceinline__ void emit(int64_t e, int64_t pos) const {
-    uint32_t k, s;
-    decode(e, k, s);
-    keys[pos] = k;
-    srcs[pos] = s;
-  }
-  __device__ __forceinline__ void every(int64_t, int64_t) const {}
-};
-
 // ---- block-wise key builder: 2048 consecutive entries of ONE segment per CTA, 8 per thread ------------------------
 // (the first version decoded one entry per thread through the generic compaction functor: 126 us per step, bound by
 //  per-entry divisions and divergent constant-bank lookups; here the per-column tables sit in shared memory, the

@@ -728,8 +728,9 @@ def run_distributed(gen: Generator, group=None):
                 out = None
             elif req[0] == "allgather":
                 t = req[1].contiguous()
-                out = torch.empty((pg.size(),) + tuple(t.shape), dtype=t.dtype, device=t.device)
-                pg._allgather_base(out, t).wait()
+                flat = torch.empty(pg.size() * t.numel(), dtype=t.dtype, device=t.device)
+                pg._allgather_base(flat, t.reshape(-1)).wait()
+                out = flat.view((pg.size(),) + tuple(t.shape))
             elif req[0] == "a2a_equal":
                 out = torch.empty_like(req[1])
                 pg.alltoall_base(out, req[1].contiguous(), [], []).wait()

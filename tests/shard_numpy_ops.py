@@ -138,3 +138,54 @@ class NumpyShardOps:
 
     def apply_cached(self, owner_state, recv_grads, R, hyper):
         self.apply(owner_state, recv_grads, R, hyper)
+
+
+class NumpyPeerShardOps(NumpyShardOps):
+    """The peer-memory flavour of the protocol (sharded.FactShardOps) with numpy arrays standing in for NVLink peer
+    memory: ranks emulated in ONE process see each other's shard / gradient window objects directly. Rows are read in
+    place from their owners (no row all-to-all), the owner pulls gradient rows out of every source's window."""
+
+    def __init__(self, layout, local_table, mm_params, W, window_rows):
+        super().__init__(layout, local_table, mm_params, W)
+        self.peers = None
+        self.grad_peers = None
+        self.grad_win = torch.zeros((window_rows, layout.H))
+        self._bar = torch.zeros(1)
+        self.pulled = 0          # steps whose gradients were pulled through the window
+
+    def link(self, all_ops):
+        self.peers = list(all_ops)
+        self.grad_peers = list(all_ops)
+
+    def fetch_rows_async(self, pf):
+        n = int(pf["n_unique"][0])
+        u = pf["uniq"].numpy()[:n].view(np.uint32).astype(np.int64)
+        rows = np.zeros((n + 1, self.layout.H), np.float32)          # row 0 = the zero row the concat builder expects
+        for i, k in enumerate(u):
+            rows[1 + i] = self.peers[int(k % self.W)].local.numpy()[int(k // self.W)]
+        pf["rows_sorted"] = torch.from_numpy(rows)
+
+    def forward_prefetched(self, pb, st, out_dtype=None):
+        pf = st["pf"]
+        ident = torch.arange(pf["cap"], dtype=torch.int32)
+        return self.forward_from_rows(pb, pf["uniq"], pf["n_unique"], ident, pf["rows_sorted"], out_dtype)
+
+    def prepare_owner(self, recv_rows, R, counts_dev=None):
+        if counts_dev is None:
+            return super().prepare_owner(recv_rows, R)
+        cnt = counts_dev.numpy().astype(np.int64)
+        src = np.repeat(np.arange(self.W), cnt)
+        idx = np.arange(R) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        return recv_rows.clone(), src, idx
+
+    def permute_to_window(self, grads, perm, n_unique, cap):
+        n = int(n_unique[0])
+        self.grad_win[perm[:n].long()] = grads[:n]
+
+    def apply_from_peers(self, owner_state, starts, R, hyper):
+        rows, src, idx = owner_state
+        g = np.zeros((max(R, 1), self.layout.H), np.float32)
+        for j in range(R):
+            g[j] = self.grad_peers[int(src[j])].grad_win.numpy()[starts[int(src[j])] + int(idx[j])]
+        self.pulled += 1
+        self.apply(rows, torch.from_numpy(g), R, hyper)

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from shard_numpy_ops import NumpyShardOps
+from shard_numpy_ops import NumpyPeerShardOps, NumpyShardOps
 from tencent_recommendation_2025_b200.packed import to_device
 from tencent_recommendation_2025_b200.sharded import (ShardedRank, run_distributed, run_emulated, shard_of_tables,
                                                       tables_from_shards)
@@ -81,6 +81,14 @@ def _worker(rank, W, port, tmp, prefetch=False):
     torch.set_num_threads(1)
     cfg, world, lay, tables, mm = make_world()
     outs, local, facts = rank_job(rank, W, lay, world, tables, mm, lambda g: run_distributed(g), prefetch)
+
+    def extra():   # the request kinds only the peer-memory protocol issues, through the real process group
+        m = yield ("allgather", torch.tensor([rank, 10 + rank], dtype=torch.int32))
+        yield ("barrier", torch.ones(1))
+        return m
+
+    m = run_distributed(extra())
+    assert m.tolist() == [[r, 10 + r] for r in range(W)]
     torch.save({"outs": outs, "local": local, "facts": facts}, os.path.join(tmp, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -156,6 +164,42 @@ def test_emulated_w4_equals_w1_numpy():
     m1 = tables_from_shards(lay, [torch.from_numpy(rk1.ops.m)])
     for x, y in zip(m4, m1):
         assert torch.allclose(x, y, rtol=0, atol=1e-6 * max(float(y.abs().max()), 1e-30))
+
+
+@pytest.mark.parametrize("window_rows", [4096, 1])
+def test_emulated_peer_memory_protocol_equals_exchange_protocol(window_rows):
+    """The peer-memory protocol (rows read in place from the owners, gradient rows pulled from the sources' windows,
+    W x W count matrix by all-gather) gives bit-identical forward rows and updated tables to the all-to-all protocol;
+    a window that is too small falls back to the gradient all-to-all on every rank alike."""
+    cfg, world, lay, tables, mm = make_world()
+    W = 4
+    steps = [world.make_step(r) for r in range(W)]
+    results = []
+    for peer in (False, True):
+        if peer:
+            ops = [NumpyPeerShardOps(lay, shard_of_tables(tables, r, W), mm, W, window_rows) for r in range(W)]
+            for o in ops:
+                o.link(ops)
+        else:
+            ops = [NumpyShardOps(lay, shard_of_tables(tables, r, W), mm, W) for r in range(W)]
+        ranks = [ShardedRank(lay, ops[r], r, W) for r in range(W)]
+        pbs = [[to_device(lay, pc, "cpu", pin=False) for pc in st.calls] for st in steps]
+        run_emulated([ranks[r].prepare_gen(pbs[r]) for r in range(W)])
+        run_emulated([ranks[r].finish_prepare_gen() for r in range(W)])
+        run_emulated([ranks[r].prefetch_gen(pbs[r]) for r in range(W)])
+        outs = [run_emulated([ranks[r].forward_gen(pbs[r][c]) for r in range(W)]) for c in range(3)]
+        for r in range(W):
+            for pb, (di, du) in zip(pbs[r], dcats(lay, steps[r], 50 + r)):
+                ranks[r].queue(pb, di, du)
+        run_emulated([rk.step_gen(dict(HYPER)) for rk in ranks])
+        results.append((outs, tables_from_shards(lay, [o.local for o in ops])))
+        if peer:
+            assert all(o.pulled == (1 if window_rows > 1 else 0) for o in ops)
+    for c in range(3):
+        for r in range(W):
+            assert torch.equal(results[0][0][c][r][0], results[1][0][c][r][0])
+    for a, b in zip(results[0][1], results[1][1]):
+        assert torch.equal(a, b)
 
 
 def test_shard_layout_round_trip():
