@@ -215,10 +215,12 @@ class HostPrefetcher:
         self.taken = []
 
     @staticmethod
-    def _fit(lst, i, n, dtype, device):
+    def _fit(lst, i, n, dtype, device, reader=None):
         while len(lst) <= i:
             lst.append(None)
         if lst[i] is None or lst[i].numel() < n or lst[i].dtype != dtype:
+            if lst[i] is not None and reader is not None:
+                lst[i].record_stream(reader)    # a step enqueued on the compute stream may still read the old buffer
             lst[i] = torch.empty(int(n * 1.1) + 64, dtype=dtype, device=device)
         return lst[i]
 
@@ -230,16 +232,17 @@ class HostPrefetcher:
         if slot["done"] is not None:
             slot["done"].synchronize()          # the step that read this slot finished slots - 1 steps ago
         pbs = []
+        reader = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.stream):
             j = 0
             for i, hp in enumerate(host_calls):
                 n = hp.ints.numel()
-                dev = self._fit(slot["ints"], i, n, torch.int32, self.device)[:n]
+                dev = self._fit(slot["ints"], i, n, torch.int32, self.device, reader)[:n]
                 dev.copy_(hp.ints, non_blocking=True)
                 o, s, T = hp.offs, hp.sizes, hp.T
                 mm = []
                 for x in hp.mm_x:
-                    d = self._fit(slot["mm"], j, x.numel(), x.dtype, self.device)[:x.numel()].view(x.shape)
+                    d = self._fit(slot["mm"], j, x.numel(), x.dtype, self.device, reader)[:x.numel()].view(x.shape)
                     d.copy_(x, non_blocking=True)
                     mm.append(d)
                     j += 1
