@@ -320,6 +320,14 @@ def run_gpu(args):
             e.update({"alg_MB_per_step": round(kbytes[name] / args.steps / 1e6, 1), "GBs": round(gbs, 1),
                       "frac": round(gbs / hbm_peak, 4)})
         table[name] = e
+    # the two row kernels are fp32 FFMA GEMMs over the unique rows (2*U*H*H and 4*U*H*H flop): their own ceiling is the
+    # CUDA-core rate (148 SMs x 128 FMA/clk x 2 at the max SM clock), stated next to the HBM figure
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    u_total = sum(stats[k][1] for k in used)
+    for name, mult in (("fact_project_rows", 2), ("fact_unique_backward", 4)):
+        if name in table and table[name]["ms_per_step"] > 0:
+            tf = mult * u_total * lay.H * lay.H / (kern_ms[name][0] * 1e-3) / 1e12
+            table[name].update({"fp32_TFLOPs": round(tf, 2), "frac_of_fp32_ffma_peak": round(tf / fp32_peak, 3)})
     cand = [n_ for n_ in table if "GBs" in table[n_]]
     dom = max(cand, key=lambda n_: table[n_]["ms_per_step"]) if cand else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": table[dom]["GBs"] if dom else 0.0, "peak": hbm_peak,
