@@ -106,6 +106,26 @@ class _FeatEmbMixin:
     def fused_step(self, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
         return self._tgr_engine.fused_step(lr, betas, eps, weight_decay, grad_scale)
 
+    def save_item_emb(self, item_ids, retrieval_ids, feat_dict, save_path, batch_size=1024):
+        """Candidate-embedding sweep with the reference's signature and outputs (model/BaseLine/model.py:402-433):
+        ``feat2emb`` over ``[1, n]`` id blocks with ``[np.array(dicts)]`` features, then ``embedding.fbin`` (float32
+        [N, H]) and ``id.u64bin`` (uint64 [N, 1]) in ``save_path``."""
+        import os
+
+        from .binfmt import save_emb
+        all_embs = []
+        with torch.no_grad():
+            for start in range(0, len(item_ids), batch_size):
+                end = min(start + batch_size, len(item_ids))
+                item_seq = torch.tensor(item_ids[start:end], device=self.dev).unsqueeze(0)
+                batch_feat = np.array([feat_dict[i] for i in range(start, end)], dtype=object)
+                emb = self.feat2emb(item_seq, [batch_feat], include_user=False).squeeze(0)
+                all_embs.append(emb.detach().float().cpu().numpy().astype(np.float32))
+        final_ids = np.array(retrieval_ids, dtype=np.uint64).reshape(-1, 1)
+        final_embs = np.concatenate(all_embs, axis=0) if all_embs else np.zeros((0, self._tgr_layout.H), np.float32)
+        save_emb(final_embs, os.path.join(save_path, "embedding.fbin"))
+        save_emb(final_ids, os.path.join(save_path, "id.u64bin"))
+
     def check_padding_rows(self):
         """Row 0 of every table must be all-zero (the reference keeps it so: main.py:106-111, padding_idx
         gradient masking, AdamW fixed point). Array pooling drops padding ids on that basis."""

@@ -235,3 +235,25 @@ def test_incomplete_prefetched_group_raises():
     loss = sum(o.sum() for o in outs)
     with pytest.raises(RuntimeError):
         loss.backward()
+
+
+@pytest.mark.parametrize("path", ["concat", "factored"])
+def test_save_item_emb_writes_reference_format(path, tmp_path):
+    """save_item_emb(item_ids, retrieval_ids, feat_dict, save_path, batch_size) (model.py:402-433): embedding.fbin holds
+    the [1, n] sweep outputs of the reference fixture, id.u64bin the retrieval ids, in the reference's wire format."""
+    from tencent_recommendation_2025_b200 import binfmt
+    from tencent_recommendation_2025_b200.module import BaselineEmbedding
+    g = Golden("item_sweep")
+    args = types.SimpleNamespace(device="cuda", hidden_units=g.H)
+    m = BaselineEmbedding(g.user_num, g.item_num, g.feat_statistics, g.feat_types, args, "parity", path=path).to("cuda")
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in g.params0().items()})
+    dicts = packed_to_dicts(g.layout, g.sweep_call())[0]
+    item_ids = [int(x) for x in g.z["seq"].reshape(-1)]
+    n = len(item_ids)
+    retrieval = list(range(1000, 1000 + n))
+    m.save_item_emb(item_ids, retrieval, {i: dicts[i] for i in range(n)}, str(tmp_path), batch_size=max(1, n // 3 + 1))
+    emb = binfmt.load_emb(tmp_path / "embedding.fbin", np.float32)
+    ids = binfmt.load_emb(tmp_path / "id.u64bin", np.uint64)
+    assert emb.shape == (n, g.H) and ids.shape == (n, 1)
+    assert ids.reshape(-1).tolist() == retrieval
+    _close(emb, g.z["out"][0], what=f"save_item_emb [{path}]")

@@ -184,3 +184,22 @@ def test_route_w1_identity_and_partition():
         assert counts.sum() == keys.size
         assert np.array_equal(owner.astype(np.int64) + local * W, keys.astype(np.int64))
         assert np.all(np.diff(owner[order]) >= 0)
+
+
+def test_fbin_writer_matches_reference_bytes(tmp_path):
+    """binfmt.save_emb == the reference's save_emb byte for byte (fixtures written by the unmodified reference,
+    tests/golden/make_golden_fbin.py), and the reader round-trips both files."""
+    import os
+    from golden_util import GOLDEN_DIR
+    from tencent_recommendation_2025_b200 import binfmt
+    z = np.load(os.path.join(GOLDEN_DIR, "fbin_inputs.npz"))
+    for arr, name, dt in ((z["emb"], "fbin_embedding.bin", np.float32), (z["ids"], "fbin_ids.bin", np.uint64)):
+        out = tmp_path / name
+        binfmt.save_emb(arr, out)
+        ref = open(os.path.join(GOLDEN_DIR, name), "rb").read()
+        assert out.read_bytes() == ref
+        back = binfmt.load_emb(out, dt)
+        assert back.dtype == dt and np.array_equal(back, arr)
+    binfmt.save_emb(torch.from_numpy(z["emb"]), tmp_path / "t.fbin")
+    assert (tmp_path / "t.fbin").read_bytes() == open(os.path.join(GOLDEN_DIR, "fbin_embedding.bin"), "rb").read()
+    assert np.array_equal(binfmt.read_result_ids(os.path.join(GOLDEN_DIR, "fbin_ids.bin")), z["ids"])
