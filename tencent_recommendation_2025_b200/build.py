@@ -16,6 +16,9 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(PKG, "libtgr_embed.so")
+PACK_LIB = os.path.join(PKG, "libtgr_pack.so")     # host-side dict tensorizer (plain C on the CPython API)
+PACK_SRC = os.path.join(CSRC, "tgr_pack.c")
+CC = os.environ.get("CC", "gcc")
 SOURCES = ["tgr_util.cu", "tgr_fwd.cu", "tgr_mm.cu", "tgr_bwd.cu", "tgr_sort.cu", "tgr_reduce.cu", "tgr_route.cu", "tgr_factored.cu", "tgr_fact_step.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
@@ -65,7 +68,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    build_pack(force)
     return LIB
+
+
+def build_pack(force: bool = False) -> str:
+    """gcc -shared tgr_pack.c -> libtgr_pack.so (symbols of libpython resolve against the running interpreter)."""
+    import sysconfig
+    if force or _stale(PACK_LIB, [PACK_SRC, os.path.abspath(__file__)]):
+        inc = sysconfig.get_paths()["include"]
+        r = subprocess.run([CC, "-O2", "-Wall", "-shared", "-fPIC", "-I", inc, PACK_SRC, "-o", PACK_LIB],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("gcc failed on tgr_pack.c")
+    return PACK_LIB
 
 
 if __name__ == "__main__":

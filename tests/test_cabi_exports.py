@@ -144,3 +144,70 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libtgr_embed.so")
     with pytest.raises(_lib.TgrError):
         _lib.load()
+
+
+def _same_packed(a, b):
+    assert np.array_equal(a.ids, b.ids) and a.ids.dtype == b.ids.dtype
+    assert np.array_equal(a.arr_off, b.arr_off) and np.array_equal(a.arr_val, b.arr_val)
+    assert len(a.mm_x) == len(b.mm_x)
+    for x, y in zip(a.mm_x, b.mm_x):
+        assert x.dtype == y.dtype and np.array_equal(x, y)
+    assert np.array_equal(a.seq, b.seq)
+    assert (a.mask is None) == (b.mask is None) and (a.mask is None or np.array_equal(a.mask, b.mask))
+
+
+@pytest.mark.parametrize("name", ["baseline_h32", "o1_h64_mm2", "baseline_l102_nomm"])
+def test_native_tensorizer_equals_python_restatement(name):
+    """csrc/tgr_pack.c (one dict walk in C) == packed.pack_from_dicts_py on every fixture call, and on the input
+    variants the reference's pipeline produces: object-array rows (np.array(dicts)), numpy integer ids, tuple / ndarray
+    id lists, list-typed mm vectors, mapping (non-dict) tokens."""
+    import collections
+    from tencent_recommendation_2025_b200.packed import pack_from_dicts_py
+    g = Golden(name)
+    lay = g.layout
+    for pc in g.calls(0):
+        d = packed_to_dicts(lay, pc)
+        seq = torch.from_numpy(pc.seq)
+        mask = None if pc.mask is None else torch.from_numpy(pc.mask)
+        ref = pack_from_dicts_py(lay, seq, d, mask, pc.include_user)
+        _same_packed(pack_from_dicts(lay, seq, d, mask, pc.include_user), ref)
+        # variants
+        v = []
+        for row in d:
+            new = []
+            for t, tok in enumerate(row):
+                tok2 = {}
+                for k, val in tok.items():
+                    if isinstance(val, (int, np.integer)):
+                        tok2[k] = np.int64(val) if t % 2 else int(val)
+                    elif isinstance(val, np.ndarray) and val.dtype == np.float32:
+                        tok2[k] = val.tolist() if t % 3 == 0 else val
+                    elif isinstance(val, (list, tuple, np.ndarray)):
+                        tok2[k] = tuple(val) if t % 2 else np.asarray(val, np.int64)
+                    else:
+                        tok2[k] = val
+                new.append(collections.ChainMap(tok2) if t % 5 == 4 else tok2)
+            v.append(np.array(new, dtype=object))
+        _same_packed(pack_from_dicts(lay, seq, v, mask, pc.include_user), ref)
+
+
+def test_native_tensorizer_errors():
+    g = Golden("baseline_h32")
+    lay = g.layout
+    pc = g.calls(0)[0]
+    d = packed_to_dicts(lay, pc)
+    seq, mask = torch.from_numpy(pc.seq), torch.from_numpy(pc.mask)
+    bad = [list(r) for r in d]
+    bad[0][1] = {k: v for k, v in bad[0][1].items() if k != "100"}
+    with pytest.raises(KeyError):
+        pack_from_dicts(lay, seq, bad, mask, True)                     # a dict lacking a sparse key (model.py:222)
+    bad = [list(r) for r in d]
+    bad[0][1] = dict(bad[0][1], **{"81": np.zeros(7, np.float32)})
+    with pytest.raises(ValueError):
+        pack_from_dicts(lay, seq, bad, mask, True)                     # mm vector of the wrong width
+    bad = [list(r) for r in d]
+    bad[0][1] = dict(bad[0][1], **{"100": 1 << 40})
+    with pytest.raises(OverflowError):
+        pack_from_dicts(lay, seq, bad, mask, True)
+    with pytest.raises(ValueError):
+        pack_from_dicts(lay, seq, d, None, True)                       # include_user without the mask
