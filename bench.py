@@ -412,8 +412,41 @@ def run_gpu(args):
                        "rows_per_step": rows // args.steps, "tokens_per_step": 3 * cfg.B * cfg.L,
                        "l2": "tables + AdamW state 6 GB >> 126 MB L2; "
                              f"{n_batches} distinct batches cycled (each step touches different rows)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "dict_tensorizer": None if args.no_cpu_baseline else tensorizer_timing(cfg)}
     print(json.dumps(line))
+
+
+def tensorizer_timing(cfg: synth.SynthConfig, sequences: int = 64):
+    """Host cost of the reference-signature entry (list-of-dict features -> packed calls), on a bounded sample of the
+    workload: the C tensorizer (libtgr_pack.so) next to the numpy restatement. Reported apart from the metric
+    (SURVEY.md §8(d)): a data pipeline packs in its DataLoader workers, the benchmark steps start from packed calls."""
+    import dataclasses
+    from tencent_recommendation_2025_b200.packed import pack_from_dicts, pack_from_dicts_py
+    try:
+        scfg = dataclasses.replace(cfg, B=min(sequences, cfg.B))
+        world = synth.SynthWorld(scfg, 0)
+        lay = world.layout
+        st = world.make_step(0)
+        out = {"sample": f"{scfg.B} sequences x 3 calls", "tokens": 0}
+        t_c = t_py = 0.0
+        for pc in st.calls:
+            d = synth.packed_to_dicts(lay, pc)
+            seq = torch.from_numpy(pc.seq)
+            mask = torch.from_numpy(pc.mask) if pc.include_user else None
+            t0 = time.perf_counter()
+            pack_from_dicts(lay, seq, d, mask, pc.include_user)
+            t1 = time.perf_counter()
+            pack_from_dicts_py(lay, seq, d, mask, pc.include_user)
+            t2 = time.perf_counter()
+            t_c += t1 - t0
+            t_py += t2 - t1
+            out["tokens"] += pc.T
+        out["c_us_per_token"] = round(1e6 * t_c / out["tokens"], 3)
+        out["numpy_us_per_token"] = round(1e6 * t_py / out["tokens"], 3)
+        return out
+    except Exception as e:   # never let a host-side side measurement take the benchmark line down
+        return {"error": repr(e)}
 
 
 def load_traffic(kernel, launches_per_step=1):
