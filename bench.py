@@ -421,9 +421,9 @@ def tensorizer_timing(cfg: synth.SynthConfig, sequences: int = 64):
     """Host cost of the reference-signature entry (list-of-dict features -> packed calls), on a bounded sample of the
     workload: the C tensorizer (libtgr_pack.so) next to the numpy restatement. Reported apart from the metric
     (SURVEY.md §8(d)): a data pipeline packs in its DataLoader workers, the benchmark steps start from packed calls."""
-    import dataclasses
-    from tencent_recommendation_2025_b200.packed import pack_from_dicts, pack_from_dicts_py
     try:
+        import dataclasses
+        from tencent_recommendation_2025_b200.packed import pack_from_dicts, pack_from_dicts_py
         scfg = dataclasses.replace(cfg, B=min(sequences, cfg.B))
         world = synth.SynthWorld(scfg, 0)
         lay = world.layout
