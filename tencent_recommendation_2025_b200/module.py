@@ -27,7 +27,8 @@ import torch
 from .engine import EmbeddingEngine, GatherConcatFn
 from .factored import FactoredEngine, FactoredFn
 from .layout import FeatureLayout
-from .packed import PackedBatch, pack_from_dicts, to_device
+from .packed import HostPacked, PackedBatch, pack_from_dicts, to_device
+from .synth import PackedCall
 
 
 def _concat_dtype() -> torch.dtype:
@@ -71,8 +72,32 @@ class _FeatEmbMixin:
 
     @torch.compiler.disable
     def feat2emb(self, seq, feature_array, mask=None, include_user=False):
-        """Same signature and result as model/BaseLine/model.py:226-310."""
+        """Same signature and result as model/BaseLine/model.py:226-310. ``feature_array`` may also be an already packed
+        call (``PackedBatch`` / ``HostPacked`` from ``packed.PackingCollate`` / ``PackedCall``): the dict walk is then
+        skipped, ``seq`` / ``mask`` only have to agree in shape (their values are inside the packed ids)."""
+        if isinstance(feature_array, (PackedBatch, HostPacked, PackedCall)):
+            return self.feat2emb_packed(self._resolve_packed(seq, feature_array, include_user))
         return self.feat2emb_packed(self.pack(seq, feature_array, mask, include_user))
+
+    def _resolve_packed(self, seq, packed, include_user) -> PackedBatch:
+        if bool(packed.include_user) != bool(include_user):
+            raise ValueError(f"packed call was built with include_user={packed.include_user}, feat2emb got {include_user}")
+        if seq is not None and tuple(seq.shape) != (packed.B, packed.L):
+            raise ValueError(f"seq is {tuple(seq.shape)}, the packed call holds [{packed.B}, {packed.L}]")
+        if isinstance(packed, PackedBatch):
+            return packed
+        eng = self._tgr_engine
+        dev = eng._device()
+        if isinstance(packed, PackedCall):
+            return to_device(self._tgr_layout, packed, dev)
+        group = packed.group
+        if group is None:
+            return packed.upload(dev)
+        first = group.device is None
+        pb = group.batch_of(packed, dev)
+        if first and torch.is_grad_enabled():
+            self.prefetch(group.device)      # factored path: the step's calls become one group; no-op on the concat path
+        return pb
 
     @torch.compiler.disable
     def feat2emb_packed(self, pb: PackedBatch):

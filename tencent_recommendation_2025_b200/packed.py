@@ -240,6 +240,7 @@ class HostPacked:
     arr_nnz: List[int]
     mm_x: List[torch.Tensor]          # pinned [T, mm_dim]
     n_valid: int
+    group: Optional["StepGroup"] = None   # the step's other calls (PackingCollate)
 
     @property
     def T(self) -> int:
@@ -283,6 +284,54 @@ def stage_pinned(layout: FeatureLayout, pc: PackedCall, mm_dtype: torch.dtype = 
     begins = [int(pc.arr_off[j, 0]) for j in range(n_arr)]
     nnz = [int(pc.arr_off[j, -1] - pc.arr_off[j, 0]) for j in range(n_arr)]
     return HostPacked(pc.B, pc.L, pc.include_user, ints, offs, sizes, pc.ids.shape[1], n_arr, begins, nnz, mm, pc.n_valid)
+
+
+class PackingCollate:
+    """``collate_fn`` wrapper for the reference's DataLoader (model/BaseLine/dataset.py:268-293): runs
+    the dataset's own collate, then tensorizes the three feature lists of the step IN THE WORKER (one C walk each) and
+    hands them over as ``HostPacked`` calls (pinned when CUDA is available) in place of ``seq_feat / pos_feat /
+    neg_feat``. The model code stays as it is — ``feat2emb(seq, seq_feature, mask, include_user)`` recognises a packed
+    call in the ``feature_array`` position — and the three calls of a step carry a reference to each other, so the
+    factored engine prepares them as ONE group on the first ``feat2emb`` of the step.
+
+        loader = DataLoader(dataset, batch_size=B, collate_fn=PackingCollate(model.layout, dataset.collate_fn))
+    """
+
+    def __init__(self, layout: FeatureLayout, base_collate, mm_dtype: torch.dtype = torch.float32):
+        self.layout, self.base, self.mm_dtype = layout, base_collate, mm_dtype
+
+    def __call__(self, batch):
+        out = list(self.base(batch))
+        seq, pos, neg, token_type = out[0], out[1], out[2], out[3]
+        calls = [pack_from_dicts(self.layout, seq, out[6], token_type, True),
+                 pack_from_dicts(self.layout, pos, out[7], None, False),
+                 pack_from_dicts(self.layout, neg, out[8], None, False)]
+        hps = [stage_pinned(self.layout, pc, self.mm_dtype) for pc in calls]
+        group = StepGroup(hps)
+        for hp in hps:
+            hp.group = group
+        out[6], out[7], out[8] = hps
+        return tuple(out)
+
+
+class StepGroup:
+    """The packed calls of one training step (seq / pos / neg), uploaded together on first use."""
+
+    def __init__(self, host_calls):
+        self.host = list(host_calls)
+        self.device: Optional[List[PackedBatch]] = None
+
+    def upload(self, device) -> List[PackedBatch]:
+        if self.device is None:
+            self.device = [hp.upload(device) for hp in self.host]
+        return self.device
+
+    def batch_of(self, hp, device) -> PackedBatch:
+        pbs = self.upload(device)
+        for h, pb in zip(self.host, pbs):
+            if h is hp:
+                return pb
+        raise KeyError("packed call is not part of this step group")
 
 
 class HostPrefetcher:

@@ -3,6 +3,7 @@ argument validation, the default-layout facts the specialised kernels rely on. N
 import ctypes as C
 import types
 
+import numpy as np
 import pytest
 import torch
 
@@ -102,3 +103,54 @@ def test_sharded_module_rejects_unknown_path():
     ft = {k: list(v) for k, v in DEFAULT_FEAT_TYPES.items()}
     with pytest.raises(ValueError):
         ShardedBaselineEmbedding(9, 50, stats, ft, types.SimpleNamespace(device="cpu", hidden_units=32), 0, 1, path="nope")
+
+
+def _ref_style_batch(lay, st):
+    """What the reference's MyDataset.__getitem__ yields per sequence (dataset.py:96-168): id arrays + dict arrays."""
+    from tencent_recommendation_2025_b200.synth import packed_to_dicts
+    seq_c, pos_c, neg_c = st.calls
+    ds, dp, dn = (packed_to_dicts(lay, pc) for pc in st.calls)
+    batch = []
+    for b in range(seq_c.B):
+        tt = seq_c.mask[b]
+        batch.append((seq_c.seq[b], pos_c.seq[b], neg_c.seq[b], tt, tt, tt,
+                      np.array(ds[b], dtype=object), np.array(dp[b], dtype=object), np.array(dn[b], dtype=object)))
+    return batch
+
+
+def _ref_collate(batch):   # the reference's collate_fn, dataset.py:268-293
+    seq, pos, neg, token_type, next_token_type, next_action_type, seq_feat, pos_feat, neg_feat = zip(*batch)
+    t = lambda x: torch.from_numpy(np.array(x))
+    return t(seq), t(pos), t(neg), t(token_type), t(next_token_type), t(next_action_type), list(seq_feat), list(pos_feat), list(neg_feat)
+
+
+def test_packing_collate_and_packed_dispatch(lib):
+    """PackingCollate replaces the three feature lists by packed calls equal to pack_from_dicts'; feat2emb accepts
+    them in the feature_array position (here it must get as far as the engine, which refuses CPU tables)."""
+    from tencent_recommendation_2025_b200.module import BaselineEmbedding
+    from tencent_recommendation_2025_b200.packed import HostPacked, PackingCollate, pack_from_dicts, to_device
+    from tencent_recommendation_2025_b200.synth import SynthConfig, SynthWorld
+    stats = {k: 9 for k in default_feat_statistics()}
+    cfg = SynthConfig(B=3, L=6, H=32, item_num=50, user_num=9, mm_ids=("81",), min_len=2, feat_statistics=stats)
+    w = SynthWorld(cfg, 1)
+    st = w.make_step(0)
+    args = types.SimpleNamespace(device="cpu", hidden_units=32)
+    m = BaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), args, "fused", path="factored")
+    lay = m.layout
+    out = PackingCollate(lay, _ref_collate)(_ref_style_batch(lay, st))
+    assert len(out) == 9 and all(isinstance(out[i], HostPacked) for i in (6, 7, 8))
+    assert out[6].group is out[7].group is out[8].group
+    for hp, pc in zip(out[6:9], st.calls):
+        pb = hp.upload("cpu")
+        assert pb.include_user == pc.include_user and np.array_equal(pb.ids.numpy(), pc.ids)
+        assert np.array_equal(pb.arr_val.numpy(), pc.arr_val) and np.array_equal(pb.mm_x[0].numpy(), pc.mm_x[0])
+    seq, mask = out[0], out[3]
+    for feats, s_, inc in ((out[6], seq, True), (st.calls[1], out[1], False), (to_device(lay, st.calls[2], "cpu", pin=False), out[2], False)):
+        with pytest.raises(_lib.TgrError):        # packed input accepted, dict walk skipped, engine reached
+            m.feat2emb(s_, feats, mask=mask if inc else None, include_user=inc)
+    with pytest.raises(_lib.TgrError):            # the plain list-of-dict signature takes the same way in
+        m.feat2emb(seq, _ref_collate(_ref_style_batch(lay, st))[6], mask=mask, include_user=True)
+    with pytest.raises(ValueError):
+        m.feat2emb(seq, out[7], mask=mask, include_user=True)            # a pos call passed as the seq call
+    with pytest.raises(ValueError):
+        m.feat2emb(seq[:, :-1], out[6], mask=mask, include_user=True)    # shape disagreement
