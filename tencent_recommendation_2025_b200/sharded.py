@@ -729,7 +729,10 @@ def run_distributed(gen: Generator, group=None):
             elif req[0] == "allgather":
                 t = req[1].contiguous()
                 flat = torch.empty(pg.size() * t.numel(), dtype=t.dtype, device=t.device)
-                pg._allgather_base(flat, t.reshape(-1)).wait()
+                if hasattr(pg, "_allgather_base"):
+                    pg._allgather_base(flat, t.reshape(-1)).wait()
+                else:
+                    dist.all_gather_into_tensor(flat, t.reshape(-1), group=group)
                 out = flat.view((pg.size(),) + tuple(t.shape))
             elif req[0] == "a2a_equal":
                 out = torch.empty_like(req[1])
