@@ -116,6 +116,7 @@ const char* tgr_last_error(void);
  * after tgr_timing_enable(1) every kernel-launching entry brackets its launches with a CUDA-event pair on the
  * caller's stream; tgr_timing_collect synchronises those events and returns, per entry name ('\n'-joined in
  * `names`), the summed milliseconds and the number of calls. Returns the number of distinct names. */
+int64_t tgr_launch_count(void); /* kernels launched by this library in this process so far (a count, monotone) */
 int tgr_timing_enable(int on);
 int tgr_timing_collect(char* names, size_t names_bytes, float* ms, int32_t* counts, int max_entries);
 

@@ -108,6 +108,7 @@ def make_adam(lr: float, beta1: float, beta2: float, eps: float, weight_decay: f
 SIGNATURES = {
     "tgr_abi_version": (C.c_int, []),
     "tgr_last_error": (C.c_char_p, []),
+    "tgr_launch_count": (C.c_int64, []),
     "tgr_timing_enable": (C.c_int, [C.c_int]),
     "tgr_timing_collect": (C.c_int, [C.c_char_p, C.c_size_t, f32p, i32p, C.c_int]),
     "tgr_fwd_gather_pool_concat": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.POINTER(Call), C.c_void_p]),
@@ -199,6 +200,11 @@ def load():
             raise TgrError(f"ABI mismatch: library {lib.tgr_abi_version()} vs binding {TGR_ABI_VERSION}")
         _lib = lib
         return lib
+
+
+def launch_count() -> int:
+    """Kernels launched by libtgr_embed.so in this process so far (counted at every launch site)."""
+    return int(load().tgr_launch_count())
 
 
 def timing_enable(on: bool = True):

@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if verbose:
                     sys.stderr.write(r.stderr)
     if jobs or force or _stale(LIB, objs):
-        r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+        r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")

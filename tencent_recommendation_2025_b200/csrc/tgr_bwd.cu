@@ -374,9 +374,9 @@ extern "C" int tgr_bwd_build_keys(const tgr_table_t* tables, int n_tables, const
     nb += (int)((kp.seg[i].count + kKB - 1) / kKB);
   }
   P.seg_first_block[ns] = nb;
-  keys_block_kernel<false><<<nb, kKT, 0, st>>>(P, block_cnt, nullptr, nullptr);
-  block_scan_kernel<<<1, kScanBlock, 0, st>>>(block_cnt, nb, n_valid_dev);
-  keys_block_kernel<true><<<nb, kKT, 0, st>>>(P, block_cnt, keys, srcs);
+  TGR_K(keys_block_kernel<false>)<<<nb, kKT, 0, st>>>(P, block_cnt, nullptr, nullptr);
+  TGR_K(block_scan_kernel)<<<1, kScanBlock, 0, st>>>(block_cnt, nb, n_valid_dev);
+  TGR_K(keys_block_kernel<true>)<<<nb, kKT, 0, st>>>(P, block_cnt, keys, srcs);
   return check_launch("build_keys");
 }
 
@@ -400,10 +400,10 @@ extern "C" int tgr_dedup(const uint32_t* keys_sorted, int64_t n, uint32_t* uniq,
   int32_t* block_cnt = (int32_t*)workspace;
   const int nb = (int)((n + kScanBlock - 1) / kScanBlock);
   HeadFunctor f{keys_sorted, uniq, seg_off, seg_of_entry};
-  flag_count_kernel<<<nb, kScanBlock, 0, st>>>(f, n, block_cnt);
-  block_scan_kernel<<<1, kScanBlock, 0, st>>>(block_cnt, nb, n_unique_dev);
-  flag_emit_kernel<<<nb, kScanBlock, 0, st>>>(f, n, block_cnt);
-  dedup_finish_kernel<<<1, 1, 0, st>>>(seg_off, n_unique_dev, n);
+  TGR_K(flag_count_kernel)<<<nb, kScanBlock, 0, st>>>(f, n, block_cnt);
+  TGR_K(block_scan_kernel)<<<1, kScanBlock, 0, st>>>(block_cnt, nb, n_unique_dev);
+  TGR_K(flag_emit_kernel)<<<nb, kScanBlock, 0, st>>>(f, n, block_cnt);
+  TGR_K(dedup_finish_kernel)<<<1, 1, 0, st>>>(seg_off, n_unique_dev, n);
   return check_launch("dedup");
 }
 
@@ -418,7 +418,7 @@ extern "C" int tgr_adam_rows(const tgr_table_t* tables, int n_tables, int H, con
   if (max_unique <= 0) return 0;
   int64_t blocks = (max_unique * rp.H4 + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  rows_kernel<0><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rp, uniq, grads, n_unique_dev);
+  TGR_K(rows_kernel<0>)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rp, uniq, grads, n_unique_dev);
   return check_launch("adam_rows");
 }
 
@@ -431,7 +431,7 @@ extern "C" int tgr_scatter_rows(const tgr_table_t* tables, int n_tables, int H, 
   if (max_unique <= 0) return 0;
   int64_t blocks = (max_unique * rp.H4 + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  rows_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rp, uniq, grads, n_unique_dev);
+  TGR_K(rows_kernel<1>)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rp, uniq, grads, n_unique_dev);
   return check_launch("scatter_rows");
 }
 
@@ -443,6 +443,6 @@ extern "C" int tgr_gather_rows(const float* table, int H, const uint32_t* rows, 
   if (max_n <= 0) return 0;
   int64_t blocks = (max_n * (H / 4) + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, H / 4, rows, n_dev, out);
+  TGR_K(gather_rows_kernel)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, H / 4, rows, n_dev, out);
   return check_launch("gather_rows");
 }

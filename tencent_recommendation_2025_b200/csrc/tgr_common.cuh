@@ -33,6 +33,11 @@ class TimedScope {
   void* a_;
 };
 
+// Every kernel launch of the library goes through TGR_K(kernel)<<<...>>>(...): a comma expression bumps a process-wide
+// counter ahead of the launch, so tgr_launch_count() is a COUNT of launches, not an estimate (bench.py gpu_launches).
+void count_launch();
+#define TGR_K(...) ::tgr::count_launch(), __VA_ARGS__
+
 constexpr int kNumSMs = 148;  // B200
 
 // ---- cache-hinted 128-bit accesses --------------------------------------------------------

@@ -643,7 +643,7 @@ static int launch_rows(const FactParams& p, const uint32_t* uniq, const int32_t*
                        cudaStream_t st) {
   const size_t smem = fact_smem(H, MODE == 1);
   { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_rows_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
-  fact_rows_kernel<H, MODE><<<MODE ? kRowsGridBwd : kRowsGridFwd, RowsCfg<H>::NT, smem, st>>>(p, uniq, n_unique_dev, PG, dw_part);
+  TGR_K(fact_rows_kernel<H, MODE>)<<<MODE ? kRowsGridBwd : kRowsGridFwd, RowsCfg<H>::NT, smem, st>>>(p, uniq, n_unique_dev, PG, dw_part);
   return check_launch(MODE ? "fact_unique_backward" : "fact_project_rows");
 }
 
@@ -688,9 +688,9 @@ extern "C" int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables,
   if (rc) return rc;
   if (dW_item == nullptr && dW_user == nullptr) return 0;
   const dim3 grid(n_tables, H * H / 64);
-  if (H == 32) fact_dw_reduce_kernel<32><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
-  else if (H == 64) fact_dw_reduce_kernel<64><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
-  else fact_dw_reduce_kernel<128><<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
+  if (H == 32) TGR_K(fact_dw_reduce_kernel<32>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
+  else if (H == 64) TGR_K(fact_dw_reduce_kernel<64>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
+  else TGR_K(fact_dw_reduce_kernel<128>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
   return check_launch("fact_dw_reduce");
 }
 
@@ -743,9 +743,9 @@ extern "C" int tgr_fact_forward(const tgr_call_t* call, int H, const int32_t* id
   const int nsi = p.n_item_single, nsu = p.n_user_single;
 #define TGR_FWD(L)                                                                                         \
   do {                                                                                                     \
-    if (ident && nsi == 15 && nsu == 0) fact_forward_kernel<L, 15, 0><<<grid, kFT, smem, st>>>(p);        \
-    else if (ident && nsi == 15 && nsu == 5) fact_forward_kernel<L, 15, 5><<<grid, kFT, smem, st>>>(p);   \
-    else fact_forward_kernel<L, -1, 0><<<grid, kFT, smem, st>>>(p);                                       \
+    if (ident && nsi == 15 && nsu == 0) TGR_K(fact_forward_kernel<L, 15, 0>)<<<grid, kFT, smem, st>>>(p);        \
+    else if (ident && nsi == 15 && nsu == 5) TGR_K(fact_forward_kernel<L, 15, 5>)<<<grid, kFT, smem, st>>>(p);   \
+    else TGR_K(fact_forward_kernel<L, -1, 0>)<<<grid, kFT, smem, st>>>(p);                                       \
   } while (0)
   if (H == 32) TGR_FWD(8);
   else if (H == 64) TGR_FWD(16);
@@ -775,15 +775,15 @@ static int launch_dz(const float* d_out, const uint8_t* mask, int T, float* dz_i
                      int mm_x_dtype, float* part, int grid, int chunk, cudaStream_t st) {
   const size_t smem = (size_t)(kDzTok * (H + 4) + kDzTok * (kDzMM + 4)) * sizeof(float);
   if (mm_x == nullptr) {
-    fact_dz_kernel<H, false, false><<<grid, kFT, 0, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user,
+    TGR_K(fact_dz_kernel<H, false, false>)<<<grid, kFT, 0, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user,
                                                          nullptr, T, chunk, part);
   } else if (mm_x_dtype == TGR_DTYPE_BF16) {
     { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_dz_kernel<H, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
-    fact_dz_kernel<H, true, true><<<grid, kFT, smem, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user,
+    TGR_K(fact_dz_kernel<H, true, true>)<<<grid, kFT, smem, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user,
                                                           mm_x, T, chunk, part);
   } else {
     { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_dz_kernel<H, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
-    fact_dz_kernel<H, true, false><<<grid, kFT, smem, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user,
+    TGR_K(fact_dz_kernel<H, true, false>)<<<grid, kFT, smem, st>>>((const float4*)d_out, mask, (float4*)dz_item, (float4*)dz_user,
                                                            mm_x, T, chunk, part);
   }
   return check_launch("fact_dz");
@@ -810,7 +810,7 @@ extern "C" int tgr_fact_relu_mask(const float* d_out, const uint8_t* mask, int64
   if (rc) return rc;
   if (db_item == nullptr && db_user == nullptr && mm_x == nullptr) return 0;
   const int part_ld = 2 * H + (mm_x ? H * kDzMM : 0);
-  fact_dz_finish_kernel<<<(part_ld + 15) / 16, 256, 0, st>>>(part, grid, part_ld, H, db_item, dz_user ? db_user : nullptr,
+  TGR_K(fact_dz_finish_kernel)<<<(part_ld + 15) / 16, 256, 0, st>>>(part, grid, part_ld, H, db_item, dz_user ? db_user : nullptr,
                                                            mm_x ? mm_A : nullptr, mm_x ? mm_s : nullptr);
   return check_launch("fact_dz_finish");
 }
@@ -820,7 +820,7 @@ extern "C" int tgr_fact_mm_fold(const float* w_slot, int64_t ld, const float* w_
   tgr::TimedScope tgr_timed_("fact_mm_fold", stream);
   TGR_REQUIRE(w_slot && w_mm && M && c && H > 0 && mm_dim > 0, "bad argument");
   const int n = H * mm_dim + H;
-  fact_mm_fold_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_slot, ld, w_mm, b_mm, H, mm_dim, M, c);
+  TGR_K(fact_mm_fold_kernel)<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_slot, ld, w_mm, b_mm, H, mm_dim, M, c);
   return check_launch("fact_mm_fold");
 }
 
@@ -830,7 +830,7 @@ extern "C" int tgr_fact_mm_chain_bwd(const float* w_slot, int64_t ld, const floa
   tgr::TimedScope tgr_timed_("fact_mm_chain_bwd", stream);
   TGR_REQUIRE(w_slot && w_mm && A && s && dW_mm && dW_slot && H > 0 && mm_dim > 0, "bad argument");
   const int n = H * mm_dim + H + H * H;
-  fact_mm_chain_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_slot, ld, w_mm, b_mm, A, s, H, mm_dim, dW_mm,
+  TGR_K(fact_mm_chain_kernel)<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_slot, ld, w_mm, b_mm, A, s, H, mm_dim, dW_mm,
                                                                           db_mm, dW_slot, dld);
   return check_launch("fact_mm_chain_bwd");
 }

@@ -158,9 +158,9 @@ static int launch_fwd(const FwdParams& p, bool bf16, cudaStream_t st) {
   const int grid = (p.T + kTT - 1) / kTT;
   const size_t smem = (size_t)kTT * p.n_single * sizeof(int32_t);
   if (bf16)
-    fwd_gather_pool_concat_kernel<LANES, true><<<grid, kThreads, smem, st>>>(p);
+    TGR_K(fwd_gather_pool_concat_kernel<LANES, true>)<<<grid, kThreads, smem, st>>>(p);
   else
-    fwd_gather_pool_concat_kernel<LANES, false><<<grid, kThreads, smem, st>>>(p);
+    TGR_K(fwd_gather_pool_concat_kernel<LANES, false>)<<<grid, kThreads, smem, st>>>(p);
   return check_launch("fwd_gather_pool_concat");
 }
 

@@ -245,7 +245,7 @@ extern "C" int tgr_mm_proj_fwd(const void* x, int x_dtype, int64_t T, int mm_dim
   const int64_t ldb = out_ld * (out_dtype == TGR_DTYPE_BF16 ? 2 : 4);
   const bool xb = x_dtype == TGR_DTYPE_BF16, ob = out_dtype == TGR_DTYPE_BF16;
 #define TGR_LAUNCH_FWD(BM, BN, XB, OB)                                                                  \
-  mm_proj_fwd_kernel<BM, BN, XB, OB><<<dim3((unsigned)((T + BM - 1) / BM), (H + BN - 1) / BN), kMmThreads, 0, st>>>( \
+  TGR_K(mm_proj_fwd_kernel<BM, BN, XB, OB>)<<<dim3((unsigned)((T + BM - 1) / BM), (H + BN - 1) / BN), kMmThreads, 0, st>>>( \
       x, T, mm_dim, W, bias, H, (char*)out, ldb)
   if (H >= 64) {
     if (xb && ob) TGR_LAUNCH_FWD(128, 64, true, true);
@@ -284,13 +284,13 @@ extern "C" int tgr_mm_proj_bwd(const void* x, int x_dtype, int64_t T, int mm_dim
   const bool xb = x_dtype == TGR_DTYPE_BF16, dbf = dy_dtype == TGR_DTYPE_BF16;
   dim3 grid(n, (mm_dim + kBKb - 1) / kBKb);
   if (T > 0) {
-    if (xb && dbf) mm_proj_bwd_partial_kernel<true, true><<<grid, kMmThreads, 0, st>>>(x, T, mm_dim, (const char*)dy, ldb, H, n, ws_dw, ws_db);
-    else if (xb) mm_proj_bwd_partial_kernel<true, false><<<grid, kMmThreads, 0, st>>>(x, T, mm_dim, (const char*)dy, ldb, H, n, ws_dw, ws_db);
-    else if (dbf) mm_proj_bwd_partial_kernel<false, true><<<grid, kMmThreads, 0, st>>>(x, T, mm_dim, (const char*)dy, ldb, H, n, ws_dw, ws_db);
-    else mm_proj_bwd_partial_kernel<false, false><<<grid, kMmThreads, 0, st>>>(x, T, mm_dim, (const char*)dy, ldb, H, n, ws_dw, ws_db);
+    if (xb && dbf) TGR_K(mm_proj_bwd_partial_kernel<true, true>)<<<grid, kMmThreads, 0, st>>>(x, T, mm_dim, (const char*)dy, ldb, H, n, ws_dw, ws_db);
+    else if (xb) TGR_K(mm_proj_bwd_partial_kernel<true, false>)<<<grid, kMmThreads, 0, st>>>(x, T, mm_dim, (const char*)dy, ldb, H, n, ws_dw, ws_db);
+    else if (dbf) TGR_K(mm_proj_bwd_partial_kernel<false, true>)<<<grid, kMmThreads, 0, st>>>(x, T, mm_dim, (const char*)dy, ldb, H, n, ws_dw, ws_db);
+    else TGR_K(mm_proj_bwd_partial_kernel<false, false>)<<<grid, kMmThreads, 0, st>>>(x, T, mm_dim, (const char*)dy, ldb, H, n, ws_dw, ws_db);
     if (int rc = check_launch("mm_proj_bwd_partial")) return rc;
   }
   const int64_t total = (int64_t)H * mm_dim + H;
-  mm_proj_bwd_reduce_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, st>>>(ws_dw, ws_db, T > 0 ? n : 0, H, mm_dim, dW, db, accumulate);
+  TGR_K(mm_proj_bwd_reduce_kernel)<<<(unsigned)((total * 32 + 255) / 256), 256, 0, st>>>(ws_dw, ws_db, T > 0 ? n : 0, H, mm_dim, dW, db, accumulate);
   return check_launch("mm_proj_bwd_reduce");
 }

@@ -296,18 +296,18 @@ static int launch_reduce(RedParams& p, const RowParams* rp, bool bf16, int n_cta
   const size_t smem = (size_t)(2 * TILE + 4) * 4 + (size_t)2 * G * p.H4 * 16 + (size_t)2 * G * 4 + 16;
   if (bf16) {
     { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(reduce_tiles_kernel<LANES, NJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
-    reduce_tiles_kernel<LANES, NJ, true><<<n_cta, kRedThreads, smem, st>>>(p);
+    TGR_K(reduce_tiles_kernel<LANES, NJ, true>)<<<n_cta, kRedThreads, smem, st>>>(p);
   } else {
     { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(reduce_tiles_kernel<LANES, NJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
-    reduce_tiles_kernel<LANES, NJ, false><<<n_cta, kRedThreads, smem, st>>>(p);
+    TGR_K(reduce_tiles_kernel<LANES, NJ, false>)<<<n_cta, kRedThreads, smem, st>>>(p);
   }
   if (int rc = check_launch("reduce_tiles")) return rc;
   if (n_cta > 1) {
-    reduce_fixup_kernel<LANES, NJ><<<(n_cta + G - 1) / G, kRedThreads, 0, st>>>(p, n_cta);
+    TGR_K(reduce_fixup_kernel<LANES, NJ>)<<<(n_cta + G - 1) / G, kRedThreads, 0, st>>>(p, n_cta);
     if (int rc = check_launch("reduce_fixup")) return rc;
   }
   if (p.mode == 1) {
-    adam_regions_kernel<LANES, NJ><<<dim3(n_cta, kAdamSplit), kRedThreads, 0, st>>>(*rp, p.row_keys, p.row_buf, p.row_cnt);
+    TGR_K(adam_regions_kernel<LANES, NJ>)<<<dim3(n_cta, kAdamSplit), kRedThreads, 0, st>>>(*rp, p.row_keys, p.row_buf, p.row_cnt);
     return check_launch("adam_regions");
   }
   return 0;

@@ -131,9 +131,9 @@ extern "C" int tgr_route_bucket(const uint32_t* uniq, const int32_t* n_unique_de
   }
   const int nb = (int)((max_unique + kRouteBlock - 1) / kRouteBlock);
   int32_t* cnt = (int32_t*)workspace;
-  route_count_kernel<<<nb, kRouteBlock, 0, st>>>(uniq, n_unique_dev, W, nb, cnt);
-  route_scan_kernel<<<1, kRouteBlock, 0, st>>>(cnt, W, nb, counts_dev);
-  route_emit_kernel<<<nb, kRouteBlock, 0, st>>>(uniq, n_unique_dev, W, nb, cnt, bucketed_local_rows, perm);
+  TGR_K(route_count_kernel)<<<nb, kRouteBlock, 0, st>>>(uniq, n_unique_dev, W, nb, cnt);
+  TGR_K(route_scan_kernel)<<<1, kRouteBlock, 0, st>>>(cnt, W, nb, counts_dev);
+  TGR_K(route_emit_kernel)<<<nb, kRouteBlock, 0, st>>>(uniq, n_unique_dev, W, nb, cnt, bucketed_local_rows, perm);
   return check_launch("route_bucket");
 }
 
@@ -197,7 +197,7 @@ extern "C" int tgr_remap_ids(const int32_t* ids, int64_t n, int n_cols, const ui
   for (int c = 0; c < n_cols; ++c) { cols.key_base[c] = col_key_base[c]; cols.rows[c] = col_rows[c]; }
   int64_t blocks = (n + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  remap_ids_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ids, n, n_cols, cols, uniq, n_unique_dev, perm, out);
+  TGR_K(remap_ids_kernel)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ids, n, n_cols, cols, uniq, n_unique_dev, perm, out);
   return check_launch("remap_ids");
 }
 
@@ -209,7 +209,7 @@ extern "C" int tgr_permute_rows(const float* in, int H, const int32_t* perm, con
   if (max_n <= 0) return 0;
   int64_t blocks = (max_n * (H / 4) + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  permute_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, H / 4, perm, n_dev, inverse, out);
+  TGR_K(permute_rows_kernel)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, H / 4, perm, n_dev, inverse, out);
   return check_launch("permute_rows");
 }
 
@@ -254,7 +254,7 @@ extern "C" int tgr_remap_scatter(const uint32_t* srcs_sorted, const int32_t* seg
   }
   int64_t blocks = (n + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  remap_scatter_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(srcs_sorted, seg_of_entry, n, perm, p);
+  TGR_K(remap_scatter_kernel)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(srcs_sorted, seg_of_entry, n, perm, p);
   return check_launch("remap_scatter");
 }
 
@@ -325,7 +325,7 @@ extern "C" int tgr_remap_arrays(const tgr_table_t* tables, int n_tables, const t
   if (total == 0) return 0;
   int blocks = (total + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  remap_arrays_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, uniq, n_unique_dev, perm);
+  TGR_K(remap_arrays_kernel)<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, uniq, n_unique_dev, perm);
   return check_launch("remap_arrays");
 }
 
@@ -378,8 +378,8 @@ extern "C" int tgr_fetch_peer_rows(const float* const* peer_rows, int n_peers, i
   int64_t blocks = (max_unique + (256 / lanes) * 4 - 1) / ((256 / lanes) * 4);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  if (lanes == 8) fetch_peer_rows_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(pp, n_peers, H4, uniq, n_unique_dev, out);
-  else if (lanes == 16) fetch_peer_rows_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(pp, n_peers, H4, uniq, n_unique_dev, out);
-  else fetch_peer_rows_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(pp, n_peers, H4, uniq, n_unique_dev, out);
+  if (lanes == 8) TGR_K(fetch_peer_rows_kernel<8>)<<<(unsigned)blocks, 256, 0, st>>>(pp, n_peers, H4, uniq, n_unique_dev, out);
+  else if (lanes == 16) TGR_K(fetch_peer_rows_kernel<16>)<<<(unsigned)blocks, 256, 0, st>>>(pp, n_peers, H4, uniq, n_unique_dev, out);
+  else TGR_K(fetch_peer_rows_kernel<32>)<<<(unsigned)blocks, 256, 0, st>>>(pp, n_peers, H4, uniq, n_unique_dev, out);
   return check_launch("fetch_peer_rows");
 }

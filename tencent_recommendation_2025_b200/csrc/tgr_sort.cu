@@ -245,10 +245,10 @@ extern "C" int tgr_sort_pairs(const uint32_t* keys_in, const uint32_t* srcs_in, 
     const bool to_out = ((P - 1 - p) % 2) == 0;   // the last pass lands in the caller's output
     uint32_t* kdst = to_out ? keys_out : keys_tmp;
     uint32_t* vdst = to_out ? srcs_out : srcs_tmp;
-    radix_hist_kernel<<<g.n_blocks, kSortThreads, (size_t)R * 4, st>>>(ksrc, (int)n, g.tile, shift, bits, g.n_blocks, block_hist);
-    radix_binscan_kernel<<<(R * 32 + kSortThreads - 1) / kSortThreads, kSortThreads, 0, st>>>(block_hist, g.n_blocks, R, bin_total);
-    radix_totals_kernel<<<1, 1024, 0, st>>>(bin_total, R, bin_base);
-    radix_scatter_kernel<<<g.n_blocks, kSortThreads, (size_t)R * 4 + (size_t)kSortWarps * R * 2, st>>>(ksrc, vsrc, kdst, vdst, (int)n, g.tile, shift,
+    TGR_K(radix_hist_kernel)<<<g.n_blocks, kSortThreads, (size_t)R * 4, st>>>(ksrc, (int)n, g.tile, shift, bits, g.n_blocks, block_hist);
+    TGR_K(radix_binscan_kernel)<<<(R * 32 + kSortThreads - 1) / kSortThreads, kSortThreads, 0, st>>>(block_hist, g.n_blocks, R, bin_total);
+    TGR_K(radix_totals_kernel)<<<1, 1024, 0, st>>>(bin_total, R, bin_base);
+    TGR_K(radix_scatter_kernel)<<<g.n_blocks, kSortThreads, (size_t)R * 4 + (size_t)kSortWarps * R * 2, st>>>(ksrc, vsrc, kdst, vdst, (int)n, g.tile, shift,
                                                                                     bits, g.n_blocks, block_hist, bin_base);
     if (int rc = check_launch("sort_pairs")) return rc;
     ksrc = kdst;

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -19,6 +20,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -92,5 +96,6 @@ extern "C" int tgr_timing_collect(char* names, size_t names_bytes, float* ms, in
   return n;
 }
 
+extern "C" int64_t tgr_launch_count(void) { return (int64_t)tgr::g_launches.load(std::memory_order_relaxed); }
 extern "C" int tgr_abi_version(void) { return TGR_ABI_VERSION; }
 extern "C" const char* tgr_last_error(void) { return tgr::g_err; }

@@ -71,7 +71,7 @@ class EmbeddingEngine:
         self.exp_avg_sq: List[Optional[torch.Tensor]] = [None] * len(self.tables)
         self.pending: List[Tuple[PackedBatch, torch.Tensor, Optional[torch.Tensor]]] = []
         self._ws: Dict[str, torch.Tensor] = {}
-        self.launches = 0          # kernels launched by this engine (bench's gpu_launches)
+        self.launches = 0          # host-side estimate kept for debugging; the real count is _lib.launch_count()
         self.check_ids = _DEBUG
         self._err: Optional[torch.Tensor] = None
         self.timing: Optional[Dict[str, list]] = None   # set to {} to time every C-ABI call with CUDA events
@@ -290,6 +290,12 @@ class EmbeddingEngine:
     # ------------------------------------------------------------------ fused step
     def queue(self, pb: PackedBatch, d_item: torch.Tensor, d_user: Optional[torch.Tensor]):
         self.pending.append((pb, d_item, d_user))
+
+    def discard_pending(self) -> int:
+        """Drop row gradients queued for a row update that will not happen (a GradScaler skipped the step)."""
+        n = len(self.pending)
+        self.pending = []
+        return n
 
     def fused_step(self, lr: float = 1e-3, betas=(0.9, 0.98), eps: float = 1e-8, weight_decay: float = 1e-2,
                    grad_scale: float = 1.0):

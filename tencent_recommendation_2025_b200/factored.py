@@ -316,6 +316,13 @@ class FactoredEngine(EmbeddingEngine):
             self.launches += 1
         return grads
 
+    def discard_pending(self) -> int:
+        """Drop the groups whose row gradients wait for a row update that will not happen (skipped optimizer step)."""
+        groups, self.ready = self.ready, []
+        for g in groups:
+            g.release()
+        return len(groups) + super().discard_pending()
+
     # ------------------------------------------------------------------ row update
     def fused_step(self, lr: float = 1e-3, betas=(0.9, 0.98), eps: float = 1e-8, weight_decay: float = 1e-2,
                    grad_scale: float = 1.0):

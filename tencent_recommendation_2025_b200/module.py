@@ -219,13 +219,18 @@ class BaselineEmbedding(_FeatEmbMixin, torch.nn.Module):
         return [p for p in self.parameters() if id(p) not in tabs]
 
 
-def install(model, optimizer: Optional[torch.optim.Optimizer] = None, mode: str = "parity", path: str = "concat"):
+def install(model, optimizer: Optional[torch.optim.Optimizer] = None, mode: str = "parity", path: str = "concat",
+            scaler=None):
     """Replace ``model.feat2emb`` of a reference-style ``BaselineModel`` with the CUDA path, in place.
 
     The model keeps its own nn.Embedding / nn.Linear parameters (so init, checkpoints and, in parity
     mode, the optimizer are untouched). In fused mode pass the optimizer: after every
     ``optimizer.step()`` a post-hook applies the queued row updates with that optimizer's lr / betas /
-    eps / weight_decay; the tables receive no ``.grad`` so the dense optimizer skips them.
+    eps / weight_decay; the tables receive no ``.grad`` so the dense optimizer skips them. The reference routes
+    every step through ``scaler.step(optimizer)`` (main.py:189): pass that ``GradScaler`` as ``scaler`` and the row
+    update is un-scaled by the same factor (``grad_scale = 1 / scale``), and a step the scaler SKIPS (inf / NaN
+    gradients: ``optimizer.step()`` never runs, so the hook never fires) drops the queued row gradients instead of
+    leaving them to be merged into the next step.
     """
     H = model.item_emb.embedding_dim
     feat_types = {
@@ -240,15 +245,27 @@ def install(model, optimizer: Optional[torch.optim.Optimizer] = None, mode: str 
     lay = FeatureLayout(model.user_num, model.item_num, stats, feat_types, H)
     model._tgr_layout = lay
     model._tgr_engine = _make_engine(model, lay, mode, path)
-    for name in ("feat2tensor", "pack", "feat2emb", "feat2emb_packed", "prefetch", "fused_step", "check_padding_rows"):
-        setattr(model, name, types.MethodType(getattr(_FeatEmbMixin, name), model))
+    for name, fn in vars(_FeatEmbMixin).items():     # every method of the mixin, private helpers included
+        if callable(fn) and not name.startswith("__"):
+            setattr(model, name, types.MethodType(fn, model))
     if mode == "fused":
         if optimizer is None:
             raise ValueError("fused mode needs the optimizer whose step() should trigger the row update")
 
         def _post_step(opt, args, kwargs):
             g = opt.param_groups[0]
-            model._tgr_engine.fused_step(g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"])
+            scale = float(scaler.get_scale()) if scaler is not None and scaler.is_enabled() else 1.0
+            model._tgr_engine.fused_step(g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"], grad_scale=1.0 / scale)
 
         model._tgr_hook = optimizer.register_step_post_hook(_post_step)
+        if scaler is not None:
+            inner = scaler.step
+
+            def _scaler_step(opt, *a, **kw):
+                out = inner(opt, *a, **kw)
+                if opt is optimizer:
+                    model._tgr_engine.discard_pending()    # non-empty only when the scaler skipped optimizer.step()
+                return out
+
+            scaler.step = _scaler_step
     return model

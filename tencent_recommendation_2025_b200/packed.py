@@ -250,6 +250,14 @@ class HostPacked:
     def nbytes(self) -> int:
         return self.ints.numel() * 4 + sum(x.numel() * x.element_size() for x in self.mm_x)
 
+    def pin_memory(self, device=None) -> "HostPacked":
+        """DataLoader(pin_memory=True) hook (torch/utils/data/_utils/pin_memory.py calls ``.pin_memory()`` on custom
+        batch members): page-lock the staging buffers in the MAIN process, in place."""
+        if not self.ints.is_pinned():
+            self.ints = self.ints.pin_memory()
+            self.mm_x = [x.pin_memory() for x in self.mm_x]
+        return self
+
     def upload(self, device, non_blocking: bool = True) -> "PackedBatch":
         dev = self.ints.to(device, non_blocking=non_blocking)
         o, s, T = self.offs, self.sizes, self.T
@@ -260,8 +268,24 @@ class HostPacked:
                            self.arr_begin, self.arr_nnz, mm, self.n_valid, self.nbytes)
 
 
-def stage_pinned(layout: FeatureLayout, pc: PackedCall, mm_dtype: torch.dtype = torch.float32) -> HostPacked:
-    pin = torch.cuda.is_available()
+def _may_pin() -> bool:
+    """Pinned allocations need a CUDA context: never inside a DataLoader worker (fork after CUDA init cannot
+    re-initialise it, and tensors crossing the worker queue lose their pinned status anyway)."""
+    if not torch.cuda.is_available():
+        return False
+    try:
+        from torch.utils.data import get_worker_info
+        return get_worker_info() is None
+    except Exception:
+        return True
+
+
+def stage_pinned(layout: FeatureLayout, pc: PackedCall, mm_dtype: torch.dtype = torch.float32,
+                 pin: Optional[bool] = None) -> HostPacked:
+    """Host staging of one packed call: pinned in the main process, plain CPU memory inside a DataLoader worker
+    (``HostPacked.pin_memory`` lets ``DataLoader(pin_memory=True)`` pin it after it crossed the worker queue)."""
+    if pin is None:
+        pin = _may_pin()
     if pc.n_valid is None:
         pc.n_valid = count_valid(layout, pc)
     arr_tok = _arr_tok(pc)
@@ -289,7 +313,8 @@ def stage_pinned(layout: FeatureLayout, pc: PackedCall, mm_dtype: torch.dtype = 
 class PackingCollate:
     """``collate_fn`` wrapper for the reference's DataLoader (model/BaseLine/dataset.py:268-293): runs
     the dataset's own collate, then tensorizes the three feature lists of the step IN THE WORKER (one C walk each) and
-    hands them over as ``HostPacked`` calls (pinned when CUDA is available) in place of ``seq_feat / pos_feat /
+    hands them over as ``HostPacked`` calls (plain CPU tensors inside a worker; pinned by ``DataLoader(pin_memory=True)``
+    through ``HostPacked.pin_memory`` or directly when the collate runs in the main process) in place of ``seq_feat / pos_feat /
     neg_feat``. The model code stays as it is — ``feat2emb(seq, seq_feature, mask, include_user)`` recognises a packed
     call in the ``feature_array`` position — and the three calls of a step carry a reference to each other, so the
     factored engine prepares them as ONE group on the first ``feat2emb`` of the step.

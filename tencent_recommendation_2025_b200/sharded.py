@@ -585,9 +585,15 @@ class ShardedRank:
         h, ev = p["host"]
         if ev is not None:
             ev.synchronize()          # normally long complete: the copy was issued a phase earlier
+        if getattr(ops, "peers", None) is not None and getattr(self, "pf", None) is not None:
+            # peers read rows / write gradient windows as soon as this step's id all-to-all completes: that is only
+            # safe behind every owner's previous row update, i.e. after fused_step() of the step in flight
+            raise RuntimeError("finish_prepare() before fused_step() of the current step: the id all-to-all is the "
+                               "barrier behind the owners' row update and must be enqueued after it")
         starts, window = None, False
         if "M" in p:
             M = h.tolist()
+            p["M_host"] = M
             send_counts, recv_counts = M[self.rank], [M[s][self.rank] for s in range(self.W)]
             starts = [sum(M[s][:self.rank]) for s in range(self.W)]      # my bucket's first row in source s' window
             # every rank sees the same matrix, so all of them take the same branch
@@ -622,8 +628,11 @@ class ShardedRank:
             # exchange is ordering — every owner's previous row update must be complete before anybody reads. The
             # local-row id all-to-all of this step was enqueued AFTER that update on every rank and completes here
             # only once every peer's part has arrived, so it already is that barrier — unless some pair of ranks
-            # exchanged nothing, in which case an explicit one is issued.
-            if min(p["send_counts"]) == 0 or min(p["recv_counts"]) == 0:
+            # exchanged nothing (then no message orders them), in which case an explicit one is issued.
+            # The decision must be the same on EVERY rank (a barrier is a collective): it is taken from the all-gathered
+            # W x W count matrix when the step has one, else the barrier is always issued.
+            M = p.get("M_host")
+            if M is None or any(c == 0 for row in M for c in row):
                 yield ("barrier", ops._bar)
             ops.fetch_rows_async(p["pf"])
             back = None
