@@ -131,6 +131,17 @@ int tgr_fwd_gather_pool_concat(const tgr_table_t* tables, int n_tables, int H, c
 int tgr_mm_proj_fwd(const void* x, int x_dtype, int64_t T, int mm_dim, const float* W, const float* bias, int H,
                     void* out, int64_t out_ld, int out_dtype, void* stream);
 
+/* The same projection on the 5th-generation tensor cores (tcgen05.mma kind::f16 + TMEM accumulator, x and W tiles
+ * streamed by TMA with 128-byte swizzle; csrc/tgr_mm_tc.cu) for the wide frozen mm features kept in bf16 (BASELINE.json
+ * config 3: '82' = 1024-d ... '84' = 4096-d, model.py:183): x bf16 [T, mm_dim], w_bf16 = bf16 copy of W [H, mm_dim]
+ * (tgr_cast_bf16), fp32 accumulate, bias fp32 or NULL. Needs mm_dim % 64 == 0, mm_dim >= 128, H in {32, 64, 128}
+ * (tgr_mm_proj_fwd_tc_supported). */
+int tgr_mm_proj_fwd_tc_supported(int x_dtype, int mm_dim, int H);
+int tgr_mm_proj_fwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* w_bf16, const float* bias, int H, void* out,
+                       int64_t out_ld, int out_dtype, void* stream);
+/* dst_bf16[i] = bf16(src[i]) (round to nearest even), n elements; src 16-byte, dst 8-byte aligned. */
+int tgr_cast_bf16(const float* src, int64_t n, void* dst_bf16, void* stream);
+
 /* mm projection backward: dW[H, mm_dim] (+)= dY^T . x ; db[H] (+)= sum_t dY. dY is read in place from the
  * concat gradient (pointer already offset to the slot's column). Deterministic split-T reduction.
  * workspace: tgr_mm_proj_bwd_workspace_bytes(). (autograd of model.py:297) */
@@ -360,6 +371,7 @@ typedef struct tgr_fact_group {
   float* dz_user[TGR_MAX_CALLS];
   float* mmz[TGR_MAX_CALLS][TGR_MAX_MM];
   float *fold_M[TGR_MAX_MM], *fold_c[TGR_MAX_MM], *mm_A[TGR_MAX_MM], *mm_s[TGR_MAX_MM];
+  void* fold_Mb[TGR_MAX_MM];           /* bf16 copy of fold_M for the tcgen05 projection (wide bf16 mm features) */
   void* ws;
   size_t ws_bytes;
   int32_t projected, n_backward;       /* progress */

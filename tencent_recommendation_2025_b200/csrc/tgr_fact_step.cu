@@ -85,6 +85,7 @@ static size_t carve(tgr_fact_group_t* g, void* arena, int n_tables) {
     g->fold_c[f] = cv.take<float>(H);
     g->mm_A[f] = cv.take<float>((size_t)H * g->mm_dim[f]);
     g->mm_s[f] = cv.take<float>(H);
+    g->fold_Mb[f] = cv.take<uint16_t>((size_t)H * g->mm_dim[f]);
   }
   ws = max(ws, tgr_build_keys_workspace_bytes(max_entries));
   ws = max(ws, tgr_sort_workspace_bytes(g->n));
@@ -163,12 +164,19 @@ extern "C" int tgr_fact_call_forward(const tgr_table_t* tables, int n_tables, co
       TGR_REQUIRE(m.mm_dim == g->mm_dim[f], "mm_dim mismatch");
       if (int rc = tgr_fact_mm_fold(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, H, m.mm_dim, g->fold_M[f],
                                     g->fold_c[f], stream)) return rc;
+      if (tgr_mm_proj_fwd_tc_supported(g->mm_x_dtype, m.mm_dim, H))   // wide bf16 feature: tcgen05 path wants a bf16 M
+        if (int rc = tgr_cast_bf16(g->fold_M[f], (int64_t)H * m.mm_dim, g->fold_Mb[f], stream)) return rc;
     }
     g->projected = 1;
   }
   tgr_call_t& cl = g->calls[c];
   for (int f = 0; f < g->n_mm; ++f) {
     TGR_REQUIRE(g->mm_x[c][f] != nullptr, "mm input %d of call %d is NULL", f, c);
+    if (tgr_mm_proj_fwd_tc_supported(g->mm_x_dtype, g->mm_dim[f], H)) {
+      if (int rc = tgr_mm_proj_fwd_tc(g->mm_x[c][f], cl.T, g->mm_dim[f], g->fold_Mb[f], g->fold_c[f], H, g->mmz[c][f], H,
+                                      TGR_DTYPE_F32, stream)) return rc;
+      continue;
+    }
     if (int rc = tgr_mm_proj_fwd(g->mm_x[c][f], g->mm_x_dtype, cl.T, g->mm_dim[f], g->fold_M[f], g->fold_c[f], H,
                                  g->mmz[c][f], H, TGR_DTYPE_F32, stream)) return rc;
   }

@@ -21,7 +21,11 @@
 // parity bar. Every reduction order is a function of the sorted unique-key list and the launch geometry only.
 // This is SURVEY.md §8(f) N4 obtained through deduplication instead of a gather-prologue GEMM.
 #include "tgr_common.cuh"
+#include "tgr_mma.cuh"
 #include "tgr_rows.cuh"
+#include "tgr_tc.cuh"
+
+#include <stdlib.h>
 
 namespace tgr {
 
@@ -239,9 +243,401 @@ __global__ void __launch_bounds__(RowsCfg<H>::NT) fact_rows_kernel(const __grid_
   if (MODE == 1 && cur_t >= 0) flush_dw(cur_t);
 }
 
+// ---- tensor-core variant of the two row GEMMs (H = 32, 64): 3xTF32 mma.sync, fp32 accumulate (tgr_mma.cuh) ---------
+// Same persistent tiling and the same (CTA, table) split-K partial scheme as fact_rows_kernel; what changes is the
+// contraction: a CTA is 4 warps over a 128-row tile, warp w owns rows [32w, 32w+32) x all H columns of the row GEMM
+// (2 x H/8 m16n8 accumulator tiles) and, in MODE 1, one 16-row slab (x H/8 / n_groups column tiles) of the H x H dW
+// block, accumulated over the tile's rows (K = 128 per tile) and kept in registers across the CTA's tiles.
+// Shared memory: the table's weight block already split into tf32 hi / lo parts, laid out [n][k] with pitch H + 4 so
+// that every fragment load of the row GEMM is bank-conflict free (rows 4 banks apart); the row tiles stay fp32 and are
+// split after the load. 70 KB (MODE 0, 3 CTAs / SM) / 104 KB (MODE 1, 2 CTAs / SM) at H = 64.
+template <int H>
+struct MmaRowsCfg {
+  static constexpr int RT = 128, NT = 128, LD = H + 4, NTILES = H / 8, KSTEPS = H / 8;
+  static constexpr int MT_DW = H / 16;            // 16-row slabs of the dW block
+  static constexpr int NG_DW = 4 / MT_DW;         // warps sharing one slab split its column tiles
+  static constexpr int NPW = NTILES / NG_DW;      // column tiles of the dW block per warp
+  static_assert(H == 32 || H == 64, "tile shape");
+};
+constexpr int kMmaGridFwd = 3 * kNumSMs;
+constexpr int kMmaGridBwd = 2 * kNumSMs;
+
+template <int H, int MODE>
+__global__ void __launch_bounds__(MmaRowsCfg<H>::NT) fact_rows_mma_kernel(const __grid_constant__ FactParams p,
+                                                                          const uint32_t* __restrict__ uniq,
+                                                                          const int32_t* __restrict__ n_unique_dev,
+                                                                          float* __restrict__ PG,
+                                                                          float* __restrict__ dw_part) {
+  using Cfg = MmaRowsCfg<H>;
+  constexpr int kRT = Cfg::RT, NT = Cfg::NT, LD = Cfg::LD, NTILES = Cfg::NTILES, KSTEPS = Cfg::KSTEPS;
+  constexpr int MT_DW = Cfg::MT_DW, NPW = Cfg::NPW;
+  extern __shared__ __align__(16) float sm[];
+  uint32_t* Whi = reinterpret_cast<uint32_t*>(sm);   // [H][LD] tf32 hi part; MODE 0: [n = h][k]  MODE 1: [n = k][h]
+  uint32_t* Wlo = Whi + H * LD;                      // [H][LD] tf32 lo part
+  float* Xs = reinterpret_cast<float*>(Wlo + H * LD);   // [kRT][LD] MODE 0: table rows   MODE 1: G rows
+  float* Rs = Xs + kRT * LD;                            // [kRT][LD] MODE 1: table rows
+  __shared__ uint32_t s_key[kRT];
+  __shared__ int32_t s_perm[kRT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const int U = *n_unique_dev;
+  const int n_tiles = (U + kRT - 1) / kRT;
+  const int tpc = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_a = blockIdx.x * tpc, tile_b = min(n_tiles, tile_a + tpc);
+  const int mt_dw = warp % MT_DW, ng_dw = warp / MT_DW;
+  int cur_t = -1;
+  float dw[NPW][4];
+#pragma unroll
+  for (int j = 0; j < NPW; ++j) dw[j][0] = dw[j][1] = dw[j][2] = dw[j][3] = 0.f;
+
+  auto flush_dw = [&](int t) {
+    float* dst = dw_part + (size_t)(blockIdx.x + t) * H * H;   // (cta, table) pairs are monotone => unique slots
+#pragma unroll
+    for (int j = 0; j < NPW; ++j) {
+      const int h = 16 * mt_dw + g, k = 8 * (ng_dw * NPW + j) + 2 * t4;
+      *reinterpret_cast<float2*>(dst + h * H + k) = make_float2(dw[j][0], dw[j][1]);
+      *reinterpret_cast<float2*>(dst + (h + 8) * H + k) = make_float2(dw[j][2], dw[j][3]);
+      dw[j][0] = dw[j][1] = dw[j][2] = dw[j][3] = 0.f;
+    }
+  };
+
+  for (int tile = tile_a; tile < tile_b; ++tile) {
+    const int r0 = tile * kRT;
+    const int nr = min(kRT, U - r0);
+    __syncthreads();
+    for (int i = tid; i < kRT; i += NT) {
+      s_key[i] = i < nr ? __ldg(uniq + r0 + i) : 0xFFFFFFFFu;
+      if (p.fetched != nullptr) s_perm[i] = i >= nr ? 0 : (p.fetched_perm ? __ldg(p.fetched_perm + r0 + i) : r0 + i);
+    }
+    __syncthreads();
+    int seg_a = 0;
+    while (seg_a < nr) {
+      const int t = find_table(p.key_base, p.n_tables, s_key[seg_a]);
+      const uint32_t kend = p.key_base[t + 1];
+      int seg_b;
+      if (s_key[nr - 1] < kend) {
+        seg_b = nr;
+      } else {   // first row of the next table, by bisection (uniform across the CTA: shared-memory broadcast reads)
+        int lo = seg_a + 1, hi = nr - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] < kend) lo = mid + 1; else hi = mid; }
+        seg_b = lo;
+      }
+      const int ns = seg_b - seg_a;
+      __syncthreads();   // previous segment's readers of Xs / Rs / W are done
+      if (t != cur_t) {
+        if (MODE == 1 && cur_t >= 0) flush_dw(cur_t);
+        const float* W = p.dnn_w[p.side[t]];
+        const int64_t ld = p.dnn_ld[p.side[t]];
+        const int col = p.col[t];
+        constexpr int WPT = H * (H / 4) / NT;   // all 128-bit loads in flight before the first use
+        float4 wv[WPT];
+#pragma unroll
+        for (int q = 0; q < WPT; ++q) {
+          const int i = tid + q * NT, h = i / (H / 4), c = i - h * (H / 4);
+          wv[q] = __ldg(reinterpret_cast<const float4*>(W + (size_t)h * ld + col) + c);   // col % H == 0, ld % 4 == 0
+        }
+#pragma unroll
+        for (int q = 0; q < WPT; ++q) {
+          const int i = tid + q * NT, h = i / (H / 4), k = (i - h * (H / 4)) * 4;
+          const float w4[4] = {wv[q].x, wv[q].y, wv[q].z, wv[q].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t hi, lo;
+            split_tf32(w4[j], hi, lo);
+            const int idx = MODE == 1 ? (k + j) * LD + h : h * LD + k + j;
+            Whi[idx] = hi;
+            Wlo[idx] = lo;
+          }
+        }
+        cur_t = t;
+      }
+      const float* tab = p.w[t];
+      const uint32_t kb = p.key_base[t];
+      for (int i = tid; i < kRT * (H / 4); i += NT) {   // every 16-byte piece of the tile in flight at once (zero-filled past ns)
+        const int r = i / (H / 4), c = i - r * (H / 4);
+        const bool ok = r < ns;
+        const float* rsrc;
+        if (p.n_peers > 0) {          // the owner's shard, read in place through NVLink peer memory
+          const uint32_t key = ok ? s_key[seg_a + r] : 0u;
+          rsrc = p.peer[key % (uint32_t)p.n_peers] + (size_t)(key / (uint32_t)p.n_peers) * H + c * 4;
+        } else if (p.fetched != nullptr) {
+          rsrc = ok ? p.fetched + (size_t)s_perm[seg_a + r] * H + c * 4 : p.fetched;
+        } else {
+          rsrc = ok ? tab + (size_t)(s_key[seg_a + r] - kb) * H + c * 4 : tab;
+        }
+        if (MODE == 1) {
+          cp_async16(Rs + r * LD + c * 4, rsrc, ok ? 16 : 0);
+          cp_async16(Xs + r * LD + c * 4, ok ? PG + (size_t)(r0 + seg_a + r) * H + c * 4 : PG, ok ? 16 : 0);
+        } else {
+          cp_async16(Xs + r * LD + c * 4, rsrc, ok ? 16 : 0);
+        }
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      if (MODE == 0 && p.save_rows != nullptr) {
+        for (int i = tid; i < ns * (H / 4); i += NT) {
+          const int r = i / (H / 4), c = i - r * (H / 4);
+          st_stream(reinterpret_cast<float4*>(p.save_rows + (size_t)(r0 + seg_a + r) * H) + c,
+                    *reinterpret_cast<const float4*>(Xs + r * LD + c * 4));
+        }
+      }
+      // ---- row GEMM: out[r][n] = sum_k Xs[r][k] * Wsm[n][k]; warp rows [32 warp, 32 warp + 32)
+      const int m0 = warp * 32;
+      if (m0 < ns) {
+        float acc[2][NTILES][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NTILES; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll 2
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const float* xr = Xs + (m0 + 16 * mt + g) * LD + 8 * ks + t4;
+            split_tf32(xr[0], ahi[mt][0], alo[mt][0]);
+            split_tf32(xr[8 * LD], ahi[mt][1], alo[mt][1]);
+            split_tf32(xr[4], ahi[mt][2], alo[mt][2]);
+            split_tf32(xr[8 * LD + 4], ahi[mt][3], alo[mt][3]);
+          }
+#pragma unroll
+          for (int nt = 0; nt < NTILES; ++nt) {
+            const int wi = (8 * nt + g) * LD + 8 * ks + t4;
+            const uint32_t bhi[2] = {Whi[wi], Whi[wi + 4]};
+            const uint32_t blo[2] = {Wlo[wi], Wlo[wi + 4]};
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_3xtf32(acc[mt][nt], ahi[mt], alo[mt], bhi, blo);
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int ra = m0 + 16 * mt + g, rb = ra + 8;
+          float* da = PG + (size_t)(r0 + seg_a + ra) * H + 2 * t4;
+          float* db = PG + (size_t)(r0 + seg_a + rb) * H + 2 * t4;
+#pragma unroll
+          for (int nt = 0; nt < NTILES; ++nt) {
+            if (ra < ns) *reinterpret_cast<float2*>(da + 8 * nt) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+            if (rb < ns) *reinterpret_cast<float2*>(db + 8 * nt) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+          }
+        }
+      }
+      // ---- dW GEMM: dw[h][k] += sum_r G[r][h] * R[r][k] over the tile's rows (zero-filled past ns), 8 rows per step
+      if (MODE == 1) {
+        const int ksn = (ns + 7) >> 3;
+#pragma unroll 2
+        for (int ks = 0; ks < ksn; ++ks) {
+          const float* ga = Xs + (8 * ks + t4) * LD + 16 * mt_dw + g;
+          uint32_t ahi[4], alo[4];
+          split_tf32(ga[0], ahi[0], alo[0]);
+          split_tf32(ga[8], ahi[1], alo[1]);
+          split_tf32(ga[4 * LD], ahi[2], alo[2]);
+          split_tf32(ga[4 * LD + 8], ahi[3], alo[3]);
+          const float* rb = Rs + (8 * ks + t4) * LD + 8 * (ng_dw * NPW) + g;
+#pragma unroll
+          for (int j = 0; j < NPW; ++j) {
+            uint32_t bhi[2], blo[2];
+            split_tf32(rb[8 * j], bhi[0], blo[0]);
+            split_tf32(rb[8 * j + 4 * LD], bhi[1], blo[1]);
+            mma_3xtf32(dw[j], ahi, alo, bhi, blo);
+          }
+        }
+      }
+      seg_a = seg_b;
+    }
+  }
+  if (MODE == 1 && cur_t >= 0) flush_dw(cur_t);
+}
+
+// ---- tcgen05 variant of the forward projection (H = 32, 64): P[u] = W_s . row[u] on the 5th-generation tensor cores ----
+// M = 128 unique rows x N = H x K = H per tile, kind::tf32 with the 3xTF32 split (tgr_mma.cuh): 3 * H/8 MMAs issued by one
+// thread into ONE TMEM accumulator [128 lanes x H fp32 columns], committed to an mbarrier; the four warps then read
+// their 32 lanes back with tcgen05.ld and store the rows. Operands are staged in shared memory in the K-major no-swizzle
+// core-matrix layout (tgr_tc.cuh): rows are loaded with 128-bit LDGs (lanes 0-7 = 8 consecutive rows of one 64-byte
+// column block, so each row segment is two full sectors and each STS.128 phase writes one 128-byte core matrix),
+// split into tf32 hi / lo in registers and stored to the A_hi / A_lo tiles. mma.sync (fact_rows_mma_kernel) tops out at
+// the legacy tensor path's rate (measured 54 us for 227 k rows vs 70 us FFMA); the tcgen05 pipe runs kind::tf32 ~8x faster,
+// which leaves the kernel bound by the scattered row reads.
+template <int H>
+struct TcRowsCfg {
+  static constexpr int RT = 128, NT = 128;
+  static constexpr int LBO = 128, SBO = (H / 4) * 128;          // bytes
+  static constexpr int A_BYTES = RT * H * 4, B_BYTES = H * H * 4;
+  static constexpr int TMEM_COLS = H < 32 ? 32 : H;
+  static constexpr size_t SMEM = 2 * (size_t)A_BYTES + 2 * (size_t)B_BYTES + 1024;   // + alignment slack
+  static_assert(H == 32 || H == 64, "tile shape");
+};
+constexpr int kTcGridFwd = 2 * kNumSMs;
+
+template <int H>
+__global__ void __launch_bounds__(TcRowsCfg<H>::NT) fact_rows_tc_kernel(const __grid_constant__ FactParams p,
+                                                                        const uint32_t* __restrict__ uniq,
+                                                                        const int32_t* __restrict__ n_unique_dev,
+                                                                        float* __restrict__ P) {
+  using Cfg = TcRowsCfg<H>;
+  constexpr int kRT = Cfg::RT, NT = Cfg::NT, H4 = H / 4;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* Ahi = base;
+  uint8_t* Alo = Ahi + Cfg::A_BYTES;
+  uint8_t* Bhi = Alo + Cfg::A_BYTES;
+  uint8_t* Blo = Bhi + Cfg::B_BYTES;
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t s_tmem;
+  __shared__ uint32_t s_key[kRT];
+  __shared__ int32_t s_perm[kRT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) tc::mbar_init(&mbar, 1);
+  if (warp == 0) tc::tmem_alloc<Cfg::TMEM_COLS>(&s_tmem);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tacc = s_tmem;
+  const uint32_t idesc = tc::make_idesc(2u, 128, H);
+  uint32_t phase = 0;
+  const int U = *n_unique_dev;
+  const int n_tiles = (U + kRT - 1) / kRT;
+  const int tpc = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_a = blockIdx.x * tpc, tile_b = min(n_tiles, tile_a + tpc);
+  int cur_t = -1;
+  for (int tile = tile_a; tile < tile_b; ++tile) {
+    const int r0 = tile * kRT;
+    const int nr = min(kRT, U - r0);
+    __syncthreads();
+    for (int i = tid; i < kRT; i += NT) {
+      s_key[i] = i < nr ? __ldg(uniq + r0 + i) : 0xFFFFFFFFu;
+      if (p.fetched != nullptr) s_perm[i] = i >= nr ? 0 : (p.fetched_perm ? __ldg(p.fetched_perm + r0 + i) : r0 + i);
+    }
+    __syncthreads();
+    int seg_a = 0;
+    while (seg_a < nr) {
+      const int t = find_table(p.key_base, p.n_tables, s_key[seg_a]);
+      const uint32_t kend = p.key_base[t + 1];
+      int seg_b;
+      if (s_key[nr - 1] < kend) {
+        seg_b = nr;
+      } else {
+        int lo = seg_a + 1, hi = nr - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] < kend) lo = mid + 1; else hi = mid; }
+        seg_b = lo;
+      }
+      const int ns = seg_b - seg_a;
+      // (the previous segment's MMAs have completed — every thread waited on the mbarrier — so the tiles are free)
+      if (t != cur_t) {
+        const float* W = p.dnn_w[p.side[t]];
+        const int64_t ld = p.dnn_ld[p.side[t]];
+        const int col = p.col[t];
+        // B[n = h][k]: core matrix (h / 8, k / 4). All of the thread's 128-bit loads are issued before the first use (a
+        // load -> split -> store loop exposed one L2 round trip per iteration: 12 us per table switch, profiles/README.md)
+        constexpr int WPT = H * H4 / NT;
+        float4 wv[WPT];
+#pragma unroll
+        for (int q = 0; q < WPT; ++q) {
+          const int i = tid + q * NT, h = i / H4, c = i - h * H4;
+          wv[q] = __ldg(reinterpret_cast<const float4*>(W + (size_t)h * ld + col) + c);   // col % H == 0, ld % 4 == 0
+        }
+#pragma unroll
+        for (int q = 0; q < WPT; ++q) {
+          const int i = tid + q * NT, h = i / H4, c = i - h * H4;
+          uint4 hi, lo;
+          split_tf32(wv[q].x, hi.x, lo.x);
+          split_tf32(wv[q].y, hi.y, lo.y);
+          split_tf32(wv[q].z, hi.z, lo.z);
+          split_tf32(wv[q].w, hi.w, lo.w);
+          const int off = (h >> 3) * Cfg::SBO + c * Cfg::LBO + (h & 7) * 16;
+          *reinterpret_cast<uint4*>(Bhi + off) = hi;
+          *reinterpret_cast<uint4*>(Blo + off) = lo;
+        }
+        cur_t = t;
+      }
+      const float* tab = p.w[t];
+      const uint32_t kb = p.key_base[t];
+      // unit = (8-row group rg, block of 4 chunks): lane -> (row rg * 8 + lane % 8, chunk 4 * cq + lane / 8)
+      constexpr int UNITS = (kRT / 8) * (H4 / 4), UPW = UNITS / 4;
+      float4 v[UPW];
+#pragma unroll
+      for (int q = 0; q < UPW; ++q) {
+        const int unit = warp * UPW + q;
+        const int rg = unit / (H4 / 4), cq = unit % (H4 / 4);
+        const int r = rg * 8 + (lane & 7), c = cq * 4 + (lane >> 3);
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < ns) {
+          const float* rsrc;
+          if (p.n_peers > 0) {
+            const uint32_t key = s_key[seg_a + r];
+            rsrc = p.peer[key % (uint32_t)p.n_peers] + (size_t)(key / (uint32_t)p.n_peers) * H;
+          } else if (p.fetched != nullptr) {
+            rsrc = p.fetched + (size_t)s_perm[seg_a + r] * H;
+          } else {
+            rsrc = tab + (size_t)(s_key[seg_a + r] - kb) * H;
+          }
+          v[q] = __ldg(reinterpret_cast<const float4*>(rsrc) + c);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < UPW; ++q) {
+        const int unit = warp * UPW + q;
+        const int rg = unit / (H4 / 4), cq = unit % (H4 / 4);
+        const int r = rg * 8 + (lane & 7), c = cq * 4 + (lane >> 3);
+        if (p.save_rows != nullptr && r < ns)
+          st_stream(reinterpret_cast<float4*>(p.save_rows + (size_t)(r0 + seg_a + r) * H) + c, v[q]);
+        uint4 hi, lo;
+        split_tf32(v[q].x, hi.x, lo.x);
+        split_tf32(v[q].y, hi.y, lo.y);
+        split_tf32(v[q].z, hi.z, lo.z);
+        split_tf32(v[q].w, hi.w, lo.w);
+        const int off = rg * Cfg::SBO + c * Cfg::LBO + (lane & 7) * 16;
+        *reinterpret_cast<uint4*>(Ahi + off) = hi;
+        *reinterpret_cast<uint4*>(Alo + off) = lo;
+      }
+      tc::fence_smem_to_async();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t a_hi = tc::smem_u32(Ahi), a_lo = tc::smem_u32(Alo), b_hi = tc::smem_u32(Bhi), b_lo = tc::smem_u32(Blo);
+#pragma unroll
+        for (int ks = 0; ks < H / 8; ++ks) {
+          const uint32_t o = ks * 2 * Cfg::LBO;
+          const uint64_t dah = tc::make_desc(a_hi + o, Cfg::LBO, Cfg::SBO, 0), dal = tc::make_desc(a_lo + o, Cfg::LBO, Cfg::SBO, 0);
+          const uint64_t dbh = tc::make_desc(b_hi + o, Cfg::LBO, Cfg::SBO, 0), dbl = tc::make_desc(b_lo + o, Cfg::LBO, Cfg::SBO, 0);
+          tc::mma_tf32(tacc, dal, dbh, idesc, ks > 0);
+          tc::mma_tf32(tacc, dah, dbl, idesc, true);
+          tc::mma_tf32(tacc, dah, dbh, idesc, true);
+        }
+        tc::commit(&mbar);
+      }
+      tc::mbar_wait(&mbar, phase);
+      phase ^= 1u;
+      tc::fence_after_sync();
+      {
+        const int r = warp * 32 + lane;
+        float* dst = P + (size_t)(r0 + seg_a + r) * H;
+        const uint32_t taddr = tacc + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < H; c0 += 16) {
+          uint32_t rr[16];
+          tc::ld16(taddr + c0, rr);
+          tc::ld_wait();
+          if (r < ns) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]),
+                                                                     __uint_as_float(rr[j + 2]), __uint_as_float(rr[j + 3]));
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncthreads();   // every warp has drained its TMEM lanes before the next segment's first MMA overwrites them
+      seg_a = seg_b;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<Cfg::TMEM_COLS>(tacc);
+}
+
 // dW[:, col(t) : col(t)+H] (+)= sum of table t's split-K partials in CTA order. grid = (n_tables, H*H/64);
 // 4 strided lanes per output element (ascending inside a lane, unrolled loads), combined in fixed order.
-template <int H>
+template <int H, int kRT, int RG>
 __global__ void __launch_bounds__(kFT) fact_dw_reduce_kernel(const __grid_constant__ FactParams p,
                                                              const uint32_t* __restrict__ uniq,
                                                              const int32_t* __restrict__ n_unique_dev,
@@ -260,14 +656,12 @@ __global__ void __launch_bounds__(kFT) fact_dw_reduce_kernel(const __grid_consta
   float* dW = p.side[t] == 0 ? dW_item : dW_user;
   if (dW == nullptr) return;
   const int64_t ld = p.dnn_ld[p.side[t]];
-  constexpr int kRT = RowsCfg<H>::RT;
   const int n_tiles = (U + kRT - 1) / kRT;
   const int tpc = (n_tiles + rows_grid - 1) / rows_grid;
   const int cta_a = (a / kRT) / tpc, cta_b = ((b - 1) / kRT) / tpc;
   const int ol = threadIdx.x % 64, pl = threadIdx.x / 64;
   const int i = blockIdx.y * 64 + ol;
   // partial slots of table t: ((cta + t) * RG + rg), cta in [cta_a, cta_b], rg in [0, RG)  => one contiguous run
-  constexpr int RG = RowsCfg<H>::RG;
   const float* src = dw_part + (size_t)t * RG * H * H + i;
   const int ca = cta_a * RG, cb = cta_b * RG + RG - 1;
   float s = 0.f;
@@ -425,19 +819,20 @@ __global__ void __launch_bounds__(kFT) fact_dz_kernel(const float4* __restrict__
                                                       float4* __restrict__ dzi, float4* __restrict__ dzu,
                                                       const void* __restrict__ x, int T, int chunk,
                                                       float* __restrict__ part /* [grid][2H (+ H*32)] */) {
-  constexpr int H4 = H / 4, RL = kFT / H4, NJ = kDzTok / RL, LD = H + 4, XLD = kDzMM + 4, NI = H / 32;
+  constexpr int H4 = H / 4, RL = kFT / H4, NJ = kDzTok / RL, LD = H + 4, XLD = kDzMM + 4, TPW = H / 32;
   constexpr int PART = 2 * H + (MM ? H * kDzMM : 0);
   extern __shared__ __align__(16) float dsm[];
   float* Ds = dsm;                      // [kDzTok][LD]   (MM)
   float* Xs = Ds + kDzTok * LD;         // [kDzTok][XLD]  (MM)
   __shared__ float4 s_acc[2][kFT];
   const int tid = threadIdx.x, c = tid % H4, rl = tid / H4;
-  const int tk = tid % 8, th = tid / 8;
+  // A = dZ_item^T x on the tensor cores (3xTF32, tgr_mma.cuh): the [H x 32] block is (H/16) x 4 m16n8 tiles, TPW per warp
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const int ta = blockIdx.x * chunk, tb = min(T, ta + chunk);
   float4 si = make_float4(0.f, 0.f, 0.f, 0.f), su = si;
-  float4 acc[NI];
+  float acc[TPW][4];
 #pragma unroll
-  for (int i = 0; i < NI; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < TPW; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
   for (int t0 = ta; t0 < tb; t0 += kDzTok) {
     float4 d[NJ];
     unsigned m[NJ];
@@ -484,11 +879,22 @@ __global__ void __launch_bounds__(kFT) fact_dz_kernel(const float4* __restrict__
     }
     if (MM) {
       __syncthreads();
-#pragma unroll 4
-      for (int r = 0; r < kDzTok; ++r) {
-        const float4 xv = *reinterpret_cast<const float4*>(Xs + r * XLD + tk * 4);
+#pragma unroll 2
+      for (int ks = 0; ks < kDzTok / 8; ++ks) {
 #pragma unroll
-        for (int i = 0; i < NI; ++i) fma4(acc[i], Ds[r * LD + th + 32 * i], xv);
+        for (int i = 0; i < TPW; ++i) {
+          const int q = warp * TPW + i, mt = q >> 2, nt = q & 3;
+          const float* da = Ds + (8 * ks + t4) * LD + 16 * mt + g;     // A[m = h][k = token] = Ds[token][h]
+          const float* xb = Xs + (8 * ks + t4) * XLD + 8 * nt + g;     // B[k = token][n = j] = Xs[token][j]
+          uint32_t ahi[4], alo[4], bhi[2], blo[2];
+          split_tf32(da[0], ahi[0], alo[0]);
+          split_tf32(da[8], ahi[1], alo[1]);
+          split_tf32(da[4 * LD], ahi[2], alo[2]);
+          split_tf32(da[4 * LD + 8], ahi[3], alo[3]);
+          split_tf32(xb[0], bhi[0], blo[0]);
+          split_tf32(xb[4 * XLD], bhi[1], blo[1]);
+          mma_3xtf32(acc[i], ahi, alo, bhi, blo);
+        }
       }
       __syncthreads();
     }
@@ -505,7 +911,12 @@ __global__ void __launch_bounds__(kFT) fact_dz_kernel(const float4* __restrict__
   }
   if (MM) {
 #pragma unroll
-    for (int i = 0; i < NI; ++i) *reinterpret_cast<float4*>(dst + 2 * H + (th + 32 * i) * kDzMM + tk * 4) = acc[i];
+    for (int i = 0; i < TPW; ++i) {
+      const int q = warp * TPW + i, mt = q >> 2, nt = q & 3;
+      float* d0 = dst + 2 * H + (16 * mt + g) * kDzMM + 8 * nt + 2 * t4;
+      *reinterpret_cast<float2*>(d0) = make_float2(acc[i][0], acc[i][1]);
+      *reinterpret_cast<float2*>(d0 + 8 * kDzMM) = make_float2(acc[i][2], acc[i][3]);
+    }
   }
 }
 
@@ -623,12 +1034,14 @@ static int fill_fact(FactParams& p, const tgr_table_t* tables, int n_tables, int
     TGR_REQUIRE(p.side[t] == 0 || (p.side[t] == 1 && dnn->w_user), "table %d: bad side %d", t, (int)p.side[t]);
     const int64_t ld = p.side[t] == 0 ? dnn->item_ld : dnn->user_ld;
     TGR_REQUIRE(p.col[t] >= 0 && p.col[t] + H <= ld, "table %d: DNN columns out of range", t);
+    TGR_REQUIRE(p.col[t] % 4 == 0 && ld % 4 == 0, "table %d: DNN column / pitch not 128-bit tileable", t);
     if (t) TGR_REQUIRE(tables[t].key_base == tables[t - 1].key_base + tables[t - 1].rows, "key bases must be cumulative");
   }
   p.key_base[n_tables] = (uint32_t)(tables[n_tables - 1].key_base + tables[n_tables - 1].rows);
   TGR_REQUIRE(fetched != nullptr || fetched_perm == nullptr, "a permutation without fetched rows");
   p.fetched = fetched;
   p.fetched_perm = fetched_perm;
+  TGR_REQUIRE(((uintptr_t)dnn->w_item & 15) == 0 && ((uintptr_t)dnn->w_user & 15) == 0, "DNN weights must be 16-byte aligned");
   p.dnn_w[0] = dnn->w_item; p.dnn_ld[0] = dnn->item_ld;
   p.dnn_w[1] = dnn->w_user; p.dnn_ld[1] = dnn->user_ld;
   return 0;
@@ -637,6 +1050,12 @@ static int fill_fact(FactParams& p, const tgr_table_t* tables, int n_tables, int
 static int rows_rt(int H) { return H == 64 ? 64 : 128; }
 static size_t fact_smem(int H, bool bwd) { return (size_t)(H * (H + 4) + (bwd ? 2 : 1) * rows_rt(H) * (H + 4)) * sizeof(float); }
 static int rows_rg(int H) { return (H / 8) * (rows_rt(H) / 8) / ((H / 8) * (H / 8)); }
+static size_t mma_smem(int H, bool bwd) { return (size_t)(2 * H * (H + 4) + (bwd ? 2 : 1) * 128 * (H + 4)) * sizeof(float); }
+// TGR_ROWS_FFMA=1 selects the fp32 CUDA-core kernels for every H (A/B timing, tools/rows_bench.py)
+static bool rows_use_mma(int H) {
+  static const bool ffma = [] { const char* e = getenv("TGR_ROWS_FFMA"); return e && e[0] == '1'; }();
+  return (H == 32 || H == 64) && !ffma;
+}
 
 template <int H, int MODE>
 static int launch_rows(const FactParams& p, const uint32_t* uniq, const int32_t* n_unique_dev, float* PG, float* dw_part,
@@ -644,6 +1063,29 @@ static int launch_rows(const FactParams& p, const uint32_t* uniq, const int32_t*
   const size_t smem = fact_smem(H, MODE == 1);
   { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_rows_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
   TGR_K(fact_rows_kernel<H, MODE>)<<<MODE ? kRowsGridBwd : kRowsGridFwd, RowsCfg<H>::NT, smem, st>>>(p, uniq, n_unique_dev, PG, dw_part);
+  return check_launch(MODE ? "fact_unique_backward" : "fact_project_rows");
+}
+
+// TGR_ROWS_TC=0 keeps the forward projection on mma.sync (A/B timing)
+static bool rows_use_tc(int H) {
+  static const bool off = [] { const char* e = getenv("TGR_ROWS_TC"); return e && e[0] == '0'; }();
+  return rows_use_mma(H) && !off;
+}
+
+template <int H>
+static int launch_rows_tc(const FactParams& p, const uint32_t* uniq, const int32_t* n_unique_dev, float* P, cudaStream_t st) {
+  const size_t smem = TcRowsCfg<H>::SMEM;
+  { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_rows_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
+  TGR_K(fact_rows_tc_kernel<H>)<<<kTcGridFwd, TcRowsCfg<H>::NT, smem, st>>>(p, uniq, n_unique_dev, P);
+  return check_launch("fact_project_rows");
+}
+
+template <int H, int MODE>
+static int launch_rows_mma(const FactParams& p, const uint32_t* uniq, const int32_t* n_unique_dev, float* PG, float* dw_part,
+                           cudaStream_t st) {
+  const size_t smem = mma_smem(H, MODE == 1);
+  { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_rows_mma_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
+  TGR_K(fact_rows_mma_kernel<H, MODE>)<<<MODE ? kMmaGridBwd : kMmaGridFwd, MmaRowsCfg<H>::NT, smem, st>>>(p, uniq, n_unique_dev, PG, dw_part);
   return check_launch(MODE ? "fact_unique_backward" : "fact_project_rows");
 }
 
@@ -660,6 +1102,14 @@ extern "C" int tgr_fact_project_rows(const tgr_table_t* tables, int n_tables, in
   TGR_REQUIRE(uniq && n_unique_dev && P, "null argument");
   if (max_unique <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (rows_use_tc(H)) {
+    if (H == 32) return launch_rows_tc<32>(p, uniq, n_unique_dev, P, st);
+    return launch_rows_tc<64>(p, uniq, n_unique_dev, P, st);
+  }
+  if (rows_use_mma(H)) {
+    if (H == 32) return launch_rows_mma<32, 0>(p, uniq, n_unique_dev, P, nullptr, st);
+    return launch_rows_mma<64, 0>(p, uniq, n_unique_dev, P, nullptr, st);
+  }
   if (H == 32) return launch_rows<32, 0>(p, uniq, n_unique_dev, P, nullptr, st);
   if (H == 64) return launch_rows<64, 0>(p, uniq, n_unique_dev, P, nullptr, st);
   return launch_rows<128, 0>(p, uniq, n_unique_dev, P, nullptr, st);
@@ -682,15 +1132,19 @@ extern "C" int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables,
   cudaStream_t st = (cudaStream_t)stream;
   float* part = (float*)workspace;
   int rc;
-  if (H == 32) rc = launch_rows<32, 1>(p, uniq, n_unique_dev, G, part, st);
+  const bool mma = rows_use_mma(H);
+  if (mma) rc = H == 32 ? launch_rows_mma<32, 1>(p, uniq, n_unique_dev, G, part, st) : launch_rows_mma<64, 1>(p, uniq, n_unique_dev, G, part, st);
+  else if (H == 32) rc = launch_rows<32, 1>(p, uniq, n_unique_dev, G, part, st);
   else if (H == 64) rc = launch_rows<64, 1>(p, uniq, n_unique_dev, G, part, st);
   else rc = launch_rows<128, 1>(p, uniq, n_unique_dev, G, part, st);
   if (rc) return rc;
   if (dW_item == nullptr && dW_user == nullptr) return 0;
   const dim3 grid(n_tables, H * H / 64);
-  if (H == 32) TGR_K(fact_dw_reduce_kernel<32>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
-  else if (H == 64) TGR_K(fact_dw_reduce_kernel<64>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
-  else TGR_K(fact_dw_reduce_kernel<128>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
+  if (mma && H == 32) TGR_K(fact_dw_reduce_kernel<32, 128, 1>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kMmaGridBwd, dW_item, dW_user);
+  else if (mma) TGR_K(fact_dw_reduce_kernel<64, 128, 1>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kMmaGridBwd, dW_item, dW_user);
+  else if (H == 32) TGR_K(fact_dw_reduce_kernel<32, RowsCfg<32>::RT, RowsCfg<32>::RG>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
+  else if (H == 64) TGR_K(fact_dw_reduce_kernel<64, RowsCfg<64>::RT, RowsCfg<64>::RG>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
+  else TGR_K(fact_dw_reduce_kernel<128, RowsCfg<128>::RT, RowsCfg<128>::RG>)<<<grid, kFT, 0, st>>>(p, uniq, n_unique_dev, part, kRowsGridBwd, dW_item, dW_user);
   return check_launch("fact_dw_reduce");
 }
 

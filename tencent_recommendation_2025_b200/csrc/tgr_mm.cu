@@ -4,11 +4,15 @@
 //   forward : out[t, 0:H] = x[t, :] . W^T + b            W is nn.Linear.weight [H, mm_dim]
 //   backward: dW[h, k] (+)= sum_t dY[t, h] x[t, k] ;  db[h] (+)= sum_t dY[t, h]      (x is frozen data: no dX)
 //
-// This file is the fp32 CUDA-core path: it meets the 1e-5 fp32 bar (single-pass TF32 would not,
-// SURVEY.md §7 H5). Arithmetic intensity is 2H/4 = 32 flop/B on x, so for mm_dim = 32 ('81', the
-// benchmark config) the kernel is HBM/L2-bound on the x read + concat write, not on FFMA issue.
-// The bf16 tensor-core (tcgen05) variant for the 1024..4096-wide features lives in tgr_mm_tc.cu.
+// fp32 path: the forward runs on the tensor cores with error-compensated TF32 (3xTF32 mma.sync, tgr_mma.cuh — single-pass
+// TF32 would miss the 1e-5 fp32 bar); the first version's fp32 FFMA kernel is kept for other H and as
+// the A/B reference (TGR_MM_FFMA=1). Arithmetic intensity is 2H/4 = 32 flop/B on x, so for mm_dim = 32 ('81', the
+// benchmark config) the kernel is HBM/L2-bound on the x read + output write. The bf16 tcgen05 + TMA kernel for the
+// 1024..4096-wide features lives in tgr_mm_tc.cu.
+#include <stdlib.h>
+
 #include "tgr_common.cuh"
+#include "tgr_mma.cuh"
 
 namespace tgr {
 
@@ -101,6 +105,91 @@ __global__ void __launch_bounds__(kMmThreads) mm_proj_fwd_kernel(const void* __r
           st_stream_u2(reinterpret_cast<uint2*>(row) + (n >> 2), pack_bf16x4(v));
         else
           st_stream(reinterpret_cast<float4*>(row) + (n >> 2), v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward on the tensor cores: 128 tokens x H outputs per CTA (4 warps x 32 tokens), K swept in chunks of 32;
+// x fp32 (split hi/lo after the shared-memory load) or bf16 (exact in tf32: lo = 0), W split once per chunk
+// ------------------------------------------------------------------------------------------------
+template <int H, bool XBF16, bool OBF16>
+__global__ void __launch_bounds__(128) mm_proj_fwd_mma_kernel(const void* __restrict__ x, int64_t T, int K,
+                                                              const float* __restrict__ W,
+                                                              const float* __restrict__ bias,
+                                                              char* __restrict__ out, int64_t out_ld_bytes) {
+  constexpr int BM = 128, BK = 32, LD = BK + 4, NTILES = H / 8, NT = 128;
+  __shared__ __align__(16) float Xs[BM * LD];
+  __shared__ __align__(16) uint32_t Whi[H * LD];
+  __shared__ __align__(16) uint32_t Wlo[H * LD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const int64_t t0 = (int64_t)blockIdx.x * BM;
+  float acc[2][NTILES][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NTILES; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int i = tid; i < BM * (BK / 4); i += NT) {
+      const int r = i / (BK / 4), c4 = i % (BK / 4);
+      const int64_t t = t0 + r;
+      const int k = k0 + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < T && k < K) v = load_x4<XBF16>(x, (size_t)t * K + k);   // K % 4 == 0
+      *reinterpret_cast<float4*>(Xs + r * LD + c4 * 4) = v;
+    }
+    for (int i = tid; i < H * BK; i += NT) {
+      const int n = i / BK, k = i % BK;
+      uint32_t hi = 0u, lo = 0u;
+      if (k0 + k < K) split_tf32(__ldg(W + (size_t)n * K + k0 + k), hi, lo);
+      Whi[n * LD + k] = hi;
+      Wlo[n * LD + k] = lo;
+    }
+    __syncthreads();
+    const int m0 = warp * 32;
+#pragma unroll
+    for (int ks = 0; ks < BK / 8; ++ks) {
+      uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* xr = Xs + (m0 + 16 * mt + g) * LD + 8 * ks + t4;
+        split_tf32(xr[0], ahi[mt][0], alo[mt][0]);
+        split_tf32(xr[8 * LD], ahi[mt][1], alo[mt][1]);
+        split_tf32(xr[4], ahi[mt][2], alo[mt][2]);
+        split_tf32(xr[8 * LD + 4], ahi[mt][3], alo[mt][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NTILES; ++nt) {
+        const int wi = (8 * nt + g) * LD + 8 * ks + t4;
+        const uint32_t bhi[2] = {Whi[wi], Whi[wi + 4]};
+        const uint32_t blo[2] = {Wlo[wi], Wlo[wi + 4]};
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if constexpr (XBF16) { mma_tf32(acc[mt][nt], ahi[mt], blo); mma_tf32(acc[mt][nt], ahi[mt], bhi); }
+          else mma_3xtf32(acc[mt][nt], ahi[mt], alo[mt], bhi, blo);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int m0 = warp * 32;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int64_t ra = t0 + m0 + 16 * mt + g, rb = ra + 8;
+#pragma unroll
+    for (int nt = 0; nt < NTILES; ++nt) {
+      const int n = 8 * nt + 2 * t4;
+      const float b0 = bias ? __ldg(bias + n) : 0.f, b1 = bias ? __ldg(bias + n + 1) : 0.f;
+      if (ra < T) {
+        char* row = out + (size_t)ra * out_ld_bytes;
+        if constexpr (OBF16) reinterpret_cast<__nv_bfloat162*>(row)[n >> 1] = __floats2bfloat162_rn(acc[mt][nt][0] + b0, acc[mt][nt][1] + b1);
+        else reinterpret_cast<float2*>(row)[n >> 1] = make_float2(acc[mt][nt][0] + b0, acc[mt][nt][1] + b1);
+      }
+      if (rb < T) {
+        char* row = out + (size_t)rb * out_ld_bytes;
+        if constexpr (OBF16) reinterpret_cast<__nv_bfloat162*>(row)[n >> 1] = __floats2bfloat162_rn(acc[mt][nt][2] + b0, acc[mt][nt][3] + b1);
+        else reinterpret_cast<float2*>(row)[n >> 1] = make_float2(acc[mt][nt][2] + b0, acc[mt][nt][3] + b1);
       }
     }
   }
@@ -244,6 +333,21 @@ extern "C" int tgr_mm_proj_fwd(const void* x, int x_dtype, int64_t T, int mm_dim
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ldb = out_ld * (out_dtype == TGR_DTYPE_BF16 ? 2 : 4);
   const bool xb = x_dtype == TGR_DTYPE_BF16, ob = out_dtype == TGR_DTYPE_BF16;
+  static const bool ffma = [] { const char* e = getenv("TGR_MM_FFMA"); return e && e[0] == '1'; }();
+  if (!ffma && (H == 32 || H == 64)) {
+    const unsigned grid = (unsigned)((T + 127) / 128);
+#define TGR_LAUNCH_MMA(HH)                                                                                                     \
+    do {                                                                                                                       \
+      if (xb && ob) TGR_K(mm_proj_fwd_mma_kernel<HH, true, true>)<<<grid, 128, 0, st>>>(x, T, mm_dim, W, bias, (char*)out, ldb);   \
+      else if (xb) TGR_K(mm_proj_fwd_mma_kernel<HH, true, false>)<<<grid, 128, 0, st>>>(x, T, mm_dim, W, bias, (char*)out, ldb);   \
+      else if (ob) TGR_K(mm_proj_fwd_mma_kernel<HH, false, true>)<<<grid, 128, 0, st>>>(x, T, mm_dim, W, bias, (char*)out, ldb);   \
+      else TGR_K(mm_proj_fwd_mma_kernel<HH, false, false>)<<<grid, 128, 0, st>>>(x, T, mm_dim, W, bias, (char*)out, ldb);          \
+    } while (0)
+    if (H == 32) TGR_LAUNCH_MMA(32);
+    else TGR_LAUNCH_MMA(64);
+#undef TGR_LAUNCH_MMA
+    return check_launch("mm_proj_fwd");
+  }
 #define TGR_LAUNCH_FWD(BM, BN, XB, OB)                                                                  \
   TGR_K(mm_proj_fwd_kernel<BM, BN, XB, OB>)<<<dim3((unsigned)((T + BM - 1) / BM), (H + BN - 1) / BN), kMmThreads, 0, st>>>( \
       x, T, mm_dim, W, bias, H, (char*)out, ldb)

@@ -196,14 +196,19 @@ __global__ void __launch_bounds__(kRedThreads, 4) reduce_tiles_kernel(const __gr
   }
 }
 
-// cross-CTA fix-up: one group per CTA tile; the tile that holds the START of a run leaving it owns the run
+// cross-CTA fix-up: one CTA per tile; the tile that holds the START of a run leaving it owns the run. The run's extent
+// is found by galloping + bisection over the tile borders (the keys are sorted, so "this tile is entirely key K" is
+// monotone), and the head partials of the tiles it covers are summed by the CTA's G groups in a fixed strided order
+// (group q takes tiles first + q, first + q + G, ... ascending; the group sums are then added in group order). The
+// first version walked the tiles one by one from a single group: a 56 k-entry run of a 100-row table cost 55 dependent
+// round trips (38 us, 6 % active warps — profiles/README.md r1e).
 template <int LANES, int NJ>
 __global__ void __launch_bounds__(kRedThreads) reduce_fixup_kernel(const __grid_constant__ RedParams p, int n_cta) {
   constexpr int G = kRedThreads / LANES;
   constexpr int64_t TILE = (int64_t)G * kC;
+  __shared__ float4 s_part[G][NJ * LANES];
   const int lane = threadIdx.x % LANES, grp = threadIdx.x / LANES;
-  const int c0 = blockIdx.x * G + grp;
-  if (c0 >= n_cta) return;
+  const int c0 = blockIdx.x;
   const int64_t n = p.n;
   const int H4 = p.H4;
   const int64_t a = (int64_t)c0 * TILE, b = min(n, a + TILE);
@@ -211,15 +216,36 @@ __global__ void __launch_bounds__(kRedThreads) reduce_fixup_kernel(const __grid_
   const uint32_t K = __ldg(p.keys + b - 1);
   if (__ldg(p.keys + b) != K) return;                                        // nothing leaves this tile
   if (a > 0 && __ldg(p.keys + a) == K && __ldg(p.keys + a - 1) == K) return;  // "through" tile: an earlier tile owns it
+  // through(t): tile t lies inside the run and the run continues past it. First tile that is not: the run's last one.
+  auto through = [&](int t) {
+    const int64_t te = min(n, (int64_t)(t + 1) * TILE);
+    return te < n && __ldg(p.keys + te - 1) == K && __ldg(p.keys + te) == K;
+  };
+  int lo = c0 + 1, hi = c0 + 1, step = 1;
+  while (through(hi)) {              // through(n_cta - 1) is false: terminates
+    lo = hi + 1;
+    hi = min(hi + step, n_cta - 1);
+    step <<= 1;
+  }
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (through(mid)) lo = mid + 1; else hi = mid;
+  }
+  const int c1 = lo;                 // heads of tiles c0 + 1 .. c1 belong to the run
   float4 acc[NJ];
-  const float4* src = reinterpret_cast<const float4*>(p.cta_tail + (size_t)c0 * (size_t)(H4 * 4));
-  TGR_FOR_COLS(j, c) acc[j] = src[c];
-  for (int t = c0 + 1; t < n_cta; ++t) {
+  TGR_FOR_COLS(j, c) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = c0 + 1 + grp; t <= c1; t += G) {
     const float4* hs = reinterpret_cast<const float4*>(p.cta_head + (size_t)t * (size_t)(H4 * 4));
     TGR_FOR_COLS(j, c) acc[j] = f4_add(acc[j], hs[c]);
-    const int64_t te = min(n, (int64_t)(t + 1) * TILE);
-    const bool through = (__ldg(p.keys + te - 1) == K) && te < n && (__ldg(p.keys + te) == K);
-    if (!through) break;
+  }
+  TGR_FOR_COLS(j, c) s_part[grp][j * LANES + lane] = acc[j];
+  __syncthreads();
+  if (grp != 0) return;
+  const float4* src = reinterpret_cast<const float4*>(p.cta_tail + (size_t)c0 * (size_t)(H4 * 4));
+  TGR_FOR_COLS(j, c) acc[j] = src[c];
+  const int used = min(G, c1 - c0);
+  for (int q = 0; q < used; ++q) {
+    TGR_FOR_COLS(j, c) acc[j] = f4_add(acc[j], s_part[q][j * LANES + lane]);
   }
   float4* dst;
   if (p.mode == 0) {
@@ -303,7 +329,7 @@ static int launch_reduce(RedParams& p, const RowParams* rp, bool bf16, int n_cta
   }
   if (int rc = check_launch("reduce_tiles")) return rc;
   if (n_cta > 1) {
-    TGR_K(reduce_fixup_kernel<LANES, NJ>)<<<(n_cta + G - 1) / G, kRedThreads, 0, st>>>(p, n_cta);
+    TGR_K(reduce_fixup_kernel<LANES, NJ>)<<<n_cta - 1, kRedThreads, 0, st>>>(p, n_cta);
     if (int rc = check_launch("reduce_fixup")) return rc;
   }
   if (p.mode == 1) {
