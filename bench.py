@@ -175,7 +175,7 @@ def unique_counts(lay, calls):
     return per, int(np.unique(np.concatenate(allk)).size)
 
 
-def kernel_bytes_step(lay, st, pbs, per_u, step_u, path):
+def kernel_bytes_step(lay, st, pbs, per_u, step_u, path, x_esz=4):
     """Compulsory (algorithmic) bytes of OUR kernels for one step, by C-ABI entry name. Every operand is counted once
     per launch that must touch it (a row read by many lookups counts once: cache hits cannot inflate the figure)."""
     H = lay.H
@@ -202,12 +202,20 @@ def kernel_bytes_step(lay, st, pbs, per_u, step_u, path):
     out["dedup"] = 4 * n + 4 * n + 4 * U
     out["remap_scatter"] = 8 * n + 4 * n
     out["fact_project_rows"] = 2 * U * H * 4
-    out["mm_proj_fwd"] = sum(pc.T * (X * 4 + H * 4 * len(lay.item_emb_feat)) for pc in st.calls)
+    # mm features: wide bf16 ones run on the tcgen05 kernels (forward x read + [T, H] write; backward x + bf16 dz read)
+    tc_dims = [d for d in lay.item_emb_feat.values() if x_esz == 2 and d >= 128 and d % 64 == 0]
+    sm_dims = [d for d in lay.item_emb_feat.values() if d not in tc_dims]
+    Tsum = sum(pc.T for pc in st.calls)
+    out["mm_proj_fwd"] = Tsum * sum(d * x_esz + H * 4 for d in sm_dims)
+    if tc_dims:
+        out["mm_proj_fwd_tc"] = Tsum * sum(d * 2 + H * 4 for d in tc_dims)
+        out["mm_proj_bwd_tc"] = Tsum * sum(d * 2 + H * 2 for d in tc_dims)
+        out["cast_bf16"] = Tsum * H * 6
     fw = rm = red = 0
     for pc, Uc in zip(st.calls, per_u):
         sides = 2 if pc.include_user else 1
         fw += 4 * pc.ids.size + 4 * pc.arr_val.size + Uc * H * 4 + pc.T * H * 4 * (1 + len(lay.item_emb_feat)) + pc.T * H // 4
-        rm += pc.T * H * 4 * (1 + sides) + pc.T * H // 4 + pc.T * X * 4
+        rm += pc.T * H * 4 * (1 + sides) + pc.T * H // 4 + pc.T * 32 * x_esz * (1 if 32 in lay.item_emb_feat.values() else 0)
         red += pc.T * H * 4 * sides
     out["fact_forward"] = fw
     out["fact_relu_mask"] = rm
@@ -237,6 +245,9 @@ def run_gpu(args):
     torch.backends.cuda.matmul.allow_tf32 = args.dnn_matmul == "tf32"
     hbm_peak, peak_src = load_peaks()
     cfg = get_config(args.config, args.batch)
+    # frozen mm features: fp32 as the reference holds them, or bf16 storage (config 3: the wide features go through the
+    # bf16 tcgen05 projection)
+    mm_dtype = torch.bfloat16 if (args.mm_dtype or ("bf16" if args.config == "c3" else "f32")) == "bf16" else torch.float32
     worldgen = synth.SynthWorld(cfg, 0)
     lay = worldgen.layout
     m = init_module(cfg, dev, "fused", args.path)
@@ -246,7 +257,7 @@ def run_gpu(args):
     steps_np = [worldgen.make_step(s) for s in range(n_batches)]
     dev_steps = []
     for st in steps_np:
-        pbs = [to_device(lay, pc, dev) for pc in st.calls]
+        pbs = [to_device(lay, pc, dev, mm_dtype=mm_dtype) for pc in st.calls]
         ups = [torch.from_numpy(r).to(dev) for r in st.upstream]
         dev_steps.append((pbs, ups))
     torch.cuda.synchronize()
@@ -301,8 +312,9 @@ def run_gpu(args):
     stats = {}
     for k in sorted(set(used)):
         pu, su = unique_counts(lay, steps_np[k].calls)
-        f, b = algorithmic_bytes(lay, steps_np[k].calls, pu, su)
-        stats[k] = (pu, su, f, b, kernel_bytes_step(lay, steps_np[k], dev_steps[k][0], pu, su, args.path))
+        f, b = algorithmic_bytes(lay, steps_np[k].calls, pu, su, x_esz=2 if mm_dtype == torch.bfloat16 else 4)
+        stats[k] = (pu, su, f, b, kernel_bytes_step(lay, steps_np[k], dev_steps[k][0], pu, su, args.path,
+                                                    2 if mm_dtype == torch.bfloat16 else 4))
     kbytes = {}
     nominal = 0
     for k in used:
@@ -346,7 +358,7 @@ def run_gpu(args):
                 "reference_dataflow_frac_of_hbm_peak": round((alg_f + alg_b) / (ms * 1e-3) / 1e9 / hbm_peak, 4)}
 
     # ---- end to end from host buffers (e2e): pinned host batches -> copy stream -> step -> loss read back ----------
-    host_steps = [[stage_pinned(lay, pc) for pc in st.calls] for st in steps_np]   # as a pin_memory DataLoader would
+    host_steps = [[stage_pinned(lay, pc, mm_dtype) for pc in st.calls] for st in steps_np]   # as a pin_memory DataLoader would
     e2e_steps = max(3, min(args.steps, 20))
     e2e_warm = n_batches + 1
     feeder = HostPrefetcher(dev)
@@ -420,7 +432,8 @@ def run_gpu(args):
     conf = workload_config(args, cfg)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": conf,
+            "dtype": "f32" if mm_dtype == torch.float32 else "f32 tables / bf16 mm features (tcgen05 projection)",
+            "data": "synthetic", "config": conf,
             "impl_detail": {"row_update": "fused sparse AdamW (lazy rows)", "path": args.path,
                             "dnn": ("itemdnn/userdnn folded into the deduplicated rows (factored kernels; 3xTF32 tensor-core "
                                     "row GEMMs, fp32 accumulate)" if args.path == "factored"
@@ -645,6 +658,8 @@ def main():
     ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches to cycle")
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mm-dtype", default=None, choices=["f32", "bf16"],
+                    help="storage dtype of the frozen mm features (default: bf16 for c3, f32 otherwise)")
     ap.add_argument("--no-prefetch", action="store_true", help="sharded path: per-call exchange instead of step prefetch")
     ap.add_argument("--no-lookahead", action="store_true", help="sharded path: no one-step-ahead key processing")
     ap.add_argument("--no-p2p", action="store_true", help="sharded factored path: fetch rows with the NCCL all-to-all "

@@ -17,6 +17,100 @@ from tencent_recommendation_2025_b200 import synth
 from tencent_recommendation_2025_b200.packed import to_device
 
 
+def live_parity_check(args, rank: int, world: int, dev) -> dict:
+    """W-rank result == emulated-W result, checked on the wires the benchmark times (the NCCL +
+    symmetric-memory path had no value check). Every rank builds the SAME small problem (all ranks' batches, identical
+    parameters), runs the W-rank step twice — (a) with W emulated ranks inside its own process (`run_emulated`: the
+    configuration the single-GPU tests pin to the oracle and to the unsharded step, tests/test_gpu_sharded_factored.py) and
+    (b) as one rank of the live process group (NCCL collectives, peer-memory row reads, gradient windows) — and compares
+    its forward outputs, its dense-parameter gradients, its updated table shard and AdamW state BIT FOR BIT. The
+    arithmetic is deterministic (fixed reduction orders), so anything but equality is a transport / ordering bug."""
+    from tencent_recommendation_2025_b200.module import BaselineEmbedding
+    from tencent_recommendation_2025_b200.sharded import (FactShardOps, ShardedBaselineEmbedding, ShardedRank, run_emulated,
+                                                            shard_of_tables)
+    W = world
+    stats = {k: 50 for k in ["103", "104", "105", "109", "100", "117", "111", "118", "101", "102", "119", "120", "114", "112",
+                             "121", "115", "122", "116", "106", "107", "108", "110"]}
+    cfg = synth.SynthConfig(B=16, L=33, H=64, item_num=5000, user_num=300, alpha=1.2, mm_ids=("81",), min_len=5,
+                            feat_statistics=stats)
+    gen = synth.SynthWorld(cfg, 3)
+    steps = [gen.make_step(r) for r in range(W)]
+    margs = types.SimpleNamespace(device=str(dev), hidden_units=cfg.H)
+    torch.manual_seed(3)
+    full = BaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), margs, "fused", path="factored").to(dev)
+    g = torch.Generator(device=dev).manual_seed(17)
+    with torch.no_grad():
+        for p in full.parameters():
+            p.normal_(0.0, 0.1, generator=g)
+        for p in full.engine.tables:
+            p[0].zero_()
+    lay = full.layout
+    tables = [p.data for p in full.engine.tables]
+    hyper = dict(lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
+    pbs_all = [[to_device(lay, pc, dev) for pc in st.calls] for st in steps]
+    ups_all = [[torch.from_numpy(u).to(dev) for u in st.upstream] for st in steps]
+    # ---- (a) emulated ranks in this process ----
+    ranks = []
+    for r in range(W):
+        ops = FactShardOps(lay, shard_of_tables(tables, r, W), dict(full.emb_transform.items()),
+                           {"item": full.itemdnn, "user": full.userdnn}, W)
+        ranks.append(ShardedRank(lay, ops, r, W))
+    if not args.no_p2p:
+        wins = [torch.zeros((1 << 14, cfg.H), device=dev) for _ in ranks]
+        for rk, w_ in zip(ranks, wins):
+            rk.ops.peers = [q.ops.local.data_ptr() for q in ranks]
+            rk.ops.grad_win = w_
+            rk.ops.grad_peers = [x.data_ptr() for x in wins]
+    run_emulated([ranks[r].prefetch_gen(pbs_all[r]) for r in range(W)])
+    exp_out = []
+    for c in range(3):
+        exp_out.append(run_emulated([ranks[r].forward_gen(pbs_all[r][c]) for r in range(W)])[rank].clone())
+    for r in range(W):
+        grp = ranks[r].pf["pf"]["group"]
+        grp.n_fwd = 3
+        for c in (2, 1, 0):
+            ranks[r].ops.feng.fact_backward(grp, pbs_all[r][c], ups_all[r][c])
+            ranks[r].queue(pbs_all[r][c], None, None)
+        if r == rank:
+            exp_acc = {k: v.clone() for k, v in grp.acc.items() if isinstance(v, torch.Tensor)}
+    run_emulated([ranks[r].step_gen(dict(hyper)) for r in range(W)])
+    exp_shard, exp_m = ranks[rank].ops.local.clone(), ranks[rank].ops.exp_avg.clone()
+    # ---- (b) this process as one rank of the live group ----
+    m = ShardedBaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), margs, rank, W,
+                                 path="factored", p2p=not args.no_p2p, grad_window_rows=1 << 14)
+    m.load_full_tables(tables)
+    with torch.no_grad():
+        for k in lay.item_emb_feat:
+            m.emb_transform[k].weight.copy_(full.emb_transform[k].weight)
+            m.emb_transform[k].bias.copy_(full.emb_transform[k].bias)
+        m.itemdnn.weight.copy_(full.itemdnn.weight); m.itemdnn.bias.copy_(full.itemdnn.bias)
+        m.userdnn.weight.copy_(full.userdnn.weight); m.userdnn.bias.copy_(full.userdnn.bias)
+    torch.cuda.synchronize()
+    dist.barrier()
+    pbs = pbs_all[rank]
+    m.prefetch(pbs)
+    outs = [m.feat2emb_packed(pb) for pb in pbs]
+    torch.autograd.backward(outs, ups_all[rank])
+    m.fused_step(**hyper)
+    torch.cuda.synchronize()
+    checks = {
+        "forward": all(torch.equal(o.reshape(e.shape), e) for o, e in zip(outs, exp_out)),
+        "dense_grads": (torch.equal(m.itemdnn.weight.grad, exp_acc["dW_item"]) and torch.equal(m.userdnn.weight.grad, exp_acc["dW_user"])
+                        and torch.equal(m.emb_transform["81"].weight.grad, exp_acc["dWmm/81"])),
+        "updated_shard": torch.equal(m.local_table.data, exp_shard),
+        "adam_state": torch.equal(m.ops.exp_avg, exp_m),
+    }
+    flags = torch.tensor([1.0 if v else 0.0 for v in checks.values()], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    out = {k: bool(f) for k, f in zip(checks, flags.tolist())}
+    out["parity_ok"] = all(out.values())
+    out["how"] = (f"W={W} live ranks (NCCL + {'peer memory' if getattr(m.ops, 'peers', None) is not None else 'all-to-all'}) vs "
+                  f"{W} emulated ranks in one process, bit for bit, min over ranks; B=16 x L=33 per rank, 5000-item tables")
+    del m, ranks, full
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_sharded(args, rank: int, world: int, local_rank: int):
     from tencent_recommendation_2025_b200.sharded import ShardedBaselineEmbedding
     dev = torch.device("cuda", local_rank)
@@ -25,6 +119,10 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = args.dnn_matmul == "tf32"
     hbm_peak, peak_src = bench.load_peaks()
+    parity = live_parity_check(args, rank, world, dev) if args.path == "factored" else None
+    if parity is not None and not parity["parity_ok"] and rank == 0:
+        import sys
+        print(f"WARNING: live sharded parity check failed: {parity}", file=sys.stderr)
     cfg = bench.get_config(args.config, args.batch)
     worldgen = synth.SynthWorld(cfg, 0)
     lay = worldgen.layout
@@ -227,7 +325,8 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
                         "entry": "prefetch + feat2emb_packed x3 + backward + all-reduce + fused_step per rank from pinned "
                                  "host buffers (copy stream two steps ahead), loss read back every step; wall clock, max over ranks",
                         "loss_finite": bool(np.all(np.isfinite(losses)))},
-                "gpu_launches": launches, "clocks": clk}
+                "gpu_launches": launches, "clocks": clk, "parity": parity,
+                "parity_ok": None if parity is None else parity["parity_ok"]}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()

@@ -139,6 +139,13 @@ int tgr_mm_proj_fwd(const void* x, int x_dtype, int64_t T, int mm_dim, const flo
 int tgr_mm_proj_fwd_tc_supported(int x_dtype, int mm_dim, int H);
 int tgr_mm_proj_fwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* w_bf16, const float* bias, int H, void* out,
                        int64_t out_ld, int out_dtype, void* stream);
+/* Backward of the wide bf16 projection on the tensor cores: dW[H, mm_dim] (+)= dz^T . x with dz_bf16 a bf16 copy of the
+ * fp32 dz [T, H] (tgr_cast_bf16). Split-K over tokens, both operands MN-major straight from TMA (csrc/tgr_mm_tc.cu), chunk
+ * partials reduced in fixed order (bitwise reproducible). Needs mm_dim % 64 == 0, mm_dim >= 128, H in {64, 128}. */
+int tgr_mm_proj_bwd_tc_supported(int x_dtype, int mm_dim, int H);
+size_t tgr_mm_proj_bwd_tc_workspace_bytes(int64_t T, int mm_dim, int H);
+int tgr_mm_proj_bwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* dz_bf16, int H, float* dW, int accumulate,
+                       void* workspace, size_t workspace_bytes, void* stream);
 /* dst_bf16[i] = bf16(src[i]) (round to nearest even), n elements; src 16-byte, dst 8-byte aligned. */
 int tgr_cast_bf16(const float* src, int64_t n, void* dst_bf16, void* stream);
 
@@ -372,6 +379,7 @@ typedef struct tgr_fact_group {
   float* mmz[TGR_MAX_CALLS][TGR_MAX_MM];
   float *fold_M[TGR_MAX_MM], *fold_c[TGR_MAX_MM], *mm_A[TGR_MAX_MM], *mm_s[TGR_MAX_MM];
   void* fold_Mb[TGR_MAX_MM];           /* bf16 copy of fold_M for the tcgen05 projection (wide bf16 mm features) */
+  void* dzb;                           /* bf16 copy of one call's dz_item for the tcgen05 mm backward, [max T, H] */
   void* ws;
   size_t ws_bytes;
   int32_t projected, n_backward;       /* progress */

@@ -83,7 +83,7 @@ class FactGroup(C.Structure):
                 ("dz_item", C.c_void_p * MAX_CALLS), ("dz_user", C.c_void_p * MAX_CALLS),
                 ("mmz", (C.c_void_p * MAX_MM) * MAX_CALLS),
                 ("fold_M", C.c_void_p * MAX_MM), ("fold_c", C.c_void_p * MAX_MM), ("mm_A", C.c_void_p * MAX_MM),
-                ("mm_s", C.c_void_p * MAX_MM), ("fold_Mb", C.c_void_p * MAX_MM),
+                ("mm_s", C.c_void_p * MAX_MM), ("fold_Mb", C.c_void_p * MAX_MM), ("dzb", C.c_void_p),
                 ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
                 ("projected", C.c_int32), ("n_backward", C.c_int32)]
 
@@ -118,6 +118,10 @@ SIGNATURES = {
     "tgr_mm_proj_fwd_tc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                      C.c_int, C.c_void_p]),
     "tgr_cast_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tgr_mm_proj_bwd_tc_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "tgr_mm_proj_bwd_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "tgr_mm_proj_bwd_tc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]),
     "tgr_mm_proj_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "tgr_mm_proj_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),

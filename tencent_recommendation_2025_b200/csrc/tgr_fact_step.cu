@@ -67,6 +67,9 @@ static size_t carve(tgr_fact_group_t* g, void* arena, int n_tables) {
   g->G = cv.take<float>(cap * H);
   size_t ws = 0;
   int64_t max_entries = 0;
+  size_t max_T = 0;
+  bool any_tc_bwd = false;
+  for (int f = 0; f < g->n_mm; ++f) any_tc_bwd = any_tc_bwd || tgr_mm_proj_bwd_tc_supported(g->mm_x_dtype, g->mm_dim[f], H);
   for (int c = 0; c < g->n_calls; ++c) {
     const tgr_call_t& cl = g->calls[c];
     const size_t T = (size_t)cl.T;
@@ -78,8 +81,15 @@ static size_t carve(tgr_fact_group_t* g, void* arena, int n_tables) {
     g->dz_user[c] = call_has_user(cl) ? cv.take<float>(T * H) : nullptr;
     for (int f = 0; f < g->n_mm; ++f) g->mmz[c][f] = cv.take<float>(T * H);
     ws = max(ws, tgr_fact_relu_mask_workspace_bytes((int64_t)T, H));
-    for (int f = 0; f < g->n_mm; ++f) ws = max(ws, tgr_mm_proj_bwd_workspace_bytes((int64_t)T, g->mm_dim[f], H));
+    for (int f = 0; f < g->n_mm; ++f) {
+      if (tgr_mm_proj_bwd_tc_supported(g->mm_x_dtype, g->mm_dim[f], H))
+        ws = max(ws, tgr_mm_proj_bwd_tc_workspace_bytes((int64_t)T, g->mm_dim[f], H));
+      else
+        ws = max(ws, tgr_mm_proj_bwd_workspace_bytes((int64_t)T, g->mm_dim[f], H));
+    }
+    max_T = max(max_T, T);
   }
+  g->dzb = any_tc_bwd ? (void*)cv.take<uint16_t>(max_T * H) : nullptr;
   for (int f = 0; f < g->n_mm; ++f) {
     g->fold_M[f] = cv.take<float>((size_t)H * g->mm_dim[f]);
     g->fold_c[f] = cv.take<float>(H);
@@ -202,8 +212,19 @@ extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, c
                                     user ? gr->db_user : nullptr, fused >= 0 ? g->mm_x[c][fused] : nullptr, g->mm_x_dtype,
                                     fused >= 0 ? 32 : 0, fused >= 0 ? g->mm_A[fused] : nullptr,
                                     fused >= 0 ? g->mm_s[fused] : nullptr, g->ws, g->ws_bytes, stream)) return rc;
+    bool dz_cast = false;
     for (int f = 0; f < g->n_mm; ++f) {
       if (gr->dW_mm[f] == nullptr || f == fused) continue;
+      if (tgr_mm_proj_bwd_tc_supported(g->mm_x_dtype, prm->mm[f].mm_dim, H)) {
+        // wide bf16 feature: A += dz^T x on the tensor cores (s = colsum(dz) is read off db_item at the finish)
+        if (!dz_cast) {
+          if (int rc = tgr_cast_bf16(g->dz_item[c], (int64_t)cl.T * H, g->dzb, stream)) return rc;
+          dz_cast = true;
+        }
+        if (int rc = tgr_mm_proj_bwd_tc(g->mm_x[c][f], cl.T, prm->mm[f].mm_dim, g->dzb, H, g->mm_A[f], 1, g->ws, g->ws_bytes,
+                                        stream)) return rc;
+        continue;
+      }
       if (int rc = tgr_mm_proj_bwd(g->mm_x[c][f], g->mm_x_dtype, cl.T, prm->mm[f].mm_dim, g->dz_item[c], H, TGR_DTYPE_F32,
                                    H, g->mm_A[f], g->mm_s[f], 1, g->ws, g->ws_bytes, stream)) return rc;
     }
@@ -215,7 +236,12 @@ extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, c
     const tgr_mm_feat_t& m = prm->mm[f];
     if (gr->dW_mm[f] == nullptr) continue;
     TGR_REQUIRE(gr->dW_item != nullptr, "dW_item is NULL");
-    if (int rc = tgr_fact_mm_chain_bwd(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, g->mm_A[f], g->mm_s[f], H,
+    // tensor-core features: s = sum over the group's calls of colsum(dz_item) is exactly what the (zero-initialised)
+    // db_item accumulator holds by now
+    const bool tcb = tgr_mm_proj_bwd_tc_supported(g->mm_x_dtype, m.mm_dim, H) &&
+                     !(m.mm_dim == 32);
+    TGR_REQUIRE(!tcb || gr->db_item != nullptr, "the tensor-core mm backward reads colsum(dz) from db_item: it must not be NULL");
+    if (int rc = tgr_fact_mm_chain_bwd(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, g->mm_A[f], tcb ? gr->db_item : g->mm_s[f], H,
                                        m.mm_dim, gr->dW_mm[f], gr->db_mm[f], gr->dW_item + m.col, prm->dnn.item_ld,
                                        stream)) return rc;
   }

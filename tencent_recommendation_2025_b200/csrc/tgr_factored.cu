@@ -467,13 +467,18 @@ struct TcRowsCfg {
 };
 constexpr int kTcGridFwd = 2 * kNumSMs;
 
+// Work item of the tc kernel: rows [seg_a, seg_b) of one tile, all of one table.
+struct TcItem { int tile, seg_a, seg_b, t; };
+
 template <int H>
 __global__ void __launch_bounds__(TcRowsCfg<H>::NT) fact_rows_tc_kernel(const __grid_constant__ FactParams p,
                                                                         const uint32_t* __restrict__ uniq,
                                                                         const int32_t* __restrict__ n_unique_dev,
-                                                                        float* __restrict__ P) {
+                                                                        float* __restrict__ P, int dbg) {
   using Cfg = TcRowsCfg<H>;
   constexpr int kRT = Cfg::RT, NT = Cfg::NT, H4 = H / 4;
+  constexpr int KT = 8;                                  // tiles whose keys are staged at once
+  constexpr int UNITS = (kRT / 8) * (H4 / 4), UPW = UNITS / 4;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* Ahi = base;
@@ -482,8 +487,8 @@ __global__ void __launch_bounds__(TcRowsCfg<H>::NT) fact_rows_tc_kernel(const __
   uint8_t* Blo = Bhi + Cfg::B_BYTES;
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t s_tmem;
-  __shared__ uint32_t s_key[kRT];
-  __shared__ int32_t s_perm[kRT];
+  __shared__ uint32_t s_key[KT * kRT];
+  __shared__ int32_t s_perm[KT * kRT];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) tc::mbar_init(&mbar, 1);
   if (warp == 0) tc::tmem_alloc<Cfg::TMEM_COLS>(&s_tmem);
@@ -498,41 +503,86 @@ __global__ void __launch_bounds__(TcRowsCfg<H>::NT) fact_rows_tc_kernel(const __
   const int tpc = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tile_a = blockIdx.x * tpc, tile_b = min(n_tiles, tile_a + tpc);
   int cur_t = -1;
-  for (int tile = tile_a; tile < tile_b; ++tile) {
-    const int r0 = tile * kRT;
-    const int nr = min(kRT, U - r0);
-    __syncthreads();
-    for (int i = tid; i < kRT; i += NT) {
-      s_key[i] = i < nr ? __ldg(uniq + r0 + i) : 0xFFFFFFFFu;
-      if (p.fetched != nullptr) s_perm[i] = i >= nr ? 0 : (p.fetched_perm ? __ldg(p.fetched_perm + r0 + i) : r0 + i);
+
+  for (int win_a = tile_a; win_a < tile_b; win_a += KT) {
+    const int win_b = min(tile_b, win_a + KT);
+    __syncthreads();                                     // previous window's readers of s_key are done
+    for (int i = tid; i < (win_b - win_a) * kRT; i += NT) {
+      const int u = win_a * kRT + i;
+      s_key[i] = u < U ? __ldg(uniq + u) : 0xFFFFFFFFu;
+      if (p.fetched != nullptr) s_perm[i] = u >= U ? 0 : (p.fetched_perm ? __ldg(p.fetched_perm + u) : u);
     }
     __syncthreads();
-    int seg_a = 0;
-    while (seg_a < nr) {
-      const int t = find_table(p.key_base, p.n_tables, s_key[seg_a]);
-      const uint32_t kend = p.key_base[t + 1];
-      int seg_b;
-      if (s_key[nr - 1] < kend) {
-        seg_b = nr;
-      } else {
+
+    // item after (tile, seg_b): the next run of same-table rows, or tile == win_b when the window is exhausted
+    auto item_at = [&](int tile, int seg_a) {
+      TcItem it;
+      it.tile = tile; it.seg_a = seg_a; it.seg_b = 0; it.t = 0;
+      if (tile >= win_b) return it;
+      const uint32_t* k = s_key + (tile - win_a) * kRT;
+      const int nr = min(kRT, U - tile * kRT);
+      it.t = find_table(p.key_base, p.n_tables, k[seg_a]);
+      const uint32_t kend = p.key_base[it.t + 1];
+      if (k[nr - 1] < kend) {
+        it.seg_b = nr;
+      } else {   // first row of the next table, by bisection (uniform across the CTA: shared-memory broadcast reads)
         int lo = seg_a + 1, hi = nr - 1;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] < kend) lo = mid + 1; else hi = mid; }
-        seg_b = lo;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < kend) lo = mid + 1; else hi = mid; }
+        it.seg_b = lo;
       }
-      const int ns = seg_b - seg_a;
-      // (the previous segment's MMAs have completed — every thread waited on the mbarrier — so the tiles are free)
-      if (t != cur_t) {
-        const float* W = p.dnn_w[p.side[t]];
-        const int64_t ld = p.dnn_ld[p.side[t]];
-        const int col = p.col[t];
-        // B[n = h][k]: core matrix (h / 8, k / 4). All of the thread's 128-bit loads are issued before the first use (a
-        // load -> split -> store loop exposed one L2 round trip per iteration: 12 us per table switch, profiles/README.md)
+      return it;
+    };
+    auto next_of = [&](const TcItem& it) {
+      const int nr = min(kRT, U - it.tile * kRT);
+      return it.seg_b < nr ? item_at(it.tile, it.seg_b) : item_at(it.tile + 1, 0);
+    };
+    // unit = (8-row group rg, block of 4 chunks): lane -> (row rg * 8 + lane % 8, chunk 4 * cq + lane / 8); every 128-bit
+    // load of the item is issued here, the data is consumed one pipeline stage later
+    float4 v[UPW];
+    auto issue_loads = [&](const TcItem& it) {
+      const int ns = it.seg_b - it.seg_a;
+      const uint32_t* k = s_key + (it.tile - win_a) * kRT + it.seg_a;
+      const int32_t* pm = s_perm + (it.tile - win_a) * kRT + it.seg_a;
+      const float* tab = p.w[it.t];
+      const uint32_t kb = p.key_base[it.t];
+#pragma unroll
+      for (int q = 0; q < UPW; ++q) {
+        const int unit = warp * UPW + q;
+        const int rg = unit / (H4 / 4), cq = unit % (H4 / 4);
+        const int r = rg * 8 + (lane & 7), c = cq * 4 + (lane >> 3);
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < ns && !(dbg & 1)) {
+          const float* rsrc;
+          if (p.n_peers > 0) {
+            const uint32_t key = k[r];
+            rsrc = p.peer[key % (uint32_t)p.n_peers] + (size_t)(key / (uint32_t)p.n_peers) * H;
+          } else if (p.fetched != nullptr) {
+            rsrc = p.fetched + (size_t)pm[r] * H;
+          } else {
+            rsrc = tab + (size_t)(k[r] - kb) * H;
+          }
+          v[q] = __ldg(reinterpret_cast<const float4*>(rsrc) + c);
+        }
+      }
+    };
+
+    TcItem cur = item_at(win_a, 0);
+    issue_loads(cur);
+    while (cur.tile < win_b) {
+      const int ns = cur.seg_b - cur.seg_a;
+      const int row0 = cur.tile * kRT + cur.seg_a;       // first unique row of the item
+      // (the previous item's MMAs have completed — every thread waited on the mbarrier — so the tiles are free)
+      if (cur.t != cur_t) {
+        const float* W = p.dnn_w[p.side[cur.t]];
+        const int64_t ld = p.dnn_ld[p.side[cur.t]];
+        const int col = p.col[cur.t];
+        // B[n = h][k]: core matrix (h / 8, k / 4); all 128-bit loads in flight before the first use
         constexpr int WPT = H * H4 / NT;
         float4 wv[WPT];
 #pragma unroll
         for (int q = 0; q < WPT; ++q) {
           const int i = tid + q * NT, h = i / H4, c = i - h * H4;
-          wv[q] = __ldg(reinterpret_cast<const float4*>(W + (size_t)h * ld + col) + c);   // col % H == 0, ld % 4 == 0
+          wv[q] = __ldg(reinterpret_cast<const float4*>(W + (size_t)h * ld + col) + c);   // col % 4 == 0, ld % 4 == 0
         }
 #pragma unroll
         for (int q = 0; q < WPT; ++q) {
@@ -546,31 +596,7 @@ __global__ void __launch_bounds__(TcRowsCfg<H>::NT) fact_rows_tc_kernel(const __
           *reinterpret_cast<uint4*>(Bhi + off) = hi;
           *reinterpret_cast<uint4*>(Blo + off) = lo;
         }
-        cur_t = t;
-      }
-      const float* tab = p.w[t];
-      const uint32_t kb = p.key_base[t];
-      // unit = (8-row group rg, block of 4 chunks): lane -> (row rg * 8 + lane % 8, chunk 4 * cq + lane / 8)
-      constexpr int UNITS = (kRT / 8) * (H4 / 4), UPW = UNITS / 4;
-      float4 v[UPW];
-#pragma unroll
-      for (int q = 0; q < UPW; ++q) {
-        const int unit = warp * UPW + q;
-        const int rg = unit / (H4 / 4), cq = unit % (H4 / 4);
-        const int r = rg * 8 + (lane & 7), c = cq * 4 + (lane >> 3);
-        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < ns) {
-          const float* rsrc;
-          if (p.n_peers > 0) {
-            const uint32_t key = s_key[seg_a + r];
-            rsrc = p.peer[key % (uint32_t)p.n_peers] + (size_t)(key / (uint32_t)p.n_peers) * H;
-          } else if (p.fetched != nullptr) {
-            rsrc = p.fetched + (size_t)s_perm[seg_a + r] * H;
-          } else {
-            rsrc = tab + (size_t)(s_key[seg_a + r] - kb) * H;
-          }
-          v[q] = __ldg(reinterpret_cast<const float4*>(rsrc) + c);
-        }
+        cur_t = cur.t;
       }
 #pragma unroll
       for (int q = 0; q < UPW; ++q) {
@@ -578,7 +604,7 @@ __global__ void __launch_bounds__(TcRowsCfg<H>::NT) fact_rows_tc_kernel(const __
         const int rg = unit / (H4 / 4), cq = unit % (H4 / 4);
         const int r = rg * 8 + (lane & 7), c = cq * 4 + (lane >> 3);
         if (p.save_rows != nullptr && r < ns)
-          st_stream(reinterpret_cast<float4*>(p.save_rows + (size_t)(r0 + seg_a + r) * H) + c, v[q]);
+          st_stream(reinterpret_cast<float4*>(p.save_rows + (size_t)(row0 + r) * H) + c, v[q]);
         uint4 hi, lo;
         split_tf32(v[q].x, hi.x, lo.x);
         split_tf32(v[q].y, hi.y, lo.y);
@@ -596,6 +622,7 @@ __global__ void __launch_bounds__(TcRowsCfg<H>::NT) fact_rows_tc_kernel(const __
         const uint32_t a_hi = tc::smem_u32(Ahi), a_lo = tc::smem_u32(Alo), b_hi = tc::smem_u32(Bhi), b_lo = tc::smem_u32(Blo);
 #pragma unroll
         for (int ks = 0; ks < H / 8; ++ks) {
+          if (dbg & 4) break;
           const uint32_t o = ks * 2 * Cfg::LBO;
           const uint64_t dah = tc::make_desc(a_hi + o, Cfg::LBO, Cfg::SBO, 0), dal = tc::make_desc(a_lo + o, Cfg::LBO, Cfg::SBO, 0);
           const uint64_t dbh = tc::make_desc(b_hi + o, Cfg::LBO, Cfg::SBO, 0), dbl = tc::make_desc(b_lo + o, Cfg::LBO, Cfg::SBO, 0);
@@ -605,19 +632,22 @@ __global__ void __launch_bounds__(TcRowsCfg<H>::NT) fact_rows_tc_kernel(const __
         }
         tc::commit(&mbar);
       }
+      // software pipeline: the next item's rows are requested now and travel while the MMAs and the epilogue run
+      const TcItem nxt = next_of(cur);
+      if (nxt.tile < win_b) issue_loads(nxt);
       tc::mbar_wait(&mbar, phase);
       phase ^= 1u;
       tc::fence_after_sync();
       {
         const int r = warp * 32 + lane;
-        float* dst = P + (size_t)(r0 + seg_a + r) * H;
+        float* dst = P + (size_t)(row0 + r) * H;
         const uint32_t taddr = tacc + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
         for (int c0 = 0; c0 < H; c0 += 16) {
           uint32_t rr[16];
           tc::ld16(taddr + c0, rr);
           tc::ld_wait();
-          if (r < ns) {
+          if (r < ns && !(dbg & 2)) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
               *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]),
@@ -626,8 +656,8 @@ __global__ void __launch_bounds__(TcRowsCfg<H>::NT) fact_rows_tc_kernel(const __
         }
       }
       tc::fence_before_sync();
-      __syncthreads();   // every warp has drained its TMEM lanes before the next segment's first MMA overwrites them
-      seg_a = seg_b;
+      __syncthreads();   // every warp has drained its TMEM lanes before the next item's first MMA overwrites them
+      cur = nxt;
     }
   }
   tc::fence_before_sync();
@@ -1076,7 +1106,8 @@ template <int H>
 static int launch_rows_tc(const FactParams& p, const uint32_t* uniq, const int32_t* n_unique_dev, float* P, cudaStream_t st) {
   const size_t smem = TcRowsCfg<H>::SMEM;
   { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(fact_rows_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
-  TGR_K(fact_rows_tc_kernel<H>)<<<kTcGridFwd, TcRowsCfg<H>::NT, smem, st>>>(p, uniq, n_unique_dev, P);
+  static const int dbg = [] { const char* e = getenv("TGR_TC_DBG"); return e ? atoi(e) : 0; }();   // dev: 1 no loads, 2 no stores, 4 no MMA
+  TGR_K(fact_rows_tc_kernel<H>)<<<kTcGridFwd, TcRowsCfg<H>::NT, smem, st>>>(p, uniq, n_unique_dev, P, dbg);
   return check_launch("fact_project_rows");
 }
 

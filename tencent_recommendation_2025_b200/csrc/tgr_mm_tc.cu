@@ -154,6 +154,128 @@ __global__ void __launch_bounds__(128) mm_proj_fwd_tc_kernel(const __grid_consta
   if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tacc);
 }
 
+// ---- backward: A[h][j] (+)= sum_t dZ[t][h] x[t][j]  (dW of the projection: autograd of model.py:297 through the fold) --------
+// Split-K (over tokens) tcgen05 GEMM with BOTH operands MN-major: dZ (bf16 copy, [T, H]) and x (bf16, [T, mm_dim]) are
+// row-major with the contraction index t as the ROW, so a TMA box {64 columns, 64 tokens} lands in shared memory as eight
+// 128-byte-swizzled atoms of 8 token rows x 64 MN elements — the canonical MN-major SWIZZLE_128B operand (verified on B200,
+// tools/tc_probe2.cu variant 2: LBO = stride between 64-element MN groups, SBO = 1024 between 8-row K groups, +2048 bytes
+// per K = 16 MMA). M = 128 accumulator rows of which H are real: for H = 64 the second MN group of A repeats the first
+// (LBO = 0), rows 64..127 are never read back. CTA = (token chunk, BN-column tile): 4-slot TMA ring, one thread issues
+// the copies and the MMAs, D [128 x BN] fp32 in tensor memory, the H real lanes write the chunk's partial; the existing
+// fixed-order reduction (mm_proj_bwd_reduce_kernel) sums the chunks => bitwise reproducible.
+template <int H, int BN>
+__global__ void __launch_bounds__(128) mm_proj_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z,
+                                                             const __grid_constant__ CUtensorMap tm_x,
+                                                             float* __restrict__ ws_dw, int64_t T, int K, int n_chunks) {
+  constexpr int S = kTcStages, BT = 64;
+  constexpr int A_BYTES = (H / 64) * BT * 128, B_BYTES = (BN / 64) * BT * 128;   // boxes of 64 tokens x 128 bytes
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t mmtc_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)mmtc_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* As = base;
+  uint8_t* Bs = base + S * A_BYTES;
+  __shared__ __align__(8) uint64_t full[S], empty[S], accbar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x, j0 = blockIdx.y * BN;
+  const int64_t per = ((T + n_chunks - 1) / n_chunks + BT - 1) / BT * BT;   // tokens per chunk, multiple of 64
+  const int64_t tb = (int64_t)chunk * per, te = min(T, tb + per);
+  const int nkb = te > tb ? (int)((te - tb + BT - 1) / BT) : 0;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    tc::mbar_init(&accbar, 1);
+  }
+  if (warp == 0) tc::tmem_alloc<TMEM_COLS>(&s_tmem);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tacc = s_tmem;
+  if (tid == 0 && nkb > 0) {
+    // bf16 x bf16 -> f32, A and B MN-major (bits 15 / 16)
+    const uint32_t idesc = tc::make_idesc(1u, 128, BN) | (1u << 15) | (1u << 16);
+    auto issue_load = [&](int kb) {
+      const int s = kb % S;
+      if (kb >= S) tc::mbar_wait(&empty[s], (uint32_t)((kb / S) - 1) & 1u);
+      tc::mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+      const int t0 = (int)(tb + (int64_t)kb * BT);
+#pragma unroll
+      for (int g = 0; g < H / 64; ++g) tma_load_2d(As + s * A_BYTES + g * (BT * 128), &tm_z, &full[s], g * 64, t0);
+#pragma unroll
+      for (int g = 0; g < BN / 64; ++g) tma_load_2d(Bs + s * B_BYTES + g * (BT * 128), &tm_x, &full[s], j0 + g * 64, t0);
+    };
+    for (int kb = 0; kb < S && kb < nkb; ++kb) issue_load(kb);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      tc::mbar_wait(&full[s], (uint32_t)(kb / S) & 1u);
+      tc::fence_after_sync();
+      const uint32_t a0 = tc::smem_u32(As + s * A_BYTES), b0 = tc::smem_u32(Bs + s * B_BYTES);
+#pragma unroll
+      for (int k = 0; k < BT / 16; ++k) {
+        const uint64_t da = tc::make_desc(a0 + k * 2048, H > 64 ? BT * 128 : 0, 1024, 2);
+        const uint64_t db = tc::make_desc(b0 + k * 2048, BT * 128, 1024, 2);
+        tc::mma_f16(tacc, da, db, idesc, kb > 0 || k > 0);
+      }
+      tc::commit(&empty[s]);
+      if (kb + S < nkb) issue_load(kb + S);
+    }
+    tc::commit(&accbar);
+  }
+  const int h = warp * 32 + lane;          // accumulator lane = output row h
+  float* dst = ws_dw + ((size_t)chunk * H + h) * (size_t)K + j0;
+  if (nkb > 0) {
+    tc::mbar_wait(&accbar, 0);
+    tc::fence_after_sync();
+    const uint32_t taddr = tacc + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t rr[16];
+      tc::ld16(taddr + c0, rr);
+      tc::ld_wait();
+      if (h < H) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]),
+                                                                 __uint_as_float(rr[j + 2]), __uint_as_float(rr[j + 3]));
+      }
+    }
+  } else if (h < H) {
+    for (int c0 = 0; c0 < BN; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tacc);
+}
+
+// out[o] (+)= sum over chunks of ws[c][o], chunks ascending per lane, fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(256) chunk_reduce_kernel(const float* __restrict__ ws, int n_chunks, int64_t n_out,
+                                                           float* __restrict__ out, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n_out) return;
+  float s = 0.f;
+  for (int c = lane; c < n_chunks; c += 32) s += ws[(size_t)c * n_out + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[i] = accumulate ? out[i] + s : s;
+}
+
+static int bwd_tc_bn(int mm_dim) { return mm_dim % 256 == 0 ? 256 : (mm_dim % 128 == 0 ? 128 : 64); }
+static int bwd_tc_chunks(int64_t T, int mm_dim) {
+  const int nt = mm_dim / bwd_tc_bn(mm_dim);
+  int n = (kNumSMs + nt - 1) / nt;
+  const int64_t by_T = (T + 63) / 64;
+  if (n > by_T) n = (int)by_T;
+  return n < 1 ? 1 : n;
+}
+
+template <int H, int BN>
+static int launch_bwd_tc(const CUtensorMap& tz, const CUtensorMap& tx, float* ws, int64_t T, int K, int n_chunks, cudaStream_t st) {
+  const size_t smem = (size_t)kTcStages * ((H / 64) * 64 * 128 + (BN / 64) * 64 * 128) + 1024;
+  { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(mm_proj_bwd_tc_kernel<H, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
+  TGR_K(mm_proj_bwd_tc_kernel<H, BN>)<<<dim3(n_chunks, K / BN), 128, smem, st>>>(tz, tx, ws, T, K, n_chunks);
+  return check_launch("mm_proj_bwd_tc");
+}
+
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, int64_t n, __nv_bfloat16* __restrict__ dst) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
@@ -213,4 +335,40 @@ extern "C" int tgr_mm_proj_fwd_tc(const void* x_bf16, int64_t T, int mm_dim, con
   if (H == 32) return ob ? launch_tc<32, true>(tx, tw, bias, o, ldb, T, mm_dim, st) : launch_tc<32, false>(tx, tw, bias, o, ldb, T, mm_dim, st);
   if (H == 64) return ob ? launch_tc<64, true>(tx, tw, bias, o, ldb, T, mm_dim, st) : launch_tc<64, false>(tx, tw, bias, o, ldb, T, mm_dim, st);
   return ob ? launch_tc<128, true>(tx, tw, bias, o, ldb, T, mm_dim, st) : launch_tc<128, false>(tx, tw, bias, o, ldb, T, mm_dim, st);
+}
+
+/* ---- backward on the tensor cores (see mm_proj_bwd_tc_kernel) ---- */
+extern "C" int tgr_mm_proj_bwd_tc_supported(int x_dtype, int mm_dim, int H) {
+  return x_dtype == TGR_DTYPE_BF16 && mm_dim >= 128 && mm_dim % kTcBK == 0 && (H == 64 || H == 128) ? 1 : 0;
+}
+
+extern "C" size_t tgr_mm_proj_bwd_tc_workspace_bytes(int64_t T, int mm_dim, int H) {
+  return (size_t)bwd_tc_chunks(T, mm_dim) * H * mm_dim * sizeof(float) + 256;
+}
+
+extern "C" int tgr_mm_proj_bwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* dz_bf16, int H, float* dW,
+                                  int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  tgr::TimedScope tgr_timed_("mm_proj_bwd_tc", stream);
+  TGR_REQUIRE(x_bf16 && dz_bf16 && dW && workspace, "null argument");
+  TGR_REQUIRE(tgr_mm_proj_bwd_tc_supported(TGR_DTYPE_BF16, mm_dim, H), "mm_proj_bwd_tc: mm_dim %% 64 == 0, >= 128 and H in {64, 128} (mm_dim=%d, H=%d)", mm_dim, H);
+  TGR_REQUIRE(T >= 0 && T < (1ll << 31), "T out of range");
+  TGR_REQUIRE(workspace_bytes >= tgr_mm_proj_bwd_tc_workspace_bytes(T, mm_dim, H), "workspace too small");
+  TGR_REQUIRE(((uintptr_t)x_bf16 & 15) == 0 && ((uintptr_t)dz_bf16 & 15) == 0 && ((uintptr_t)workspace & 15) == 0, "mm_proj_bwd_tc: misaligned buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_out = (int64_t)H * mm_dim;
+  if (T == 0) {
+    if (!accumulate) cudaMemsetAsync(dW, 0, (size_t)n_out * sizeof(float), st);
+    return 0;
+  }
+  const int bn = bwd_tc_bn(mm_dim), n_chunks = bwd_tc_chunks(T, mm_dim);
+  CUtensorMap tz, tx;
+  if (int rc = make_map(&tz, dz_bf16, T, H, 64)) return rc;
+  if (int rc = make_map(&tx, x_bf16, T, mm_dim, 64)) return rc;
+  float* ws = (float*)workspace;
+  int rc;
+  if (H == 64) rc = bn == 256 ? launch_bwd_tc<64, 256>(tz, tx, ws, T, mm_dim, n_chunks, st) : (bn == 128 ? launch_bwd_tc<64, 128>(tz, tx, ws, T, mm_dim, n_chunks, st) : launch_bwd_tc<64, 64>(tz, tx, ws, T, mm_dim, n_chunks, st));
+  else rc = bn == 256 ? launch_bwd_tc<128, 256>(tz, tx, ws, T, mm_dim, n_chunks, st) : (bn == 128 ? launch_bwd_tc<128, 128>(tz, tx, ws, T, mm_dim, n_chunks, st) : launch_bwd_tc<128, 64>(tz, tx, ws, T, mm_dim, n_chunks, st));
+  if (rc) return rc;
+  TGR_K(chunk_reduce_kernel)<<<(unsigned)((n_out * 32 + 255) / 256), 256, 0, st>>>(ws, n_chunks, n_out, dW, accumulate);
+  return check_launch("mm_proj_bwd_tc_reduce");
 }

@@ -54,3 +54,21 @@ class Golden:
         z = self.z
         mm = [z[f"mm_x{j}"] for j in range(len(self.mm_ids))]
         return PackedCall(1, self.L, False, z["ids"], z["arr_off"], z["arr_val"], mm, seq=z["seq"], mask=None)
+
+
+def assert_rows_updated(got, want, grad, lr, rtol=1e-5, what=""):
+    """Updated table rows at the north_star bar (1e-5 of tensor scale) with an explicit |g| guard. AdamW's first step moves
+    an element by lr * g / (|g| + eps): where |g| is below the gradient's own resolution (rtol of the gradient scale) ANY
+    fp32 summation order — the reference's included — lands anywhere within the 2 * lr a sign flip costs, so those
+    elements are held to 2 * lr and everything else to rtol. The guard may excuse at most 1 % of the elements."""
+    import numpy as np
+    got, want, grad = np.asarray(got, np.float64), np.asarray(want, np.float64), np.asarray(grad, np.float64)
+    assert got.shape == want.shape == grad.shape, (what, got.shape, want.shape, grad.shape)
+    if got.size == 0:
+        return
+    d = np.abs(got - want)
+    wscale, gscale = max(np.abs(want).max(), 1e-30), max(np.abs(grad).max(), 1e-30)
+    firm = np.abs(grad) >= rtol * gscale
+    assert d[firm].max(initial=0.0) <= rtol * wscale, f"{what}: updated rows off by {d[firm].max():.3e} (scale {wscale:.3e})"
+    assert d[~firm].max(initial=0.0) <= 2.0 * lr * 1.001 + rtol * wscale, f"{what}: sub-resolution gradients moved {d[~firm].max():.3e}"
+    assert firm.mean() >= 0.99, f"{what}: guard excuses {1 - firm.mean():.4f} of the elements"

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import GOLDEN_DIR, Golden, TRAIN_CASES
+from golden_util import GOLDEN_DIR, Golden, TRAIN_CASES, assert_rows_updated
 from test_gpu_parity import _close, _close_fro, dev_batch
 from tencent_recommendation_2025_b200.synth import SynthConfig, SynthWorld, packed_to_dicts
 
@@ -115,9 +115,7 @@ def test_fused_row_update_matches_reference_adamw(name, prefetch):
         if k.split(".")[0] in ("item_emb", "user_emb", "sparse_emb"):
             touched = np.nonzero(np.any(ref_g[k] != 0, axis=1))[0]
             untouched = np.setdiff1d(np.arange(got.shape[0]), touched)
-            # AdamW step 1 moves an element by ~lr*g/(|g|+eps): elements with |g| ~ eps amplify the 1e-7 gradient
-            # re-association noise, hence a slightly wider bar than the gradient's own
-            _close(got[touched], ref_p[k][touched], rtol=2e-5, what=f"{name} updated rows {k}")
+            assert_rows_updated(got[touched], ref_p[k][touched], ref_g[k][touched], g.lr, what=f"{name} updated rows {k}")
             assert np.array_equal(got[untouched], p0[k][untouched]), f"{k}: untouched rows must not move"
             assert not got[0].any()
         else:

@@ -94,3 +94,96 @@ print('ERR', err)
         assert r.returncode == 0, r.stdout + r.stderr
         err = float(r.stdout.strip().split("ERR")[-1])
         assert err <= 1e-5, (env, err)
+
+
+@pytest.mark.parametrize("T,mm_dim,H", [(1000, 128, 64), (4099, 1024, 64), (300, 1024, 128), (64, 3584, 64)])
+def test_mm_proj_bwd_tc_matches_torch(T, mm_dim, H):
+    """dW += dz^T x on tcgen05 (both operands MN-major from TMA, split-K over tokens) vs fp64 on the same bf16 inputs;
+    accumulate semantics and run-to-run bitwise reproducibility."""
+    from tencent_recommendation_2025_b200 import _lib
+    lib = _lib.load()
+    assert lib.tgr_mm_proj_bwd_tc_supported(_lib.DTYPE_BF16, mm_dim, H) == 1
+    g = torch.Generator(device="cuda").manual_seed(T + mm_dim)
+    x = torch.randn(T, mm_dim, device="cuda", generator=g).to(torch.bfloat16)
+    dz = torch.randn(T, H, device="cuda", generator=g)
+    dzb = torch.empty(T, H, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.tgr_cast_bf16(dz.data_ptr(), dz.numel(), dzb.data_ptr(), _stream()), "cast")
+    ws = torch.empty(lib.tgr_mm_proj_bwd_tc_workspace_bytes(T, mm_dim, H), dtype=torch.uint8, device="cuda")
+    base = torch.randn(H, mm_dim, device="cuda", generator=g)
+    outs = []
+    for rep in range(2):
+        dW = base.clone()
+        _lib.check(lib.tgr_mm_proj_bwd_tc(x.data_ptr(), T, mm_dim, dzb.data_ptr(), H, dW.data_ptr(), 1, ws.data_ptr(), ws.numel(),
+                                          _stream()), "mm_proj_bwd_tc")
+        torch.cuda.synchronize()
+        outs.append(dW)
+    assert torch.equal(outs[0], outs[1])
+    ref = base.double() + dzb.double().t() @ x.double()
+    scale = ref.abs().max().item()
+    assert (outs[0].double() - ref).abs().max().item() <= 1e-5 * scale
+    dW = torch.full((H, mm_dim), 3.0, device="cuda")
+    _lib.check(lib.tgr_mm_proj_bwd_tc(x.data_ptr(), T, mm_dim, dzb.data_ptr(), H, dW.data_ptr(), 0, ws.data_ptr(), ws.numel(),
+                                      _stream()), "mm_proj_bwd_tc")
+    ref0 = dzb.double().t() @ x.double()
+    assert (dW.double() - ref0).abs().max().item() <= 1e-5 * ref0.abs().max().item()
+
+
+def test_factored_step_with_wide_bf16_mm_feature():
+    """BASELINE.json config 3 in small: O1-style layout with mm features '81' (32-d) + '82' (1024-d) kept in bf16. The
+    factored path runs '82' through the tcgen05 projection (forward) and the tcgen05 split-K GEMM (backward); results
+    against the torch oracle in fp64 on the SAME bf16-rounded mm inputs: north_star's 1e-2 bar for bf16, measured — as the
+    existing bf16-autocast test does — in relative Frobenius norm (a bf16-level perturbation of a pre-activation flips
+    ReLU masks of elements at ~0, which moves single gradient elements by a whole upstream value)."""
+    import types
+
+    import numpy as np
+
+    from oracle import feat2emb_numpy as onp
+    from oracle.feat2emb_torch import TorchOracle, tensors_to_torch
+    from tencent_recommendation_2025_b200.module import BaselineEmbedding
+    from tencent_recommendation_2025_b200.packed import to_device
+    from tencent_recommendation_2025_b200.synth import SynthConfig, SynthWorld
+    stats = {k: 60 for k in ["103", "104", "105", "109", "100", "117", "111", "118", "101", "102", "119", "120", "114", "112",
+                             "121", "115", "122", "116", "106", "107", "108", "110"]}
+    cfg = SynthConfig(B=24, L=41, H=64, item_num=3000, user_num=200, alpha=1.1, mm_ids=("81", "82"), min_len=6,
+                      feat_statistics=stats)
+    world = SynthWorld(cfg, 5)
+    lay = world.layout
+    st = world.make_step(0)
+    for pc in st.calls:          # the frozen features are STORED in bf16: round the inputs once, both sides see the same values
+        pc.mm_x = [torch.from_numpy(x).to(torch.bfloat16).float().numpy() for x in pc.mm_x]
+    args = types.SimpleNamespace(device="cuda", hidden_units=cfg.H)
+    torch.manual_seed(0)
+    m = BaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), args, "parity", path="factored").cuda()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.1)
+        for p in m.engine.tables:
+            p[0].zero_()
+    orc = TorchOracle(lay).double()
+    orc.load_numpy({k: v.detach().cpu().numpy() for k, v in m.named_parameters()})
+    orc = orc.double()
+    outs_ref = []
+    for pc in st.calls:
+        t = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in tensors_to_torch(onp.tensors_from_packed(lay, pc)).items()}
+        seq = torch.from_numpy(pc.seq.astype(np.int64))
+        mask = torch.from_numpy(pc.mask.astype(np.int64)) if pc.include_user else None
+        outs_ref.append(orc.feat2emb(seq, t, mask, pc.include_user))
+    torch.autograd.backward(outs_ref, [torch.from_numpy(r).double() for r in st.upstream])
+    gref = orc.grads_numpy()
+    pbs = [to_device(lay, pc, "cuda", mm_dtype=torch.bfloat16) for pc in st.calls]
+    m.prefetch(pbs)
+    outs = [m.feat2emb_packed(pb) for pb in pbs]
+    for c, (o, r) in enumerate(zip(outs, outs_ref)):
+        r = r.detach().numpy()
+        assert np.abs(o.detach().cpu().numpy() - r).max() <= 1e-2 * np.abs(r).max(), f"out call {c}"
+        assert np.linalg.norm(o.detach().cpu().numpy() - r) <= 1e-2 * np.linalg.norm(r), f"out call {c} (Frobenius)"
+    torch.autograd.backward(outs, [torch.from_numpy(r).cuda() for r in st.upstream])
+    torch.cuda.synchronize()
+    for k, p in m.named_parameters():
+        gt = gref.get(k)
+        if gt is None or not gt.any():
+            continue
+        err = np.linalg.norm(p.grad.cpu().numpy().astype(np.float64) - gt) / max(np.linalg.norm(gt), 1e-30)
+        assert err <= 1.5e-2, f"grad {k}: relative Frobenius error {err:.3e}"
