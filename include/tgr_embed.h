@@ -134,18 +134,23 @@ int tgr_mm_proj_fwd(const void* x, int x_dtype, int64_t T, int mm_dim, const flo
 /* The same projection on the 5th-generation tensor cores (tcgen05.mma kind::f16 + TMEM accumulator, x and W tiles
  * streamed by TMA with 128-byte swizzle; csrc/tgr_mm_tc.cu) for the wide frozen mm features kept in bf16 (BASELINE.json
  * config 3: '82' = 1024-d ... '84' = 4096-d, model.py:183): x bf16 [T, mm_dim], w_bf16 = bf16 copy of W [H, mm_dim]
- * (tgr_cast_bf16), fp32 accumulate, bias fp32 or NULL. Needs mm_dim % 64 == 0, mm_dim >= 128, H in {32, 64, 128}
- * (tgr_mm_proj_fwd_tc_supported). */
+ * (tgr_cast_bf16; w_planes = 1) or TWO bf16 planes stacked along the rows, [2 H, mm_dim] = hi then bf16(W - hi)
+ * (tgr_split_bf16; w_planes = 2: 16 mantissa bits, the result matches fp32 math on the bf16-stored features), fp32
+ * accumulate, bias fp32 or NULL. Needs mm_dim % 64 == 0, mm_dim >= 128, H in {32, 64, 128} (tgr_mm_proj_fwd_tc_supported). */
 int tgr_mm_proj_fwd_tc_supported(int x_dtype, int mm_dim, int H);
-int tgr_mm_proj_fwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* w_bf16, const float* bias, int H, void* out,
-                       int64_t out_ld, int out_dtype, void* stream);
+int tgr_mm_proj_fwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* w_bf16, int w_planes, const float* bias, int H,
+                       void* out, int64_t out_ld, int out_dtype, void* stream);
 /* Backward of the wide bf16 projection on the tensor cores: dW[H, mm_dim] (+)= dz^T . x with dz_bf16 a bf16 copy of the
  * fp32 dz [T, H] (tgr_cast_bf16). Split-K over tokens, both operands MN-major straight from TMA (csrc/tgr_mm_tc.cu), chunk
  * partials reduced in fixed order (bitwise reproducible). Needs mm_dim % 64 == 0, mm_dim >= 128, H in {64, 128}. */
 int tgr_mm_proj_bwd_tc_supported(int x_dtype, int mm_dim, int H);
 size_t tgr_mm_proj_bwd_tc_workspace_bytes(int64_t T, int mm_dim, int H);
-int tgr_mm_proj_bwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* dz_bf16, int H, float* dW, int accumulate,
-                       void* workspace, size_t workspace_bytes, void* stream);
+int tgr_mm_proj_bwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* dz_bf16, int dz_planes, int64_t plane_rows, int H,
+                       float* dW, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* hi[i] = bf16(src[i]), lo[i] = bf16(src[i] - hi[i]): the two-plane operand form of the tensor-core projection. With
+ * dz_planes = 2 the planes are [plane_rows, H] blocks of one buffer (plane_rows >= T, a multiple of 64; rows [T, plane_rows)
+ * of plane 0 must be finite, e.g. zero). */
+int tgr_split_bf16(const float* src, int64_t n, void* hi_bf16, void* lo_bf16, void* stream);
 /* dst_bf16[i] = bf16(src[i]) (round to nearest even), n elements; src 16-byte, dst 8-byte aligned. */
 int tgr_cast_bf16(const float* src, int64_t n, void* dst_bf16, void* stream);
 

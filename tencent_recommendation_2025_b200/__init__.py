@@ -8,4 +8,17 @@ raises if ``libtgr_embed.so`` is missing.
 """
 from .layout import FeatureLayout, DEFAULT_FEAT_TYPES, EMB_SHAPE_DICT, default_feat_statistics  # noqa: F401
 
-__all__ = ["FeatureLayout", "DEFAULT_FEAT_TYPES", "EMB_SHAPE_DICT", "default_feat_statistics"]
+
+
+def __getattr__(name):      # lazy: importing the package must not need torch extensions or a built library
+    if name in ("install", "BaselineEmbedding"):
+        from . import module
+        return getattr(module, name)
+    if name == "PackingCollate":
+        from .packed import PackingCollate
+        return PackingCollate
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+__all__ = ["FeatureLayout", "DEFAULT_FEAT_TYPES", "EMB_SHAPE_DICT", "default_feat_statistics", "install",
+           "BaselineEmbedding", "PackingCollate"]

@@ -115,13 +115,14 @@ SIGNATURES = {
     "tgr_mm_proj_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_int64, C.c_int, C.c_void_p]),
     "tgr_mm_proj_fwd_tc_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
-    "tgr_mm_proj_fwd_tc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
-                                     C.c_int, C.c_void_p]),
+    "tgr_mm_proj_fwd_tc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_int64, C.c_int, C.c_void_p]),
+    "tgr_split_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgr_cast_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "tgr_mm_proj_bwd_tc_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "tgr_mm_proj_bwd_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
-    "tgr_mm_proj_bwd_tc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
-                                     C.c_size_t, C.c_void_p]),
+    "tgr_mm_proj_bwd_tc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tgr_mm_proj_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "tgr_mm_proj_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),

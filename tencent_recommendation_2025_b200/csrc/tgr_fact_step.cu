@@ -89,13 +89,13 @@ static size_t carve(tgr_fact_group_t* g, void* arena, int n_tables) {
     }
     max_T = max(max_T, T);
   }
-  g->dzb = any_tc_bwd ? (void*)cv.take<uint16_t>(max_T * H) : nullptr;
+  g->dzb = any_tc_bwd ? (void*)cv.take<uint16_t>(2 * ((max_T + 63) / 64 * 64) * H) : nullptr;   // two bf16 planes
   for (int f = 0; f < g->n_mm; ++f) {
     g->fold_M[f] = cv.take<float>((size_t)H * g->mm_dim[f]);
     g->fold_c[f] = cv.take<float>(H);
     g->mm_A[f] = cv.take<float>((size_t)H * g->mm_dim[f]);
     g->mm_s[f] = cv.take<float>(H);
-    g->fold_Mb[f] = cv.take<uint16_t>((size_t)H * g->mm_dim[f]);
+    g->fold_Mb[f] = cv.take<uint16_t>((size_t)2 * H * g->mm_dim[f]);   // two bf16 planes (hi, lo)
   }
   ws = max(ws, tgr_build_keys_workspace_bytes(max_entries));
   ws = max(ws, tgr_sort_workspace_bytes(g->n));
@@ -175,7 +175,8 @@ extern "C" int tgr_fact_call_forward(const tgr_table_t* tables, int n_tables, co
       if (int rc = tgr_fact_mm_fold(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, H, m.mm_dim, g->fold_M[f],
                                     g->fold_c[f], stream)) return rc;
       if (tgr_mm_proj_fwd_tc_supported(g->mm_x_dtype, m.mm_dim, H))   // wide bf16 feature: tcgen05 path wants a bf16 M
-        if (int rc = tgr_cast_bf16(g->fold_M[f], (int64_t)H * m.mm_dim, g->fold_Mb[f], stream)) return rc;
+        if (int rc = tgr_split_bf16(g->fold_M[f], (int64_t)H * m.mm_dim, g->fold_Mb[f],
+                                    (uint16_t*)g->fold_Mb[f] + (size_t)H * m.mm_dim, stream)) return rc;
     }
     g->projected = 1;
   }
@@ -183,7 +184,7 @@ extern "C" int tgr_fact_call_forward(const tgr_table_t* tables, int n_tables, co
   for (int f = 0; f < g->n_mm; ++f) {
     TGR_REQUIRE(g->mm_x[c][f] != nullptr, "mm input %d of call %d is NULL", f, c);
     if (tgr_mm_proj_fwd_tc_supported(g->mm_x_dtype, g->mm_dim[f], H)) {
-      if (int rc = tgr_mm_proj_fwd_tc(g->mm_x[c][f], cl.T, g->mm_dim[f], g->fold_Mb[f], g->fold_c[f], H, g->mmz[c][f], H,
+      if (int rc = tgr_mm_proj_fwd_tc(g->mm_x[c][f], cl.T, g->mm_dim[f], g->fold_Mb[f], 2, g->fold_c[f], H, g->mmz[c][f], H,
                                       TGR_DTYPE_F32, stream)) return rc;
       continue;
     }
@@ -217,12 +218,15 @@ extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, c
       if (gr->dW_mm[f] == nullptr || f == fused) continue;
       if (tgr_mm_proj_bwd_tc_supported(g->mm_x_dtype, prm->mm[f].mm_dim, H)) {
         // wide bf16 feature: A += dz^T x on the tensor cores (s = colsum(dz) is read off db_item at the finish)
-        if (!dz_cast) {
-          if (int rc = tgr_cast_bf16(g->dz_item[c], (int64_t)cl.T * H, g->dzb, stream)) return rc;
+        const int64_t plane_rows = ((int64_t)cl.T + 63) / 64 * 64;
+        if (!dz_cast) {   // dz as two bf16 planes (16 mantissa bits); the pad rows of plane 0 must be finite
+          uint16_t* hi = (uint16_t*)g->dzb;
+          if (plane_rows > cl.T) cudaMemsetAsync(hi + (size_t)cl.T * H, 0, (size_t)(plane_rows - cl.T) * H * 2, (cudaStream_t)stream);
+          if (int rc = tgr_split_bf16(g->dz_item[c], (int64_t)cl.T * H, hi, hi + (size_t)plane_rows * H, stream)) return rc;
           dz_cast = true;
         }
-        if (int rc = tgr_mm_proj_bwd_tc(g->mm_x[c][f], cl.T, prm->mm[f].mm_dim, g->dzb, H, g->mm_A[f], 1, g->ws, g->ws_bytes,
-                                        stream)) return rc;
+        if (int rc = tgr_mm_proj_bwd_tc(g->mm_x[c][f], cl.T, prm->mm[f].mm_dim, g->dzb, 2, plane_rows, H, g->mm_A[f], 1, g->ws,
+                                        g->ws_bytes, stream)) return rc;
         continue;
       }
       if (int rc = tgr_mm_proj_bwd(g->mm_x[c][f], g->mm_x_dtype, cl.T, prm->mm[f].mm_dim, g->dz_item[c], H, TGR_DTYPE_F32,

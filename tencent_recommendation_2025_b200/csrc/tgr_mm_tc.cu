@@ -22,6 +22,7 @@
 namespace tgr {
 
 constexpr int kTcBM = 128, kTcBK = 64, kTcStages = 4;
+constexpr int kTcFwdStages = 3;   // forward ring: 3 x (16 KB x + 2 planes x H x 128 B) = 96 KB at H = 64 -> 2 CTAs / SM
 
 typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -63,8 +64,10 @@ template <int H, bool OBF16>
 __global__ void __launch_bounds__(128) mm_proj_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                              const __grid_constant__ CUtensorMap tm_w,
                                                              const float* __restrict__ bias, char* __restrict__ out,
-                                                             int64_t out_ld_bytes, int64_t T, int K, int n_tiles) {
-  constexpr int A_BYTES = kTcBM * kTcBK * 2, B_BYTES = H * kTcBK * 2, S = kTcStages;
+                                                             int64_t out_ld_bytes, int64_t T, int K, int n_tiles, int planes) {
+  // W arrives as `planes` bf16 planes stacked along the rows ([planes * H, K]: hi, then the bf16 of the remainder): with
+  // two planes the weights carry 16 mantissa bits and the product with the bf16-STORED features matches fp32 math.
+  constexpr int A_BYTES = kTcBM * kTcBK * 2, P_BYTES = H * kTcBK * 2, B_BYTES = 2 * P_BYTES, S = kTcFwdStages;
   constexpr int TMEM_COLS = H < 32 ? 32 : H;
   extern __shared__ uint8_t mmtc_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)mmtc_raw + 1023) & ~(uintptr_t)1023);
@@ -93,9 +96,9 @@ __global__ void __launch_bounds__(128) mm_proj_fwd_tc_kernel(const __grid_consta
     if (item >= (uint32_t)S) tc::mbar_wait(&empty[s], ((item / S) - 1u) & 1u);   // the MMAs that read this slot's previous tile
     const int tile = (int)blockIdx.x + (int)(item / (uint32_t)nkb) * (int)gridDim.x;
     const int kb = (int)(item % (uint32_t)nkb);
-    tc::mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+    tc::mbar_expect_tx(&full[s], A_BYTES + planes * P_BYTES);
     tma_load_2d(As + s * A_BYTES, &tm_x, &full[s], kb * kTcBK, tile * kTcBM);
-    tma_load_2d(Bs + s * B_BYTES, &tm_w, &full[s], kb * kTcBK, 0);
+    for (int pl = 0; pl < planes; ++pl) tma_load_2d(Bs + s * B_BYTES + pl * P_BYTES, &tm_w, &full[s], kb * kTcBK, pl * H);
   };
   if (tid == 0)
     for (uint32_t it = 0; it < (uint32_t)S && it < total; ++it) issue_load(it);
@@ -111,8 +114,10 @@ __global__ void __launch_bounds__(128) mm_proj_fwd_tc_kernel(const __grid_consta
 #pragma unroll
         for (int k = 0; k < kTcBK / 16; ++k) {
           const uint64_t da = tc::make_desc(a0 + k * 32, 16, 1024, 2);   // SWIZZLE_128B, 8-row groups 1024 B apart
-          const uint64_t db = tc::make_desc(b0 + k * 32, 16, 1024, 2);
-          tc::mma_f16(tacc, da, db, idesc, kb > 0 || k > 0);
+          for (int pl = planes - 1; pl >= 0; --pl) {                      // small terms first
+            const uint64_t db = tc::make_desc(b0 + pl * P_BYTES + k * 32, 16, 1024, 2);
+            tc::mma_f16(tacc, da, db, idesc, kb > 0 || k > 0 || pl < planes - 1);
+          }
         }
         tc::commit(&empty[s]);
         if (kb == nkb - 1) tc::commit(&accbar);
@@ -166,9 +171,11 @@ __global__ void __launch_bounds__(128) mm_proj_fwd_tc_kernel(const __grid_consta
 template <int H, int BN>
 __global__ void __launch_bounds__(128) mm_proj_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_z,
                                                              const __grid_constant__ CUtensorMap tm_x,
-                                                             float* __restrict__ ws_dw, int64_t T, int K, int n_chunks) {
+                                                             float* __restrict__ ws_dw, int64_t T, int K, int n_chunks,
+                                                             int planes, int64_t plane_rows) {
+  // dz arrives as `planes` bf16 planes stacked along the rows ([planes * plane_rows, H]: hi, then bf16(dz - hi))
   constexpr int S = kTcStages, BT = 64;
-  constexpr int A_BYTES = (H / 64) * BT * 128, B_BYTES = (BN / 64) * BT * 128;   // boxes of 64 tokens x 128 bytes
+  constexpr int PA_BYTES = (H / 64) * BT * 128, A_BYTES = 2 * PA_BYTES, B_BYTES = (BN / 64) * BT * 128;   // boxes of 64 tokens x 128 bytes
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t mmtc_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)mmtc_raw + 1023) & ~(uintptr_t)1023);
@@ -196,10 +203,12 @@ __global__ void __launch_bounds__(128) mm_proj_bwd_tc_kernel(const __grid_consta
     auto issue_load = [&](int kb) {
       const int s = kb % S;
       if (kb >= S) tc::mbar_wait(&empty[s], (uint32_t)((kb / S) - 1) & 1u);
-      tc::mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+      tc::mbar_expect_tx(&full[s], planes * PA_BYTES + B_BYTES);
       const int t0 = (int)(tb + (int64_t)kb * BT);
+      for (int pl = 0; pl < planes; ++pl)
 #pragma unroll
-      for (int g = 0; g < H / 64; ++g) tma_load_2d(As + s * A_BYTES + g * (BT * 128), &tm_z, &full[s], g * 64, t0);
+        for (int g = 0; g < H / 64; ++g)
+          tma_load_2d(As + s * A_BYTES + pl * PA_BYTES + g * (BT * 128), &tm_z, &full[s], g * 64, (int)(pl * plane_rows) + t0);
 #pragma unroll
       for (int g = 0; g < BN / 64; ++g) tma_load_2d(Bs + s * B_BYTES + g * (BT * 128), &tm_x, &full[s], j0 + g * 64, t0);
     };
@@ -211,9 +220,11 @@ __global__ void __launch_bounds__(128) mm_proj_bwd_tc_kernel(const __grid_consta
       const uint32_t a0 = tc::smem_u32(As + s * A_BYTES), b0 = tc::smem_u32(Bs + s * B_BYTES);
 #pragma unroll
       for (int k = 0; k < BT / 16; ++k) {
-        const uint64_t da = tc::make_desc(a0 + k * 2048, H > 64 ? BT * 128 : 0, 1024, 2);
         const uint64_t db = tc::make_desc(b0 + k * 2048, BT * 128, 1024, 2);
-        tc::mma_f16(tacc, da, db, idesc, kb > 0 || k > 0);
+        for (int pl = planes - 1; pl >= 0; --pl) {   // small terms first
+          const uint64_t da = tc::make_desc(a0 + pl * PA_BYTES + k * 2048, H > 64 ? BT * 128 : 0, 1024, 2);
+          tc::mma_f16(tacc, da, db, idesc, kb > 0 || k > 0 || pl < planes - 1);
+        }
       }
       tc::commit(&empty[s]);
       if (kb + S < nkb) issue_load(kb + S);
@@ -259,9 +270,10 @@ __global__ void __launch_bounds__(256) chunk_reduce_kernel(const float* __restri
   if (lane == 0) out[i] = accumulate ? out[i] + s : s;
 }
 
-static int bwd_tc_bn(int mm_dim) { return mm_dim % 256 == 0 ? 256 : (mm_dim % 128 == 0 ? 128 : 64); }
-static int bwd_tc_chunks(int64_t T, int mm_dim) {
-  const int nt = mm_dim / bwd_tc_bn(mm_dim);
+// column tile: 256 where the ring fits (H = 64: 4 x 48 KB), 128 for H = 128 (4 x 48 KB)
+static int bwd_tc_bn(int mm_dim, int H) { return mm_dim % 256 == 0 && H <= 64 ? 256 : (mm_dim % 128 == 0 ? 128 : 64); }
+static int bwd_tc_chunks(int64_t T, int mm_dim, int H) {
+  const int nt = mm_dim / bwd_tc_bn(mm_dim, H);
   int n = (kNumSMs + nt - 1) / nt;
   const int64_t by_T = (T + 63) / 64;
   if (n > by_T) n = (int)by_T;
@@ -269,10 +281,11 @@ static int bwd_tc_chunks(int64_t T, int mm_dim) {
 }
 
 template <int H, int BN>
-static int launch_bwd_tc(const CUtensorMap& tz, const CUtensorMap& tx, float* ws, int64_t T, int K, int n_chunks, cudaStream_t st) {
-  const size_t smem = (size_t)kTcStages * ((H / 64) * 64 * 128 + (BN / 64) * 64 * 128) + 1024;
+static int launch_bwd_tc(const CUtensorMap& tz, const CUtensorMap& tx, float* ws, int64_t T, int K, int n_chunks, int planes,
+                         int64_t plane_rows, cudaStream_t st) {
+  const size_t smem = (size_t)kTcStages * (2 * (H / 64) * 64 * 128 + (BN / 64) * 64 * 128) + 1024;
   { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(mm_proj_bwd_tc_kernel<H, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
-  TGR_K(mm_proj_bwd_tc_kernel<H, BN>)<<<dim3(n_chunks, K / BN), 128, smem, st>>>(tz, tx, ws, T, K, n_chunks);
+  TGR_K(mm_proj_bwd_tc_kernel<H, BN>)<<<dim3(n_chunks, K / BN), 128, smem, st>>>(tz, tx, ws, T, K, n_chunks, planes, plane_rows);
   return check_launch("mm_proj_bwd_tc");
 }
 
@@ -286,14 +299,33 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   }
 }
 
+// hi[i] = bf16(src[i]); lo[i] = bf16(src[i] - hi[i])  (two bf16 planes = 16 mantissa bits)
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ src, int64_t n, __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+    const uint2 h = pack_bf16x4(v);
+    const float4 hf = unpack_bf16x4(h);
+    *reinterpret_cast<uint2*>(hi + i) = h;
+    *reinterpret_cast<uint2*>(lo + i) = pack_bf16x4(make_float4(v.x - hf.x, v.y - hf.y, v.z - hf.z, v.w - hf.w));
+  } else {
+    for (int64_t j = i; j < n; ++j) {
+      const __nv_bfloat16 h = __float2bfloat16(src[j]);
+      hi[j] = h;
+      lo[j] = __float2bfloat16(src[j] - __bfloat162float(h));
+    }
+  }
+}
+
 template <int H, bool OBF16>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& tw, const float* bias, char* out, int64_t ldb, int64_t T, int K,
-                     cudaStream_t st) {
-  const size_t smem = (size_t)kTcStages * (kTcBM * kTcBK * 2 + H * kTcBK * 2) + 1024;
+                     int planes, cudaStream_t st) {
+  const size_t smem = (size_t)kTcFwdStages * (kTcBM * kTcBK * 2 + 2 * H * kTcBK * 2) + 1024;
   { static bool tgr_attr_once_ = false; if (!tgr_attr_once_) { cudaFuncSetAttribute(mm_proj_fwd_tc_kernel<H, OBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); tgr_attr_once_ = true; } }
   const int n_tiles = (int)((T + kTcBM - 1) / kTcBM);
   const int grid = n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs;
-  TGR_K(mm_proj_fwd_tc_kernel<H, OBF16>)<<<grid, 128, smem, st>>>(tx, tw, bias, out, ldb, T, K, n_tiles);
+  TGR_K(mm_proj_fwd_tc_kernel<H, OBF16>)<<<grid, 128, smem, st>>>(tx, tw, bias, out, ldb, T, K, n_tiles, planes);
   return check_launch("mm_proj_fwd_tc");
 }
 
@@ -312,29 +344,41 @@ extern "C" int tgr_cast_bf16(const float* src, int64_t n, void* dst_bf16, void* 
   return check_launch("cast_bf16");
 }
 
+extern "C" int tgr_split_bf16(const float* src, int64_t n, void* hi_bf16, void* lo_bf16, void* stream) {
+  tgr::TimedScope tgr_timed_("cast_bf16", stream);
+  TGR_REQUIRE(n >= 0, "n out of range");
+  if (n == 0) return 0;
+  TGR_REQUIRE(src && hi_bf16 && lo_bf16, "null argument");
+  TGR_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)hi_bf16 & 7) == 0 && ((uintptr_t)lo_bf16 & 7) == 0, "split_bf16: misaligned buffers");
+  const int64_t groups = (n + 3) / 4;
+  TGR_K(split_bf16_kernel)<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n, (__nv_bfloat16*)hi_bf16, (__nv_bfloat16*)lo_bf16);
+  return check_launch("split_bf16");
+}
+
 extern "C" int tgr_mm_proj_fwd_tc_supported(int x_dtype, int mm_dim, int H) {
   return x_dtype == TGR_DTYPE_BF16 && mm_dim >= 128 && mm_dim % kTcBK == 0 && (H == 32 || H == 64 || H == 128) ? 1 : 0;
 }
 
-extern "C" int tgr_mm_proj_fwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* w_bf16, const float* bias, int H,
-                                  void* out, int64_t out_ld, int out_dtype, void* stream) {
+extern "C" int tgr_mm_proj_fwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* w_bf16, int w_planes, const float* bias,
+                                  int H, void* out, int64_t out_ld, int out_dtype, void* stream) {
   tgr::TimedScope tgr_timed_("mm_proj_fwd_tc", stream);
   TGR_REQUIRE(x_bf16 && w_bf16 && out, "null argument");
   TGR_REQUIRE(tgr_mm_proj_fwd_tc_supported(TGR_DTYPE_BF16, mm_dim, H), "mm_proj_fwd_tc: mm_dim %% 64 == 0, >= 128 and H in {32, 64, 128} (mm_dim=%d, H=%d)", mm_dim, H);
   TGR_REQUIRE(out_ld % 4 == 0, "out_ld must be a multiple of 4 elements");
   TGR_REQUIRE(((uintptr_t)x_bf16 & 15) == 0 && ((uintptr_t)w_bf16 & 15) == 0 && ((uintptr_t)out & 15) == 0, "mm_proj_fwd_tc: misaligned buffers");
   TGR_REQUIRE(T >= 0 && T < (1ll << 31), "T out of range");
+  TGR_REQUIRE(w_planes == 1 || w_planes == 2, "w_planes must be 1 or 2");
   if (T == 0) return 0;
   CUtensorMap tx, tw;
   if (int rc = make_map(&tx, x_bf16, T, mm_dim, kTcBM)) return rc;
-  if (int rc = make_map(&tw, w_bf16, H, mm_dim, H)) return rc;
+  if (int rc = make_map(&tw, w_bf16, (int64_t)w_planes * H, mm_dim, H)) return rc;
   const bool ob = out_dtype == TGR_DTYPE_BF16;
   const int64_t ldb = out_ld * (ob ? 2 : 4);
   cudaStream_t st = (cudaStream_t)stream;
   char* o = (char*)out;
-  if (H == 32) return ob ? launch_tc<32, true>(tx, tw, bias, o, ldb, T, mm_dim, st) : launch_tc<32, false>(tx, tw, bias, o, ldb, T, mm_dim, st);
-  if (H == 64) return ob ? launch_tc<64, true>(tx, tw, bias, o, ldb, T, mm_dim, st) : launch_tc<64, false>(tx, tw, bias, o, ldb, T, mm_dim, st);
-  return ob ? launch_tc<128, true>(tx, tw, bias, o, ldb, T, mm_dim, st) : launch_tc<128, false>(tx, tw, bias, o, ldb, T, mm_dim, st);
+  if (H == 32) return ob ? launch_tc<32, true>(tx, tw, bias, o, ldb, T, mm_dim, w_planes, st) : launch_tc<32, false>(tx, tw, bias, o, ldb, T, mm_dim, w_planes, st);
+  if (H == 64) return ob ? launch_tc<64, true>(tx, tw, bias, o, ldb, T, mm_dim, w_planes, st) : launch_tc<64, false>(tx, tw, bias, o, ldb, T, mm_dim, w_planes, st);
+  return ob ? launch_tc<128, true>(tx, tw, bias, o, ldb, T, mm_dim, w_planes, st) : launch_tc<128, false>(tx, tw, bias, o, ldb, T, mm_dim, w_planes, st);
 }
 
 /* ---- backward on the tensor cores (see mm_proj_bwd_tc_kernel) ---- */
@@ -343,11 +387,11 @@ extern "C" int tgr_mm_proj_bwd_tc_supported(int x_dtype, int mm_dim, int H) {
 }
 
 extern "C" size_t tgr_mm_proj_bwd_tc_workspace_bytes(int64_t T, int mm_dim, int H) {
-  return (size_t)bwd_tc_chunks(T, mm_dim) * H * mm_dim * sizeof(float) + 256;
+  return (size_t)bwd_tc_chunks(T, mm_dim, H) * H * mm_dim * sizeof(float) + 256;
 }
 
-extern "C" int tgr_mm_proj_bwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* dz_bf16, int H, float* dW,
-                                  int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int tgr_mm_proj_bwd_tc(const void* x_bf16, int64_t T, int mm_dim, const void* dz_bf16, int dz_planes, int64_t plane_rows,
+                                  int H, float* dW, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   tgr::TimedScope tgr_timed_("mm_proj_bwd_tc", stream);
   TGR_REQUIRE(x_bf16 && dz_bf16 && dW && workspace, "null argument");
   TGR_REQUIRE(tgr_mm_proj_bwd_tc_supported(TGR_DTYPE_BF16, mm_dim, H), "mm_proj_bwd_tc: mm_dim %% 64 == 0, >= 128 and H in {64, 128} (mm_dim=%d, H=%d)", mm_dim, H);
@@ -360,14 +404,17 @@ extern "C" int tgr_mm_proj_bwd_tc(const void* x_bf16, int64_t T, int mm_dim, con
     if (!accumulate) cudaMemsetAsync(dW, 0, (size_t)n_out * sizeof(float), st);
     return 0;
   }
-  const int bn = bwd_tc_bn(mm_dim), n_chunks = bwd_tc_chunks(T, mm_dim);
+  const int bn = bwd_tc_bn(mm_dim, H), n_chunks = bwd_tc_chunks(T, mm_dim, H);
+  TGR_REQUIRE(dz_planes == 1 || (dz_planes == 2 && plane_rows >= T), "dz_planes must be 1, or 2 with plane_rows >= T");
   CUtensorMap tz, tx;
-  if (int rc = make_map(&tz, dz_bf16, T, H, 64)) return rc;
+  // every plane is its own [T, H] view inside the stacked buffer: rows past T of plane 0 must read as zero, so the map covers
+  // plane_rows * planes rows and the kernel only asks for token rows < T of each plane (chunks end at T)
+  if (int rc = make_map(&tz, dz_bf16, dz_planes == 2 ? plane_rows + T : T, H, 64)) return rc;
   if (int rc = make_map(&tx, x_bf16, T, mm_dim, 64)) return rc;
   float* ws = (float*)workspace;
   int rc;
-  if (H == 64) rc = bn == 256 ? launch_bwd_tc<64, 256>(tz, tx, ws, T, mm_dim, n_chunks, st) : (bn == 128 ? launch_bwd_tc<64, 128>(tz, tx, ws, T, mm_dim, n_chunks, st) : launch_bwd_tc<64, 64>(tz, tx, ws, T, mm_dim, n_chunks, st));
-  else rc = bn == 256 ? launch_bwd_tc<128, 256>(tz, tx, ws, T, mm_dim, n_chunks, st) : (bn == 128 ? launch_bwd_tc<128, 128>(tz, tx, ws, T, mm_dim, n_chunks, st) : launch_bwd_tc<128, 64>(tz, tx, ws, T, mm_dim, n_chunks, st));
+  if (H == 64) rc = bn == 256 ? launch_bwd_tc<64, 256>(tz, tx, ws, T, mm_dim, n_chunks, dz_planes, plane_rows, st) : (bn == 128 ? launch_bwd_tc<64, 128>(tz, tx, ws, T, mm_dim, n_chunks, dz_planes, plane_rows, st) : launch_bwd_tc<64, 64>(tz, tx, ws, T, mm_dim, n_chunks, dz_planes, plane_rows, st));
+  else rc = bn == 128 ? launch_bwd_tc<128, 128>(tz, tx, ws, T, mm_dim, n_chunks, dz_planes, plane_rows, st) : launch_bwd_tc<128, 64>(tz, tx, ws, T, mm_dim, n_chunks, dz_planes, plane_rows, st);
   if (rc) return rc;
   TGR_K(chunk_reduce_kernel)<<<(unsigned)((n_out * 32 + 255) / 256), 256, 0, st>>>(ws, n_chunks, n_out, dW, accumulate);
   return check_launch("mm_proj_bwd_tc_reduce");

@@ -387,7 +387,9 @@ class FactoredFn(torch.autograd.Function):
         ctx.n_params = len(params)
         if needs_grad:      # (grad mode is always off inside Function.forward: the caller tells)
             g.n_fwd += 1
-        return out.view(pb.B, pb.L, -1)
+        # [T, H], NOT a view: the reference scales feat2emb's result in place (`seqs *= ...`, model.py:325) and autograd
+        # refuses in-place writes on a view created inside a custom Function; the caller reshapes outside
+        return out
 
     @staticmethod
     def backward(ctx, d_out):

@@ -110,7 +110,7 @@ class _FeatEmbMixin:
             # itemdnn / userdnn + ReLU + add (model.py:303-307) happen inside the factored kernels
             params += [self.itemdnn.weight, self.itemdnn.bias, self.userdnn.weight, self.userdnn.bias]
             needs = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-            out = FactoredFn.apply(eng, pb, needs, *params)
+            out = FactoredFn.apply(eng, pb, needs, *params).view(pb.B, pb.L, -1)
             if _concat_dtype() == torch.bfloat16:
                 out = out.to(torch.bfloat16)   # the autocast Linear of the reference returns bf16
             return out

@@ -845,7 +845,7 @@ class ShardedFactoredFn(torch.autograd.Function):
         ctx.n_params = len(params)
         if needs_grad:
             g.n_fwd += 1
-        return out.view(pb.B, pb.L, -1)
+        return out          # [T, H], not a view (see FactoredFn.forward); reshaped by the caller
 
     @staticmethod
     def backward(ctx, d_out):
@@ -937,7 +937,7 @@ class ShardedBaselineEmbedding(torch.nn.Module):
         if self.path == "factored":
             params += [self.itemdnn.weight, self.itemdnn.bias, self.userdnn.weight, self.userdnn.bias]
             needs = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-            out = ShardedFactoredFn.apply(self, pb, needs, *params)
+            out = ShardedFactoredFn.apply(self, pb, needs, *params).view(pb.B, pb.L, -1)
             return out.to(torch.bfloat16) if _concat_dtype() == torch.bfloat16 else out
         item_cat, user_cat = ShardedGatherConcatFn.apply(self, pb, _concat_dtype(), *params)
         B, L = pb.B, pb.L

@@ -33,7 +33,7 @@ def test_mm_proj_fwd_tc_matches_torch(T, mm_dim, H, out_bf16):
     assert torch.equal(Wb, W.to(torch.bfloat16))                      # RNE, bit-exact with torch's cast
     ld = H + 8                                                        # strided output rows (a slot of a wider buffer)
     out = torch.full((T, ld), -7.0, device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
-    _lib.check(lib.tgr_mm_proj_fwd_tc(x.data_ptr(), T, mm_dim, Wb.data_ptr(), b.data_ptr(), H, out.data_ptr(), ld,
+    _lib.check(lib.tgr_mm_proj_fwd_tc(x.data_ptr(), T, mm_dim, Wb.data_ptr(), 1, b.data_ptr(), H, out.data_ptr(), ld,
                                       _lib.DTYPE_BF16 if out_bf16 else _lib.DTYPE_F32, _stream()), "mm_proj_fwd_tc")
     torch.cuda.synchronize()
     ref = x.double() @ Wb.double().t() + b.double()                   # exact products of the bf16 operands
@@ -42,6 +42,15 @@ def test_mm_proj_fwd_tc_matches_torch(T, mm_dim, H, out_bf16):
     tol = 1e-2 if out_bf16 else 1e-5                                  # north_star: 1e-2 (bf16) / 1e-5 (fp32) of tensor scale
     assert (got - ref).abs().max().item() <= tol * scale
     assert torch.all(out[:, H:] == -7.0)                              # nothing written outside the slot
+    # two bf16 planes of W (hi + lo): the fp32 weights against the bf16-stored features, at the fp32 bar
+    W2 = torch.empty(2 * H, mm_dim, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.tgr_split_bf16(W.data_ptr(), W.numel(), W2.data_ptr(), W2.data_ptr() + 2 * W.numel(), _stream()), "split")
+    assert torch.equal(W2[:H], Wb) and torch.equal(W2[H:], (W - Wb.float()).to(torch.bfloat16))
+    out2 = torch.zeros((T, H), device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    _lib.check(lib.tgr_mm_proj_fwd_tc(x.data_ptr(), T, mm_dim, W2.data_ptr(), 2, b.data_ptr(), H, out2.data_ptr(), H,
+                                      _lib.DTYPE_BF16 if out_bf16 else _lib.DTYPE_F32, _stream()), "mm_proj_fwd_tc x2")
+    ref2 = x.double() @ W.double().t() + b.double()
+    assert (out2.double() - ref2).abs().max().item() <= tol * ref2.abs().max().item()
 
 
 @pytest.mark.parametrize("H", [32, 64])
@@ -108,13 +117,16 @@ def test_mm_proj_bwd_tc_matches_torch(T, mm_dim, H):
     dz = torch.randn(T, H, device="cuda", generator=g)
     dzb = torch.empty(T, H, device="cuda", dtype=torch.bfloat16)
     _lib.check(lib.tgr_cast_bf16(dz.data_ptr(), dz.numel(), dzb.data_ptr(), _stream()), "cast")
+    pr = (T + 63) // 64 * 64
+    dz2 = torch.zeros(2 * pr, H, device="cuda", dtype=torch.bfloat16)          # two planes, pad rows zero
+    _lib.check(lib.tgr_split_bf16(dz.data_ptr(), dz.numel(), dz2.data_ptr(), dz2.data_ptr() + 2 * pr * H, _stream()), "split")
     ws = torch.empty(lib.tgr_mm_proj_bwd_tc_workspace_bytes(T, mm_dim, H), dtype=torch.uint8, device="cuda")
     base = torch.randn(H, mm_dim, device="cuda", generator=g)
     outs = []
     for rep in range(2):
         dW = base.clone()
-        _lib.check(lib.tgr_mm_proj_bwd_tc(x.data_ptr(), T, mm_dim, dzb.data_ptr(), H, dW.data_ptr(), 1, ws.data_ptr(), ws.numel(),
-                                          _stream()), "mm_proj_bwd_tc")
+        _lib.check(lib.tgr_mm_proj_bwd_tc(x.data_ptr(), T, mm_dim, dzb.data_ptr(), 1, 0, H, dW.data_ptr(), 1, ws.data_ptr(),
+                                          ws.numel(), _stream()), "mm_proj_bwd_tc")
         torch.cuda.synchronize()
         outs.append(dW)
     assert torch.equal(outs[0], outs[1])
@@ -122,18 +134,24 @@ def test_mm_proj_bwd_tc_matches_torch(T, mm_dim, H):
     scale = ref.abs().max().item()
     assert (outs[0].double() - ref).abs().max().item() <= 1e-5 * scale
     dW = torch.full((H, mm_dim), 3.0, device="cuda")
-    _lib.check(lib.tgr_mm_proj_bwd_tc(x.data_ptr(), T, mm_dim, dzb.data_ptr(), H, dW.data_ptr(), 0, ws.data_ptr(), ws.numel(),
+    _lib.check(lib.tgr_mm_proj_bwd_tc(x.data_ptr(), T, mm_dim, dzb.data_ptr(), 1, 0, H, dW.data_ptr(), 0, ws.data_ptr(), ws.numel(),
                                       _stream()), "mm_proj_bwd_tc")
     ref0 = dzb.double().t() @ x.double()
     assert (dW.double() - ref0).abs().max().item() <= 1e-5 * ref0.abs().max().item()
+    # two planes of dz: the fp32 dz against the bf16-stored features at the fp32 bar
+    _lib.check(lib.tgr_mm_proj_bwd_tc(x.data_ptr(), T, mm_dim, dz2.data_ptr(), 2, pr, H, dW.data_ptr(), 0, ws.data_ptr(), ws.numel(),
+                                      _stream()), "mm_proj_bwd_tc x2")
+    ref2 = dz.double().t() @ x.double()
+    assert (dW.double() - ref2).abs().max().item() <= 1e-5 * ref2.abs().max().item()
 
 
 def test_factored_step_with_wide_bf16_mm_feature():
     """BASELINE.json config 3 in small: O1-style layout with mm features '81' (32-d) + '82' (1024-d) kept in bf16. The
     factored path runs '82' through the tcgen05 projection (forward) and the tcgen05 split-K GEMM (backward); results
-    against the torch oracle in fp64 on the SAME bf16-rounded mm inputs: north_star's 1e-2 bar for bf16, measured — as the
-    existing bf16-autocast test does — in relative Frobenius norm (a bf16-level perturbation of a pre-activation flips
-    ReLU masks of elements at ~0, which moves single gradient elements by a whole upstream value)."""
+    against the torch oracle in fp64 on the SAME bf16-rounded mm inputs. Weights and dz go through the tensor cores as two
+    bf16 planes (hi + lo), so the only bf16 rounding is the STORAGE of the frozen features: the results meet the fp32 bar
+    elementwise on outputs (1e-5 of tensor scale would need the third plane; 1e-4 is asserted) and 1e-2 — north_star's
+    bf16 bar — on every gradient, in relative Frobenius norm."""
     import types
 
     import numpy as np
@@ -177,8 +195,7 @@ def test_factored_step_with_wide_bf16_mm_feature():
     outs = [m.feat2emb_packed(pb) for pb in pbs]
     for c, (o, r) in enumerate(zip(outs, outs_ref)):
         r = r.detach().numpy()
-        assert np.abs(o.detach().cpu().numpy() - r).max() <= 1e-2 * np.abs(r).max(), f"out call {c}"
-        assert np.linalg.norm(o.detach().cpu().numpy() - r) <= 1e-2 * np.linalg.norm(r), f"out call {c} (Frobenius)"
+        assert np.abs(o.detach().cpu().numpy() - r).max() <= 1e-4 * np.abs(r).max(), f"out call {c}"
     torch.autograd.backward(outs, [torch.from_numpy(r).cuda() for r in st.upstream])
     torch.cuda.synchronize()
     for k, p in m.named_parameters():
@@ -186,4 +203,4 @@ def test_factored_step_with_wide_bf16_mm_feature():
         if gt is None or not gt.any():
             continue
         err = np.linalg.norm(p.grad.cpu().numpy().astype(np.float64) - gt) / max(np.linalg.norm(gt), 1e-30)
-        assert err <= 1.5e-2, f"grad {k}: relative Frobenius error {err:.3e}"
+        assert err <= 1e-2, f"grad {k}: relative Frobenius error {err:.3e}"
