@@ -664,6 +664,8 @@ def main():
     ap.add_argument("--no-lookahead", action="store_true", help="sharded path: no one-step-ahead key processing")
     ap.add_argument("--no-p2p", action="store_true", help="sharded factored path: fetch rows with the NCCL all-to-all "
                     "instead of reading the owners' shards in place over NVLink peer memory")
+    ap.add_argument("--no-symm-io", action="store_true", help="sharded path: counts / ids / dense gradients through NCCL "
+                    "collectives instead of the peer-memory transport")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks (debug)")
     ap.add_argument("--no-kernel-timing", action="store_true", help="no per-kernel CUDA events (debug)")
     ap.add_argument("--clock-period-ms", type=int, default=20)

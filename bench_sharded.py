@@ -61,6 +61,8 @@ def live_parity_check(args, rank: int, world: int, dev) -> dict:
             rk.ops.peers = [q.ops.local.data_ptr() for q in ranks]
             rk.ops.grad_win = w_
             rk.ops.grad_peers = [x.data_ptr() for x in wins]
+        from tencent_recommendation_2025_b200.sharded import emulate_io
+        emulate_io(ranks, 1 << 16)
     run_emulated([ranks[r].prefetch_gen(pbs_all[r]) for r in range(W)])
     exp_out = []
     for c in range(3):
@@ -137,7 +139,8 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     win_rows = max(1 << 20, int(n_max.item()) // 2)
     torch.manual_seed(0)                                   # identical dense parameters on every rank
     m = ShardedBaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.feat_types(), margs, rank, world,
-                                 path=args.path, p2p=not args.no_p2p, grad_window_rows=win_rows)
+                                 path=args.path, p2p=not args.no_p2p, grad_window_rows=win_rows,
+                                 max_step_entries=int(n_max.item()) + 1024, symm_io=not args.no_symm_io)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     with torch.no_grad():
         for p in m.parameters():
@@ -155,7 +158,7 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     lookups = [st.n_lookups() for st in steps_np]   # host-side row counting stays out of the timed regions
     # replicated dense parameters: their .grad tensors are views of ONE flat buffer, so the data-parallel
     # all-reduce is a single collective with no flatten / copy-back kernels
-    flat_grad = torch.zeros(sum(p.numel() for p in dense), device=dev)
+    flat_grad = m.symm_empty(sum(p.numel() for p in dense))      # symmetric memory when available: one-shot pull all-reduce
     o = 0
     for p in dense:
         p.grad = flat_grad[o:o + p.numel()].view_as(p)
@@ -171,10 +174,9 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
             m.prepare_next(next_pbs)
         outs = [m.feat2emb_packed(pb) for pb in pbs]
         torch.autograd.backward(outs, ups)
-        dist.all_reduce(flat_grad)
-        flat_grad.div_(world)
+        m.fused_step(**hyper)                    # row gradients to their owners, owners' AdamW row update
+        m.allreduce_dense_(flat_grad, pre_barrier=False)   # replicated dense parameters: mean over ranks (peer memory or NCCL)
         dense_opt.step()
-        m.fused_step(**hyper)
         if next_pbs is not None and not args.no_lookahead:
             m.finish_prepare()
         return outs
@@ -313,6 +315,9 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
                            "row_update": "fused sparse AdamW on the owner", "path": args.path,
                            "row_fetch": ("in place from the owners' shards over NVLink peer memory, fused into the projection kernel"
                                          if getattr(m.ops, "peers", None) is not None else "NCCL all-to-all of deduplicated rows"),
+                           "small_messages": ("counts / ids / dense gradients by peer-memory kernels + device-side barriers (no NCCL "
+                                              "collective in the step)" if getattr(m.ops, "io", None) is not None
+                                              else "NCCL all-gather / all-to-all / all-reduce"),
                            "grad_exchange": ("owners pull the bucketed gradient rows in place over NVLink peer memory inside the "
                                              "segmented reduce (+ one barrier)" if getattr(m.ops, "grad_peers", None) is not None
                                              else "NCCL all-to-all of locally reduced gradient rows"),

@@ -255,6 +255,22 @@ int tgr_permute_rows(const float* in, int H, const int32_t* perm, const int32_t*
 int tgr_gather_rows(const float* table, int H, const uint32_t* rows, const int32_t* n_dev, int64_t max_n, float* out,
                     void* stream);
 
+/* ---- peer-memory transport of the sharded exchange (csrc/tgr_symm.cu; no reference counterpart) -----------------------
+ * Small messages move by kernels that store to / load from the other ranks' symmetric-memory buffers over NVLink, ordered by
+ * device-side barriers: no NCCL collective and no host round trip on the step's critical path. All pointer arrays are HOST
+ * arrays of device pointers mapped into this process (own buffer included). */
+/* dst_bases[p][rank * n + i] = src[i] for every peer p: all-gather of one small int32 vector (per-owner counts) by stores. */
+int tgr_peer_put(void* const* dst_bases, int n_peers, int rank, const int32_t* src, int n, void* stream);
+/* dst = concat over s of src_ptrs[s][0 : counts[s]]: this owner's bucket out of every source's bucketed local-row list. */
+int tgr_peer_pull(const uint32_t* const* src_ptrs, const int64_t* counts, int n_peers, uint32_t* dst, void* stream);
+/* Stable n_buckets-way merge of sorted buckets stored back to back in `rows` (counts on the host): keys_out = merged keys,
+ * code_out = bucket << 24 | index inside the bucket (with_code) or the position in `rows`. Bit-identical to a stable sort by
+ * key of the concatenation (ties keep bucket order) — replaces the owner-side second radix sort. */
+int tgr_merge_buckets(const uint32_t* rows, const int64_t* counts, int n_buckets, int with_code, uint32_t* keys_out,
+                      uint32_t* code_out, void* stream);
+/* out[i] = scale * sum over r (ascending) of peers[r][i]: one-shot pull all-reduce of a small replicated buffer. */
+int tgr_allreduce_peers(const float* const* peers, int n_peers, int64_t n, float scale, float* out, void* stream);
+
 /* ---- factored path: the item/user DNN applied to DEDUPLICATED rows -----------------
  * model.py:302-307 computes out = relu(itemdnn(cat(item slots))) + relu(userdnn(cat(user slots))); a Linear over
  * a concat is a sum of per-slot H x H blocks applied to the slot's row, and every table feeds exactly one slot

@@ -24,6 +24,7 @@
 #include "tgr_mma.cuh"
 #include "tgr_rows.cuh"
 #include "tgr_tc.cuh"
+#include "tgr_fact_params.cuh"
 
 #include <stdlib.h>
 
@@ -33,20 +34,6 @@ constexpr int kFT = 256;          // threads per CTA
 constexpr int kRowsGridFwd = 6 * kNumSMs;   // H = 64: 35 KB smem, 64 threads x 163 regs -> 6 CTAs / SM
 constexpr int kRowsGridBwd = 4 * kNumSMs;   // H = 64: 52 KB smem, 64 threads x 225 regs -> 4 CTAs / SM
 
-struct FactParams {
-  const float* w[TGR_MAX_TABLES];       // table rows
-  uint32_t key_base[TGR_MAX_TABLES + 1];
-  int32_t col[TGR_MAX_TABLES];          // first DNN-input column of the table's slot
-  int8_t side[TGR_MAX_TABLES];          // which DNN the table's slot feeds
-  const float* dnn_w[2];                // itemdnn.weight [H, item_dim], userdnn.weight [H, user_dim]
-  int64_t dnn_ld[2];
-  const float* fetched;                 // row-sharded tables: rows of this step fetched from their owners, or NULL
-  const int32_t* fetched_perm;          // row of unique key u = fetched[fetched_perm[u]] (NULL: fetched[u])
-  const float* peer[TGR_MAX_PEERS];     // row-sharded tables read in place over NVLink: shard of owner r (peer memory)
-  int32_t n_peers;                      // > 0: row(key) = peer[key % n_peers][key / n_peers]
-  float* save_rows;                     // MODE 0: also keep the raw rows, [U, H] (the backward's dW needs them again)
-  int32_t n_tables;
-};
 
 // 16-byte global -> shared copy that bypasses the register file (LDGSTS); src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -1133,6 +1120,7 @@ extern "C" int tgr_fact_project_rows(const tgr_table_t* tables, int n_tables, in
   TGR_REQUIRE(uniq && n_unique_dev && P, "null argument");
   if (max_unique <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (rows_use_mma(H) && rows_ws_supported(H)) return launch_rows_ws_fwd(p, uniq, n_unique_dev, P, st);
   if (rows_use_tc(H)) {
     if (H == 32) return launch_rows_tc<32>(p, uniq, n_unique_dev, P, st);
     return launch_rows_tc<64>(p, uniq, n_unique_dev, P, st);
@@ -1164,6 +1152,13 @@ extern "C" int tgr_fact_unique_backward(const tgr_table_t* tables, int n_tables,
   float* part = (float*)workspace;
   int rc;
   const bool mma = rows_use_mma(H);
+  if (mma && rows_ws_supported(H)) {     // warp-specialised tcgen05 kernel (tgr_rows_ws.cu), 96-row tiles, one CTA per SM
+    if (int rc2 = launch_rows_ws_bwd(p, uniq, n_unique_dev, G, part, st)) return rc2;
+    if (dW_item == nullptr && dW_user == nullptr) return 0;
+    const dim3 grid_ws(n_tables, H * H / 64);
+    TGR_K(fact_dw_reduce_kernel<64, 96, 1>)<<<grid_ws, kFT, 0, st>>>(p, uniq, n_unique_dev, part, rows_ws_bwd_grid(), dW_item, dW_user);
+    return check_launch("fact_dw_reduce");
+  }
   if (mma) rc = H == 32 ? launch_rows_mma<32, 1>(p, uniq, n_unique_dev, G, part, st) : launch_rows_mma<64, 1>(p, uniq, n_unique_dev, G, part, st);
   else if (H == 32) rc = launch_rows<32, 1>(p, uniq, n_unique_dev, G, part, st);
   else if (H == 64) rc = launch_rows<64, 1>(p, uniq, n_unique_dev, G, part, st);

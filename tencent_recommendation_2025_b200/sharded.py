@@ -60,6 +60,34 @@ def tables_from_shards(layout: FeatureLayout, shards: Sequence[torch.Tensor]) ->
 
 
 # ----------------------------------------------------------------------------------------------------
+# peer-memory transport of the small messages (counts, bucketed local-row ids, dense gradients)
+# ----------------------------------------------------------------------------------------------------
+class SymmIO:
+    """Symmetric-memory mailboxes of one rank (csrc/tgr_symm.cu). ``gather[q]`` [W*W] int32 receives every rank's per-owner
+    counts (rank s stores its row into slot s of every peer), ``rows[q]`` holds this rank's bucketed local-row ids where the
+    owners pull their bucket from; q alternates per prepared step (the look-ahead prepares step k+1 while step k's buffers
+    are still being read). ``*_peers[q][r]`` = device pointer of rank r's buffer in this process' address space."""
+
+    def __init__(self, W: int, rank: int, gather, rows, gather_peers, rows_peers, barrier=None):
+        self.W, self.rank = W, rank
+        self.gather, self.rows = gather, rows
+        self.gather_peers, self.rows_peers = gather_peers, rows_peers
+        self.barrier = barrier          # callable or None (emulated ranks: stream order is the barrier)
+        self.parity = 0
+
+
+def emulate_io(ranks, rows_cap: int):
+    """W emulated ranks in one process: plain tensors stand in for the symmetric buffers, every rank sees the others'."""
+    W = len(ranks)
+    dev = ranks[0].ops.local.device
+    gather = [[torch.zeros(W * W, dtype=torch.int32, device=dev) for _ in range(2)] for _ in range(W)]
+    rows = [[torch.zeros(rows_cap, dtype=torch.int32, device=dev) for _ in range(2)] for _ in range(W)]
+    for r, rk in enumerate(ranks):
+        rk.ops.io = SymmIO(W, r, gather[r], rows[r], [[gather[s][q].data_ptr() for s in range(W)] for q in range(2)],
+                           [[rows[s][q].data_ptr() for s in range(W)] for q in range(2)])
+
+
+# ----------------------------------------------------------------------------------------------------
 # local compute (product = CUDA kernels through the C ABI)
 # ----------------------------------------------------------------------------------------------------
 class CudaShardOps:
@@ -79,6 +107,7 @@ class CudaShardOps:
         self._ws: Dict[str, torch.Tensor] = {}
         self.launches = 0
         self.step = 0
+        self.io: Optional[SymmIO] = None      # peer-memory mailboxes (set by ShardedBaselineEmbedding / emulate_io)
         self._eng = _KeyEngine(layout, dev)
 
     def _buf(self, name, nbytes, dev):
@@ -104,9 +133,15 @@ class CudaShardOps:
         self.launches += 12
         return uniq, n_unique, cap
 
-    def route(self, uniq, n_unique, cap):
+    def route(self, uniq, n_unique, cap, out_rows: Optional[torch.Tensor] = None):
         dev = uniq.device
-        rows = torch.empty(cap, dtype=torch.int32, device=dev)
+        if out_rows is not None:
+            if out_rows.numel() < cap:
+                raise ValueError(f"the step has up to {cap} unique rows, the symmetric id buffer holds {out_rows.numel()}: "
+                                 "raise max_step_entries")
+            rows = out_rows[:cap]
+        else:
+            rows = torch.empty(cap, dtype=torch.int32, device=dev)
         perm = torch.empty(cap, dtype=torch.int32, device=dev)
         counts = torch.zeros(self.W, dtype=torch.int32, device=dev)
         ws = self._buf("route", self.lib.tgr_route_workspace_bytes(cap, self.W), dev)
@@ -114,6 +149,45 @@ class CudaShardOps:
                                         counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "tgr_route_bucket")
         self.launches += 3
         return rows, perm, counts
+
+    # -- peer-memory transport (csrc/tgr_symm.cu) ------------------------------------------------------
+    def io_put_counts(self, counts: torch.Tensor, q: int):
+        """This rank's per-owner counts into slot `rank` of every peer's gather buffer (all-gather by stores)."""
+        io = self.io
+        ptrs = (C.c_void_p * io.W)(*io.gather_peers[q])
+        check(self.lib.tgr_peer_put(ptrs, io.W, io.rank, counts.data_ptr(), io.W, _stream()), "tgr_peer_put")
+        self.launches += 1
+
+    def io_pull_ids(self, M: List[List[int]], q: int) -> torch.Tensor:
+        """This owner's bucket out of every source's bucketed id list (M[s][o] = rows source s sends to owner o)."""
+        io = self.io
+        W, me = io.W, io.rank
+        cnt = [M[s][me] for s in range(W)]
+        R = sum(cnt)
+        out = torch.empty(max(R, 1), dtype=torch.int32, device=self.local.device)
+        if R:
+            srcs = (C.c_void_p * W)(*[io.rows_peers[q][s] + 4 * sum(M[s][:me]) for s in range(W)])
+            cnts = (C.c_int64 * W)(*cnt)
+            check(self.lib.tgr_peer_pull(srcs, cnts, W, out.data_ptr(), _stream()), "tgr_peer_pull")
+            self.launches += 1
+        return out[:R]
+
+    def merge_owner(self, recv_rows: torch.Tensor, recv_counts: Sequence[int], with_code: bool):
+        """Owner-side order of the received ids: a stable W-way merge of the per-source buckets (each is sorted) — the same
+        result as the stable radix sort it replaces, in one launch and without the torch index arithmetic."""
+        R = int(sum(recv_counts))
+        if R == 0:
+            return None
+        if max(recv_counts) >= (1 << 24):
+            raise ValueError("more than 2^24 received contributions from one source in one step")
+        dev = self.local.device
+        keys_out = torch.empty(R, dtype=torch.int32, device=dev)
+        code_out = torch.empty(R, dtype=torch.int32, device=dev)
+        cnts = (C.c_int64 * len(recv_counts))(*[int(c) for c in recv_counts])
+        check(self.lib.tgr_merge_buckets(recv_rows.data_ptr(), cnts, len(recv_counts), 1 if with_code else 0, keys_out.data_ptr(),
+                                         code_out.data_ptr(), _stream()), "tgr_merge_buckets")
+        self.launches += 1
+        return keys_out, code_out
 
     def gather(self, rows: torch.Tensor, n: int) -> torch.Tensor:
         dev = self.local.device
@@ -262,10 +336,13 @@ class CudaShardOps:
             self.launches += 2
         return grads
 
-    def prepare_owner(self, recv_rows: torch.Tensor, R: int):
-        """Owner side, done during the forward: stable sort of the requested local rows (source-rank order kept)."""
+    def prepare_owner(self, recv_rows: torch.Tensor, R: int, recv_counts: Optional[Sequence[int]] = None):
+        """Owner side, done during the forward: stable order of the requested local rows (source-rank order kept) — by
+        merging the per-source buckets when their sizes are known, else by a stable sort."""
         if R == 0:
             return None
+        if recv_counts is not None and R <= (1 << 24):
+            return self.merge_owner(recv_rows, recv_counts, with_code=False)
         if R > (1 << 24):
             raise ValueError("more than 2^24 received contributions in one step")
         dev = self.local.device
@@ -418,13 +495,16 @@ class FactShardOps(CudaShardOps):
                 g.keep = (st["rows_buf"], st["perm"])
         return self.feng.fact_forward(g, pb)
 
-    def prepare_owner(self, recv_rows: torch.Tensor, R: int, counts_dev: Optional[torch.Tensor] = None):
-        """Owner side, done ahead: stable sort of the requested local rows. With the gradient window the payload of
+    def prepare_owner(self, recv_rows: torch.Tensor, R: int, counts_dev: Optional[torch.Tensor] = None,
+                      recv_counts: Optional[Sequence[int]] = None):
+        """Owner side, done ahead: stable order of the requested local rows. With the gradient window the payload of
         an entry is `source rank << 24 | index inside that source's bucket` (where the owner will pull the row from)."""
         if self.grad_peers is None or counts_dev is None:
-            return super().prepare_owner(recv_rows, R)
+            return super().prepare_owner(recv_rows, R, recv_counts)
         if R == 0:
             return None
+        if recv_counts is not None:
+            return self.merge_owner(recv_rows, recv_counts, with_code=True)
         dev = self.local.device
         cnt = counts_dev.to(torch.int64)
         src_rank = torch.repeat_interleave(torch.arange(self.W, device=dev), cnt, output_size=R)
@@ -564,6 +644,19 @@ class ShardedRank:
     def prepare_gen(self, pbs: List[PackedBatch]) -> Generator:
         ops = self.ops
         pf = ops.prepare(list(pbs))
+        io = getattr(ops, "io", None) if getattr(ops, "grad_peers", None) is not None else None
+        if io is not None:
+            # peer-memory transport: ids go into this rank's symmetric buffer (owners pull their bucket later), the counts
+            # are stored into every peer's gather buffer; one device-side barrier, no NCCL
+            q = io.parity
+            io.parity ^= 1
+            rows_b, perm, counts = ops.route(pf["uniq"], pf["n_unique"], pf["cap"], out_rows=io.rows[q])
+            ops.io_put_counts(counts, q)
+            yield ("symm_barrier",)
+            M = io.gather[q].view(self.W, self.W)
+            host = self._to_host_async(M)
+            self.prep = {"pbs": list(pbs), "pf": pf, "rows_b": rows_b, "perm": perm, "host": host, "stage": 1, "M": M, "io_q": q}
+            return None
         rows_b, perm, counts = ops.route(pf["uniq"], pf["n_unique"], pf["cap"])
         if getattr(ops, "grad_peers", None) is not None:
             # the owner will PULL gradient rows out of every source's window: it needs the whole W x W count matrix
@@ -601,11 +694,18 @@ class ShardedRank:
         else:
             send_counts, recv_counts = h[0].tolist(), h[1].tolist()
         U, R = sum(send_counts), sum(recv_counts)
-        recv_rows = yield ("a2a_v", p["rows_b"][:U], send_counts, recv_counts)
-        if window:
-            owner_state = ops.prepare_owner(recv_rows, R, counts_dev=p["M"][:, self.rank])
+        if "io_q" in p:
+            # behind this barrier every owner's previous row update is complete (it is enqueued after fused_step on every
+            # rank) and every source's bucketed ids are in place: the owners pull their buckets, nobody waits on the host
+            yield ("symm_barrier",)
+            recv_rows = ops.io_pull_ids(p["M_host"], p["io_q"])
+            p["synced"] = True
         else:
-            owner_state = ops.prepare_owner(recv_rows, R)
+            recv_rows = yield ("a2a_v", p["rows_b"][:U], send_counts, recv_counts)
+        if window:
+            owner_state = ops.prepare_owner(recv_rows, R, counts_dev=p["M"][:, self.rank], recv_counts=recv_counts)
+        else:
+            owner_state = ops.prepare_owner(recv_rows, R, recv_counts=recv_counts)
         if hasattr(ops, "remap_all"):
             ops.remap_all(p["pf"], p["perm"])
         p.update(send_counts=send_counts, recv_counts=recv_counts, U=U, R=R, recv_rows=recv_rows, owner=owner_state, stage=2,
@@ -632,7 +732,9 @@ class ShardedRank:
             # The decision must be the same on EVERY rank (a barrier is a collective): it is taken from the all-gathered
             # W x W count matrix when the step has one, else the barrier is always issued.
             M = p.get("M_host")
-            if M is None or any(c == 0 for row in M for c in row):
+            if p.get("synced"):
+                pass                                      # the peer-memory id exchange ended with a device-side barrier
+            elif M is None or any(c == 0 for row in M for c in row):
                 yield ("barrier", ops._bar)
             ops.fetch_rows_async(p["pf"])
             back = None
@@ -693,7 +795,7 @@ class ShardedRank:
                 # reduction pulls its contributions over NVLink. The window is next written a whole step later, after
                 # the following id all-to-all — which every owner enqueues behind this update.
                 ops.permute_to_window(grads, st["perm"], st["pf"]["n_unique"], st["pf"]["cap"])
-                yield ("barrier", ops._bar)
+                yield (("symm_barrier",) if getattr(ops, "io", None) is not None else ("barrier", ops._bar))
                 ops.apply_from_peers(st["owner"], st["starts"], st["R"], hyper)
             else:
                 gb = ops.permute(grads, st["perm"], st["pf"]["n_unique"], st["pf"]["cap"])
@@ -723,8 +825,9 @@ class ShardedRank:
         return U
 
 
-def run_distributed(gen: Generator, group=None):
-    """Drive one rank's generator with torch.distributed collectives (NCCL on GPUs, gloo on CPU)."""
+def run_distributed(gen: Generator, group=None, symm_barrier=None):
+    """Drive one rank's generator with torch.distributed collectives (NCCL on GPUs, gloo on CPU). ``symm_barrier``: the
+    device-side barrier of the peer-memory transport (signal pads of the symmetric allocation)."""
     import torch.distributed as dist
     pg = group if group is not None else dist.group.WORLD
     try:
@@ -732,7 +835,10 @@ def run_distributed(gen: Generator, group=None):
         while True:
             # straight to the ProcessGroup (the torch.distributed wrappers cost 50-75 us of host time per call);
             # wait() only orders the current stream behind the collective, the host does not block
-            if req[0] == "barrier":
+            if req[0] == "symm_barrier":
+                symm_barrier()
+                out = None
+            elif req[0] == "barrier":
                 pg.allreduce([req[1]]).wait()
                 out = None
             elif req[0] == "allgather":
@@ -773,7 +879,7 @@ def run_emulated(gens: List[Generator]):
         kind = reqs[0][0]
         assert all(r[0] == kind for r in reqs), "ranks diverged"
         outs = []
-        if kind == "barrier":
+        if kind in ("barrier", "symm_barrier"):
             outs = [None] * W
         elif kind == "allgather":
             full = torch.stack([reqs[s][1] for s in range(W)])
@@ -871,7 +977,8 @@ class ShardedBaselineEmbedding(torch.nn.Module):
     to all-reduce, as in any data-parallel run). Row updates are always fused (``fused_step``)."""
 
     def __init__(self, user_num, item_num, feat_statistics, feat_types, args, rank: int, world_size: int, group=None,
-                 path: str = "concat", p2p: bool = True, grad_window_rows: int = 1 << 20):
+                 path: str = "concat", p2p: bool = True, grad_window_rows: int = 1 << 20, max_step_entries: int = 1 << 22,
+                 symm_io: bool = True):
         super().__init__()
         if path not in ("concat", "factored"):
             raise ValueError("path must be 'concat' or 'factored'")
@@ -903,8 +1010,82 @@ class ShardedBaselineEmbedding(torch.nn.Module):
                 self._win_views = [self._symm_win.get_buffer(r, tuple(win.shape), torch.float32) for r in range(world_size)]
                 self.ops.grad_win = win
                 self.ops.grad_peers = [t.data_ptr() for t in self._win_views]
+                if symm_io:
+                    self._setup_symm_io(args.device, world_size, group, int(max_step_entries))
         self.rank_state = ShardedRank(lay, self.ops, rank, world_size)
-        self._run = lambda gen: run_distributed(gen, self.group)
+        self._run = lambda gen: run_distributed(gen, self.group, self._symm_barrier)
+
+    def _setup_symm_io(self, device, W: int, group, rows_cap: int):
+        """Mailboxes of the peer-memory transport: ONE symmetric allocation [2 x (W*W counts) | 2 x rows_cap ids] (int32)."""
+        n_g = (W * W + 63) // 64 * 64
+        n_r = (rows_cap + 63) // 64 * 64
+        buf, hdl = self._alloc_symm((2 * n_g + 2 * n_r,), torch.int32, device, W, group)
+        if hdl is None:
+            return
+        self._io_buf, self._io_hdl = buf, hdl
+        views = [hdl.get_buffer(r, (2 * n_g + 2 * n_r,), torch.int32) for r in range(W)]
+        self._io_views = views
+        base = [v.data_ptr() for v in views]
+        gather = [buf[q * n_g: q * n_g + W * W] for q in range(2)]
+        rows = [buf[2 * n_g + q * n_r: 2 * n_g + (q + 1) * n_r] for q in range(2)]
+        self.ops.io = SymmIO(W, self.rank, gather, rows,
+                             [[b + 4 * q * n_g for b in base] for q in range(2)],
+                             [[b + 4 * (2 * n_g + q * n_r) for b in base] for q in range(2)])
+
+    def _symm_barrier(self):
+        """Device-side barrier over the signal pads of the mailbox allocation (blocks the current stream, not the host)."""
+        self._io_hdl.barrier(channel=0)
+
+    @staticmethod
+    def _alloc_symm(shape, dtype, device, world_size: int, group):
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(shape, dtype=dtype, device=torch.device(device))
+            hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            t.zero_()
+            return t, hdl
+        except Exception as e:
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({e}); falling back to NCCL collectives")
+            return None, None
+
+    # -- replicated dense parameters: one-shot pull all-reduce over peer memory --------------------------------------
+    def symm_empty(self, n: int) -> torch.Tensor:
+        """A zeroed fp32 buffer of n elements (padded to a multiple of 4) every rank can read over NVLink — allocate the
+        flat gradient buffer of the replicated parameters here and ``allreduce_dense_`` needs no NCCL collective."""
+        n4 = (int(n) + 3) // 4 * 4
+        if getattr(self.ops, "io", None) is not None:
+            t, hdl = self._alloc_symm((n4,), torch.float32, self.dev, self.W, self.group)
+            if hdl is not None:
+                self._dense = (t, hdl, [hdl.get_buffer(r, (n4,), torch.float32) for r in range(self.W)],
+                               torch.empty(n4, dtype=torch.float32, device=self.dev))
+                return t
+        self._dense = None
+        return torch.zeros(n4, dtype=torch.float32, device=self.dev)
+
+    def allreduce_dense_(self, flat: torch.Tensor, average: bool = True, pre_barrier: bool = True) -> torch.Tensor:
+        """flat <- (mean | sum) over ranks, in place: one kernel in which every rank adds the W buffers in rank order
+        (csrc/tgr_symm.cu; identical result everywhere) between two device-side barriers — every rank's backward is complete
+        before anybody reads, every rank has read before anybody overwrites its own buffer. ``pre_barrier=False`` when the call
+        follows ``fused_step`` of the same step (the barrier that orders the gradient windows there already orders the
+        finished backward). Without symmetric memory: NCCL all-reduce."""
+        import torch.distributed as dist
+        d = getattr(self, "_dense", None)
+        if d is None or d[0].data_ptr() != flat.data_ptr():
+            dist.all_reduce(flat, group=self.group)
+            if average:
+                flat.div_(self.W)
+            return flat
+        t, hdl, views, tmp = d
+        if pre_barrier:
+            hdl.barrier(channel=0)
+        ptrs = (C.c_void_p * self.W)(*[v.data_ptr() for v in views])
+        check(self.ops.lib.tgr_allreduce_peers(ptrs, self.W, t.numel(), 1.0 / self.W if average else 1.0, tmp.data_ptr(), _stream()),
+              "tgr_allreduce_peers")
+        hdl.barrier(channel=0)          # every rank has read every buffer before anybody overwrites its own
+        flat.copy_(tmp)
+        return flat
 
     @staticmethod
     def _alloc_shard(n_local: int, H: int, device, world_size: int, group, want_p2p: bool):

@@ -133,7 +133,7 @@ class NumpyShardOps:
         g[:uniq.size] = rows.astype(np.float32)
         return torch.from_numpy(g)
 
-    def prepare_owner(self, recv_rows, R):
+    def prepare_owner(self, recv_rows, R, recv_counts=None):
         return recv_rows.clone()
 
     def apply_cached(self, owner_state, recv_grads, R, hyper):
@@ -170,7 +170,7 @@ class NumpyPeerShardOps(NumpyShardOps):
         ident = torch.arange(pf["cap"], dtype=torch.int32)
         return self.forward_from_rows(pb, pf["uniq"], pf["n_unique"], ident, pf["rows_sorted"], out_dtype)
 
-    def prepare_owner(self, recv_rows, R, counts_dev=None):
+    def prepare_owner(self, recv_rows, R, counts_dev=None, recv_counts=None):
         if counts_dev is None:
             return super().prepare_owner(recv_rows, R)
         cnt = counts_dev.numpy().astype(np.int64)

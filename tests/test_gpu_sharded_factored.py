@@ -48,6 +48,8 @@ def setup(W, B=16, L=33, H=64, seed=3, p2p=False):
             rk.ops.peers = list(ptrs)
             rk.ops.grad_win = w_
             rk.ops.grad_peers = [x.data_ptr() for x in wins]
+        from tencent_recommendation_2025_b200.sharded import emulate_io
+        emulate_io(ranks, 1 << 16)      # counts / ids through the peer-memory mailboxes (tgr_peer_put / _pull / merge)
     steps = [world.make_step(r) for r in range(W)]                       # rank r's data-parallel share
     pbs = [[to_device(lay, pc, "cuda") for pc in st.calls] for st in steps]
     return cfg, full, lay, ranks, steps, pbs

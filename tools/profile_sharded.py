@@ -23,7 +23,7 @@ opt = torch.optim.AdamW(dense, lr=1e-3, betas=(0.9, 0.98), fused=True)
 st = w.make_step(1000 * rank)
 pbs = [to_device(lay, pc, dev) for pc in st.calls]; ups = [torch.from_numpy(r).to(dev) for r in st.upstream]
 
-flat_grad = torch.zeros(sum(p.numel() for p in dense), device=dev)
+flat_grad = m.symm_empty(sum(p.numel() for p in dense))
 o = 0
 for p in dense:
     p.grad = flat_grad[o:o + p.numel()].view_as(p); o += p.numel()
@@ -35,9 +35,9 @@ def step():
     if LOOK: m.prepare_next(pbs)
     outs = [m.feat2emb_packed(pb) for pb in pbs]
     torch.autograd.backward(outs, ups)
-    dist.all_reduce(flat_grad); flat_grad.div_(world)
-    opt.step()
     m.fused_step(lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
+    m.allreduce_dense_(flat_grad)
+    opt.step()
     if LOOK: m.finish_prepare()
 
 for _ in range(4): step()
