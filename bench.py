@@ -358,54 +358,78 @@ def run_gpu(args):
                 "reference_dataflow_frac_of_hbm_peak": round((alg_f + alg_b) / (ms * 1e-3) / 1e9 / hbm_peak, 4)}
 
     # ---- end to end from host buffers (e2e): pinned host batches -> copy stream -> step -> loss read back ----------
-    host_steps = [[stage_pinned(lay, pc, mm_dtype) for pc in st.calls] for st in steps_np]   # as a pin_memory DataLoader would
-    e2e_steps = max(3, min(args.steps, 20))
-    e2e_warm = n_batches + 1
-    feeder = HostPrefetcher(dev)
-    loss_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
-    loss_ev = [None, None]
-    h2d = d2h = 0
-    rows_e2e = 0
-    losses = []
-    feeder.submit(host_steps[0])
-    torch.cuda.synchronize()
-    t0 = None
-    for i in range(e2e_warm + e2e_steps):
-        k = i % n_batches
-        if i == e2e_warm:
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-        pbs = feeder.take()                                        # waits (on the stream) for this step's H2D copies
-        feeder.submit(host_steps[(i + 1) % n_batches])             # next step's copies overlap this step's kernels
-        outs = one_step(pbs, dev_steps[k][1])
+    def e2e_loop(feeder, host_steps, entry):
+        e2e_steps = max(3, min(args.steps, 20))
+        e2e_warm = n_batches + 1
+        loss_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+        loss_ev = [None, None]
+        h2d = d2h = 0
+        rows_e2e = 0
+        losses = []
+        feeder.submit(host_steps[0])
+        torch.cuda.synchronize()
+        t0 = None
+        for i in range(e2e_warm + e2e_steps):
+            k = i % n_batches
+            if i == e2e_warm:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            pbs = feeder.take()                                        # waits (on the stream) for this step's H2D copies
+            feeder.submit(host_steps[(i + 1) % n_batches])             # next step's copies overlap this step's kernels
+            outs = one_step(pbs, dev_steps[k][1])
+            feeder.retire()
+            with torch.no_grad():
+                loss = sum(o.detach().sum() for o in outs)
+            slot = i & 1
+            if loss_ev[slot] is not None:                              # step i-2's loss has long arrived: read it
+                loss_ev[slot].synchronize()
+                losses.append(float(loss_host[slot]))
+            loss_host[slot:slot + 1].copy_(loss.reshape(1), non_blocking=True)   # D2H of the step's result
+            loss_ev[slot] = torch.cuda.Event()
+            loss_ev[slot].record()
+            if i >= e2e_warm:
+                rows_e2e += lookups[k]
+                h2d += sum(pb.h2d_bytes for pb in pbs)
+                d2h += 4
+        for slot in ((e2e_warm + e2e_steps) & 1, (e2e_warm + e2e_steps + 1) & 1):
+            if loss_ev[slot] is not None:
+                loss_ev[slot].synchronize()
+                losses.append(float(loss_host[slot]))
+        torch.cuda.synchronize()
+        t = time.perf_counter() - t0
+        feeder.take()   # drain the look-ahead submission
         feeder.retire()
-        with torch.no_grad():
-            loss = sum(o.detach().sum() for o in outs)
-        slot = i & 1
-        if loss_ev[slot] is not None:                              # step i-2's loss has long arrived: read it
-            loss_ev[slot].synchronize()
-            losses.append(float(loss_host[slot]))
-        loss_host[slot:slot + 1].copy_(loss.reshape(1), non_blocking=True)   # D2H of the step's result
-        loss_ev[slot] = torch.cuda.Event()
-        loss_ev[slot].record()
-        if i >= e2e_warm:
-            rows_e2e += lookups[k]
-            h2d += sum(pb.h2d_bytes for pb in pbs)
-            d2h += 4
-    for slot in ((e2e_warm + e2e_steps) & 1, (e2e_warm + e2e_steps + 1) & 1):
-        if loss_ev[slot] is not None:
-            loss_ev[slot].synchronize()
-            losses.append(float(loss_host[slot]))
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    feeder.take()   # drain the look-ahead submission
-    feeder.retire()
-    e2e = {"value": rows_e2e / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps,
-           "d2h_bytes_per_step": d2h // e2e_steps, "ms_per_step": round(t_e2e / e2e_steps * 1e3, 3),
-           "entry": "BaselineEmbedding.prefetch + feat2emb_packed x3 + backward + fused_step from pinned host packed "
-                    "buffers; H2D of step k+1 on a copy stream overlaps step k, every step's loss is copied back and "
-                    "read on the host (two steps later, so the read never stalls the queue); wall clock",
-           "loss_finite": bool(np.all(np.isfinite(losses)))}
+        return {"value": rows_e2e / t, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps,
+                "d2h_bytes_per_step": d2h // e2e_steps, "ms_per_step": round(t / e2e_steps * 1e3, 3), "entry": entry,
+                "loss_finite": bool(np.all(np.isfinite(losses)))}, t / e2e_steps
+
+    host_steps = [[stage_pinned(lay, pc, mm_dtype) for pc in st.calls] for st in steps_np]   # as a pin_memory DataLoader would
+    feeder = HostPrefetcher(dev)
+    e2e_packed, t_e2e_step = e2e_loop(
+        feeder, host_steps,
+        "BaselineEmbedding.prefetch + feat2emb_packed x3 + backward + fused_step from pinned host PACKED buffers (every "
+        "token's feature ids and mm vectors cross PCIe); H2D of step k+1 on a copy stream overlaps step k, every step's loss "
+        "is copied back and read on the host (two steps later, so the read never stalls the queue); wall clock")
+    e2e = e2e_packed
+    e2e_resident = None
+    if args.resident_items == "on" or (args.resident_items == "auto" and args.config in ("c1", "c2")):
+        # item features resident in HBM (they are functions of the item id, dataset.py:159,260-263): the host hands over
+        # ids + user tokens only, the packed calls are rebuilt on the device (resident.py, csrc/tgr_resident.cu)
+        from tencent_recommendation_2025_b200.resident import ResidentFeeder, ResidentItemFeatures
+        try:
+            store = ResidentItemFeatures.from_world(worldgen, dev, mm_dtype)
+            slim_steps = [[store.slim(pc) for pc in st.calls] for st in steps_np]
+            e2e_resident, t_e2e_step = e2e_loop(
+                ResidentFeeder(store), slim_steps,
+                "the same step fed from pinned host buffers holding ids + user tokens only: the item-side feature table "
+                f"[{store.n_items}, {store.feat_dev.shape[1]}] and mm tables are resident in HBM and the packed calls are expanded on "
+                "the device (ResidentItemFeatures / ResidentFeeder); H2D on a copy stream one step ahead, loss read back every "
+                "step; wall clock")
+            e2e = e2e_resident
+            del store
+        except Exception as exc:   # e.g. not enough host memory for the table build: keep the packed-feed number
+            e2e_resident = {"error": repr(exc)}
+    e2e_steps = 1
 
     # ---- the reference itself, beside the number: on the box's host cores and as torch eager on this GPU -----------
     cpu = None
@@ -420,7 +444,7 @@ def run_gpu(args):
             gpu_eager = gpu_eager_reference(cfg, dev)
             gpu_eager["ours_over_eager_device"] = round(gpu_eager["device_ms_per_step"] / (ms / args.steps), 2) \
                 if "device_ms_per_step" in gpu_eager else None
-            gpu_eager["ours_e2e_over_eager_wall"] = round(gpu_eager["wall_ms_per_step"] / (t_e2e / e2e_steps * 1e3), 2) \
+            gpu_eager["ours_e2e_over_eager_wall"] = round(gpu_eager["wall_ms_per_step"] / (t_e2e_step * 1e3), 2) \
                 if "wall_ms_per_step" in gpu_eager else None
         except Exception as e:   # a side measurement never takes the benchmark line down
             gpu_eager = {"error": repr(e)}
@@ -440,6 +464,7 @@ def run_gpu(args):
                                     else f"torch F.linear (caller side, unchanged), {args.dnn_matmul} as reference run.sh --use_tf32"),
                             "rows_per_step": rows // args.steps, "distinct_batches": n_batches},
             "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "e2e": e2e,
+            "e2e_host_packed_feed": e2e_packed,
             "gpu_launches": launches, "clocks": clk,
             "dict_tensorizer": None if args.no_cpu_baseline else tensorizer_timing(cfg)}
     print(json.dumps(line))
@@ -658,6 +683,8 @@ def main():
     ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches to cycle")
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resident-items", default="auto", choices=["auto", "on", "off"],
+                    help="e2e leg with the item feature / mm tables resident in HBM (auto: c1 and c2)")
     ap.add_argument("--mm-dtype", default=None, choices=["f32", "bf16"],
                     help="storage dtype of the frozen mm features (default: bf16 for c3, f32 otherwise)")
     ap.add_argument("--no-prefetch", action="store_true", help="sharded path: per-call exchange instead of step prefetch")

@@ -255,6 +255,20 @@ int tgr_permute_rows(const float* in, int H, const int32_t* perm, const int32_t*
 int tgr_gather_rows(const float* table, int H, const uint32_t* rows, const int32_t* n_dev, int64_t max_n, float* out,
                     void* stream);
 
+/* ---- device-resident item features (csrc/tgr_resident.cu) ---------------------------------------------
+ * Item-side sparse features and frozen mm vectors are functions of the item id (model/BaseLine/dataset.py:159,260-263): with
+ * the [items + 1, n_feat] int32 feature table and the [items + 1, mm_dim] mm tables resident in HBM, a call is expanded on the
+ * device from its item-id column into exactly the packed ids / mm inputs the host tensorizer produces (model.py:186-224,283-296). */
+/* ids_out [T, n_single]: column id_col = item_ids[t], columns [col0, col0 + n_feat) = feat_table[item_ids[t], :], the rest 0. */
+int tgr_expand_item_features(const int32_t* item_ids, int64_t T, int n_single, int id_col, int col0, const int32_t* feat_table,
+                             int n_feat, int64_t n_items, int32_t* ids_out, void* stream);
+/* ids[tok[u], col0 + j] = vals[u, j]: the user-side columns of the few user tokens (one per sequence, dataset.py:119). */
+int tgr_scatter_user_tokens(const int32_t* tok, const int32_t* vals, int n_tok, int n_cols, int n_single, int col0, int32_t* ids,
+                            void* stream);
+/* out[t, :] = table[item_ids[t], :], rows of mm_dim elements (fp32 or bf16, a multiple of 16 bytes). */
+int tgr_gather_mm_rows(const int32_t* item_ids, int64_t T, const void* table, int dtype, int mm_dim, int64_t n_items, void* out,
+                       void* stream);
+
 /* ---- peer-memory transport of the sharded exchange (csrc/tgr_symm.cu; no reference counterpart) -----------------------
  * Small messages move by kernels that store to / load from the other ranks' symmetric-memory buffers over NVLink, ordered by
  * device-side barriers: no NCCL collective and no host round trip on the step's critical path. All pointer arrays are HOST

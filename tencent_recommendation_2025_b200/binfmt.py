@@ -36,3 +36,32 @@ def load_emb(path, dtype=np.float32) -> np.ndarray:
 def read_result_ids(path) -> np.ndarray:
     """uint64 [num_queries, top_k] (model/BaseLine/infer.py:51-65)."""
     return load_emb(path, np.uint64)
+
+
+class EmbWriter:
+    """Incremental writer of the same format: the header is written up front from the known shape, row blocks are appended
+    as they arrive (the streaming candidate sweep never holds the whole [N, H] array on the host)."""
+
+    def __init__(self, save_path, num_points: int, num_dimensions: int, dtype=np.float32):
+        self.f = open(os.fspath(save_path), "wb")
+        self.f.write(struct.pack("II", int(num_points), int(num_dimensions)))
+        self.n, self.d, self.dtype, self.written = int(num_points), int(num_dimensions), np.dtype(dtype), 0
+
+    def append(self, rows: np.ndarray) -> None:
+        rows = np.ascontiguousarray(rows, self.dtype)
+        if rows.ndim != 2 or rows.shape[1] != self.d:
+            raise ValueError(f"expected [k, {self.d}] rows")
+        rows.tofile(self.f)
+        self.written += rows.shape[0]
+
+    def close(self) -> None:
+        self.f.close()
+        if self.written != self.n:
+            raise ValueError(f"wrote {self.written} of {self.n} rows")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.f.close()
+        return False

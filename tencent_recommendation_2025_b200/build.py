@@ -19,7 +19,7 @@ LIB = os.path.join(PKG, "libtgr_embed.so")
 PACK_LIB = os.path.join(PKG, "libtgr_pack.so")     # host-side dict tensorizer (plain C on the CPython API)
 PACK_SRC = os.path.join(CSRC, "tgr_pack.c")
 CC = os.environ.get("CC", "gcc")
-SOURCES = ["tgr_util.cu", "tgr_fwd.cu", "tgr_mm.cu", "tgr_mm_tc.cu", "tgr_bwd.cu", "tgr_sort.cu", "tgr_reduce.cu", "tgr_route.cu", "tgr_symm.cu", "tgr_factored.cu", "tgr_rows_ws.cu", "tgr_fact_step.cu"]
+SOURCES = ["tgr_util.cu", "tgr_fwd.cu", "tgr_mm.cu", "tgr_mm_tc.cu", "tgr_bwd.cu", "tgr_sort.cu", "tgr_reduce.cu", "tgr_route.cu", "tgr_symm.cu", "tgr_resident.cu", "tgr_factored.cu", "tgr_rows_ws.cu", "tgr_fact_step.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "-I", INCLUDE, "-I", CSRC, "--expt-relaxed-constexpr", "-Xptxas", "-v"]

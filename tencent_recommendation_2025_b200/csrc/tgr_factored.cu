@@ -850,9 +850,13 @@ __global__ void __launch_bounds__(kFT) fact_dz_kernel(const float4* __restrict__
   float acc[TPW][4];
 #pragma unroll
   for (int i = 0; i < TPW; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  for (int t0 = ta; t0 < tb; t0 += kDzTok) {
-    float4 d[NJ];
-    unsigned m[NJ];
+  // software pipeline: the loads of tile i + 1 are issued right after tile i has been staged, so they travel during the
+  // barrier + MMA phase instead of in front of it
+  constexpr int XPT = kDzTok * (kDzMM / 4) / kFT;
+  float4 d[NJ];
+  unsigned m[NJ];
+  float4 xv[MM ? XPT : 1];
+  auto load_tile = [&](int t0) {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int t = t0 + rl + RL * j;
@@ -865,15 +869,25 @@ __global__ void __launch_bounds__(kFT) fact_dz_kernel(const float4* __restrict__
       }
     }
     if (MM) {
-      for (int i = tid; i < kDzTok * (kDzMM / 4); i += kFT) {
-        const int r = i / (kDzMM / 4), c4 = i % (kDzMM / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < XPT; ++q) {
+        const int i = tid + q * kFT, r = i / (kDzMM / 4), c4 = i % (kDzMM / 4);
+        xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t0 + r < tb) {
           const size_t e = (size_t)(t0 + r) * kDzMM + c4 * 4;
-          if constexpr (XBF16) v = unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + e)));
-          else v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + e));
+          if constexpr (XBF16) xv[q] = unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + e)));
+          else xv[q] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + e));
         }
-        *reinterpret_cast<float4*>(Xs + r * XLD + c4 * 4) = v;
+      }
+    }
+  };
+  if (ta < tb) load_tile(ta);
+  for (int t0 = ta; t0 < tb; t0 += kDzTok) {
+    if (MM) {
+#pragma unroll
+      for (int q = 0; q < XPT; ++q) {
+        const int i = tid + q * kFT, r = i / (kDzMM / 4), c4 = i % (kDzMM / 4);
+        *reinterpret_cast<float4*>(Xs + r * XLD + c4 * 4) = xv[q];
       }
     }
 #pragma unroll
@@ -894,6 +908,7 @@ __global__ void __launch_bounds__(kFT) fact_dz_kernel(const float4* __restrict__
         }
       }
     }
+    if (t0 + kDzTok < tb) load_tile(t0 + kDzTok);
     if (MM) {
       __syncthreads();
 #pragma unroll 2
@@ -1013,12 +1028,23 @@ __global__ void __launch_bounds__(256) fact_mm_chain_kernel(const float* __restr
       for (int h = 0; h < H; ++h) a = fmaf(__ldg(Ws + (size_t)h * ld + q), __ldg(s + h), a);
       dbmm[q] = __fadd_rn(dbmm[q], a);
     }
-  } else if (i < n3) {
-    const int e = i - n2;
-    const int h = e / H, q = e - h * H;
-    float a = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < mm_dim; ++j) a = fmaf(__ldg(A + (size_t)h * mm_dim + j), __ldg(Wmm + (size_t)q * mm_dim + j), a);
+  }
+}
+
+// dWs[h][q] += sum_j A[h][j] Wmm[q][j] + s[h] bmm[q]: one warp per output, lanes stride j (both rows coalesced), fixed
+// shuffle tree. (One THREAD per output walked Wmm with a stride of mm_dim floats: 0.15 ms at mm_dim = 1024.)
+__global__ void __launch_bounds__(256) fact_mm_chain_ws_kernel(const float* __restrict__ Wmm, const float* __restrict__ bmm,
+                                                               const float* __restrict__ A, const float* __restrict__ s, int H,
+                                                               int mm_dim, float* dWs, int64_t dld) {
+  const int lane = threadIdx.x & 31;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= H * H) return;
+  const int h = e / H, q = e - h * H;
+  float a = 0.f;
+  for (int j = lane; j < mm_dim; j += 32) a = fmaf(__ldg(A + (size_t)h * mm_dim + j), __ldg(Wmm + (size_t)q * mm_dim + j), a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) {
     if (bmm != nullptr) a = fmaf(__ldg(s + h), __ldg(bmm + q), a);
     float* d = dWs + (size_t)h * dld + q;
     *d = __fadd_rn(*d, a);
@@ -1309,8 +1335,9 @@ extern "C" int tgr_fact_mm_chain_bwd(const float* w_slot, int64_t ld, const floa
                                      int64_t dld, void* stream) {
   tgr::TimedScope tgr_timed_("fact_mm_chain_bwd", stream);
   TGR_REQUIRE(w_slot && w_mm && A && s && dW_mm && dW_slot && H > 0 && mm_dim > 0, "bad argument");
-  const int n = H * mm_dim + H + H * H;
+  const int n = H * mm_dim + H;
   TGR_K(fact_mm_chain_kernel)<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_slot, ld, w_mm, b_mm, A, s, H, mm_dim, dW_mm,
                                                                           db_mm, dW_slot, dld);
+  TGR_K(fact_mm_chain_ws_kernel)<<<(H * H * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_mm, b_mm, A, s, H, mm_dim, dW_slot, dld);
   return check_launch("fact_mm_chain_bwd");
 }

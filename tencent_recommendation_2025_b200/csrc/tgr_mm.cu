@@ -131,20 +131,40 @@ __global__ void __launch_bounds__(128) mm_proj_fwd_mma_kernel(const void* __rest
 #pragma unroll
     for (int nt = 0; nt < NTILES; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
   for (int k0 = 0; k0 < K; k0 += BK) {
-    for (int i = tid; i < BM * (BK / 4); i += NT) {
-      const int r = i / (BK / 4), c4 = i % (BK / 4);
+    // every 128-bit load of the x tile and of the W tile is issued before the first store (a load -> convert -> store loop
+    // exposes one L2 round trip per iteration: 16 of them per CTA in the first version)
+    constexpr int XPT = BM * (BK / 4) / NT, WPT = H * (BK / 4) / NT;
+    float4 xv[XPT], wv[WPT];
+#pragma unroll
+    for (int q = 0; q < XPT; ++q) {
+      const int i = tid + q * NT, r = i / (BK / 4), c4 = i % (BK / 4);
       const int64_t t = t0 + r;
       const int k = k0 + c4 * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < T && k < K) v = load_x4<XBF16>(x, (size_t)t * K + k);   // K % 4 == 0
-      *reinterpret_cast<float4*>(Xs + r * LD + c4 * 4) = v;
+      xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < T && k < K) xv[q] = load_x4<XBF16>(x, (size_t)t * K + k);   // K % 4 == 0
     }
-    for (int i = tid; i < H * BK; i += NT) {
-      const int n = i / BK, k = i % BK;
-      uint32_t hi = 0u, lo = 0u;
-      if (k0 + k < K) split_tf32(__ldg(W + (size_t)n * K + k0 + k), hi, lo);
-      Whi[n * LD + k] = hi;
-      Wlo[n * LD + k] = lo;
+#pragma unroll
+    for (int q = 0; q < WPT; ++q) {
+      const int i = tid + q * NT, n = i / (BK / 4), c4 = i % (BK / 4);
+      const int k = k0 + c4 * 4;
+      wv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K) wv[q] = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K + k));
+    }
+#pragma unroll
+    for (int q = 0; q < XPT; ++q) {
+      const int i = tid + q * NT, r = i / (BK / 4), c4 = i % (BK / 4);
+      *reinterpret_cast<float4*>(Xs + r * LD + c4 * 4) = xv[q];
+    }
+#pragma unroll
+    for (int q = 0; q < WPT; ++q) {
+      const int i = tid + q * NT, n = i / (BK / 4), c4 = i % (BK / 4);
+      uint4 hi, lo;
+      split_tf32(wv[q].x, hi.x, lo.x);
+      split_tf32(wv[q].y, hi.y, lo.y);
+      split_tf32(wv[q].z, hi.z, lo.z);
+      split_tf32(wv[q].w, hi.w, lo.w);
+      *reinterpret_cast<uint4*>(Whi + n * LD + c4 * 4) = hi;
+      *reinterpret_cast<uint4*>(Wlo + n * LD + c4 * 4) = lo;
     }
     __syncthreads();
     const int m0 = warp * 32;
@@ -329,6 +349,7 @@ extern "C" int tgr_mm_proj_fwd(const void* x, int x_dtype, int64_t T, int mm_dim
   TGR_REQUIRE(out_ld % 4 == 0, "out_ld must be a multiple of 4 elements");
   TGR_REQUIRE((x_dtype == TGR_DTYPE_F32 && mm_dim % 4 == 0) || (x_dtype == TGR_DTYPE_BF16 && mm_dim % 4 == 0),
               "mm_dim must be a multiple of 4");
+  TGR_REQUIRE(((uintptr_t)W & 15) == 0, "W must be 16-byte aligned");
   if (T == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ldb = out_ld * (out_dtype == TGR_DTYPE_BF16 ? 2 : 4);

@@ -34,20 +34,22 @@ namespace tgr {
 namespace ws {
 
 constexpr int H = 64, H4 = 16;
-constexpr int kWin = 2048;   // unique keys staged in shared memory at once
+constexpr int kStagePitch = H * 4 + 16;   // bytes per row of the output staging tile (272: conflict-free 128-bit accesses)
 
 template <int MODE>
 struct Cfg {
   static constexpr int RT = MODE ? 96 : 128;                 // rows per tile (the MMA is M = 128 either way)
-  static constexpr int NLOAD = MODE ? 8 : 4;                 // loader warps
+  static constexpr int NLOAD = 8;                            // loader warps: two groups of four, alternating tiles
   static constexpr int NT = (NLOAD + 1 + 4) * 32;            // + MMA warp + 4 epilogue warps
   static constexpr int TILE = RT * 128;                      // bytes of one bf16 piece tile
   static constexpr int WTILE = H * 128;
   static constexpr int OPS = MODE ? 2 : 1;                   // operand matrices per slot (G and R | rows)
-  static constexpr size_t SMEM = (size_t)2 * OPS * 3 * TILE + (size_t)2 * 3 * WTILE + 1024;
+  static constexpr int WIN = MODE ? 960 : 2048;              // unique keys staged in shared memory at once
+  static constexpr int STAGE = RT * kStagePitch;             // output staging tile (coalesced copy-out)
+  static constexpr size_t SMEM = (size_t)2 * OPS * 3 * TILE + (size_t)2 * 3 * WTILE + STAGE + 1024;
   static constexpr int TMEM_COLS = MODE ? 256 : 128;
-  static constexpr int TPW = kWin / RT;                      // tiles per key window
-  static constexpr int LPT = RT * H4 / (NLOAD * 32);         // 128-bit loads per loader thread and operand
+  static constexpr int TPW = WIN / RT;                       // tiles per key window
+  static constexpr int LPT = RT * H4 / 128;                  // 128-bit loads per loader thread and operand (a group = 128 threads)
 };
 
 struct Item { int tile, seg_a, seg_b, t; };
@@ -79,14 +81,15 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 1) fact_rows_ws_kernel(const __
   uint8_t* Abuf = base;                                          // [2 slots][3 pieces][TILE]   rows (MODE 0) / G (MODE 1)
   uint8_t* Rbuf = Abuf + 2 * 3 * TILE;                           // [2][3][TILE]                table rows (MODE 1)
   uint8_t* Wbuf = base + (size_t)2 * C::OPS * 3 * TILE;          // [2 weight slots][3][WTILE]
+  uint8_t* Stage = Wbuf + (size_t)2 * 3 * WTILE;                 // [RT][kStagePitch] fp32 rows on their way out
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], dw_full, dw_empty;
   __shared__ uint32_t s_tmem;
-  __shared__ uint32_t s_key[kWin];
-  __shared__ int32_t s_perm[kWin];
+  __shared__ uint32_t s_key[C::WIN];
+  __shared__ int32_t s_perm[C::WIN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
-      tc::mbar_init(&a_full[b], NLOAD * 32);
+      tc::mbar_init(&a_full[b], 128);                  // one loader group fills a slot
       tc::mbar_init(&a_empty[b], 1);
       tc::mbar_init(&t_full[b], 1);
       tc::mbar_init(&t_empty[b], 4);
@@ -144,18 +147,29 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 1) fact_rows_ws_kernel(const __
 
     if (is_loader) {
       // =================================================== LOADER ===================================================
-      const int ltid = tid;                                // loader threads are warps [0, NLOAD)
-      // lane -> (row 8 * rg + lane % 8, float4 column 4 * cq + lane / 8) of unit (rg, cq); LPT units per thread
-      auto issue = [&](const Item& x, float4 (&va)[LPT], float4 (&vr)[MODE ? LPT : 1]) {
+      // Two groups of four warps take alternate tiles (group g fills operand slot g). A group runs its tile start to end:
+      // loads -> split -> shared-memory stores -> proxy fence -> arrive. The fence orders the generic-proxy stores before
+      // the tensor core's reads and compiles to a CTA-wide memory barrier that also waits for the thread's outstanding
+      // global loads — prefetching the next tile inside the same thread would therefore be serialised again (measured:
+      // 87 us); the overlap comes from the OTHER group being in its load phase meanwhile.
+      const int grp = warp >> 2, gw = warp & 3, gtid = tid & 127;
+      for (Item x = item_at(win_a, 0); x.tile < win_b; x = next_of(x), ++it) {
+        const bool new_table = x.t != prev_t;
+        if (new_table) { wsel ^= 1; prev_t = x.t; }
+        if ((int)(it & 1u) != grp) continue;
+        const int b = grp;
         const int ns = x.seg_b - x.seg_a;
+        const int row0 = x.tile * RT + x.seg_a;
         const uint32_t* k = s_key + (x.tile - win_a) * RT + x.seg_a;
         const int32_t* pm = s_perm + (x.tile - win_a) * RT + x.seg_a;
         const float* tab = p.w[x.t];
         const uint32_t kb = p.key_base[x.t];
-        const int row0 = x.tile * RT + x.seg_a;
+        // lane -> (row 8 * rg + lane % 8, float4 column 4 * cq + lane / 8) of unit (rg, cq); LPT units per thread
+        float4 va[LPT];
+        float4 vr[MODE ? LPT : 1];
 #pragma unroll
         for (int q = 0; q < LPT; ++q) {
-          const int unit = warp * LPT + q;
+          const int unit = gw * LPT + q;
           const int rg = unit >> 2, cq = unit & 3;
           const int r = rg * 8 + (lane & 7), c = cq * 4 + (lane >> 3);
           va[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -178,28 +192,24 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 1) fact_rows_ws_kernel(const __
             }
           }
         }
-      };
-      auto store = [&](const Item& x, float4 (&va)[LPT], float4 (&vr)[MODE ? LPT : 1]) {
-        const int b = it & 1;
         if (it >= 2) tc::mbar_wait(&a_empty[b], ((it >> 1) - 1u) & 1u);   // the MMAs that read this slot have completed
-        if (x.t != prev_t) {
+        if (new_table) {
           // weight block of the new table -> three bf16 pieces in the other weight slot. MODE 0: B[n = h][k] = W[h][col + k];
           // MODE 1: B[n = k][h] (transposed: the row GEMM contracts over h)
-          wsel ^= 1;
           const float* W = p.dnn_w[p.side[x.t]];
           const int64_t ld = p.dnn_ld[p.side[x.t]];
           const int col = p.col[x.t];
           uint8_t* wb = Wbuf + (size_t)wsel * 3 * WTILE;
-          constexpr int WPT = H * H4 / (NLOAD * 32);
+          constexpr int WPT = H * H4 / 128;
           float4 wv[WPT];
 #pragma unroll
           for (int q = 0; q < WPT; ++q) {
-            const int i = ltid + q * NLOAD * 32, h = i >> 4, c = i & 15;
+            const int i = gtid + q * 128, h = i >> 4, c = i & 15;
             wv[q] = __ldg(reinterpret_cast<const float4*>(W + (size_t)h * ld + col) + c);
           }
 #pragma unroll
           for (int q = 0; q < WPT; ++q) {
-            const int i = ltid + q * NLOAD * 32, h = i >> 4, c = i & 15;
+            const int i = gtid + q * 128, h = i >> 4, c = i & 15;
             uint2 p1, p2, p3;
             split3(wv[q], p1, p2, p3);
             if (MODE == 0) {
@@ -220,15 +230,12 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 1) fact_rows_ws_kernel(const __
               }
             }
           }
-          prev_t = x.t;
         }
-        const int ns = x.seg_b - x.seg_a;
-        const int row0 = x.tile * RT + x.seg_a;
         uint8_t* ab = Abuf + (size_t)b * 3 * TILE;
         uint8_t* rb = Rbuf + (size_t)b * 3 * TILE;
 #pragma unroll
         for (int q = 0; q < LPT; ++q) {
-          const int unit = warp * LPT + q;
+          const int unit = gw * LPT + q;
           const int rg = unit >> 2, cq = unit & 3;
           const int r = rg * 8 + (lane & 7), c = cq * 4 + (lane >> 3);
           const uint32_t off = sw128(r, c >> 1) + (c & 1) * 8;
@@ -248,23 +255,6 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 1) fact_rows_ws_kernel(const __
         }
         tc::fence_smem_to_async();
         mbar_arrive(&a_full[b]);
-        ++it;
-      };
-      float4 va0[LPT], va1[LPT];
-      float4 vr0[MODE ? LPT : 1], vr1[MODE ? LPT : 1];
-      Item cur = item_at(win_a, 0);
-      issue(cur, va0, vr0);
-      while (true) {
-        Item nxt = next_of(cur);
-        if (nxt.tile < win_b) issue(nxt, va1, vr1);
-        store(cur, va0, vr0);
-        if (nxt.tile >= win_b) break;
-        cur = nxt;
-        nxt = next_of(cur);
-        if (nxt.tile < win_b) issue(nxt, va0, vr0);
-        store(cur, va1, vr1);
-        if (nxt.tile >= win_b) break;
-        cur = nxt;
       }
     } else if (is_mma) {
       // ================================================= MMA ISSUER =================================================
@@ -360,22 +350,34 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 1) fact_rows_ws_kernel(const __
         tc::fence_after_sync();
         const int ns = x.seg_b - x.seg_a;
         const int r = quarter * 32 + lane;
-        float* dst = PG + (size_t)(x.tile * RT + x.seg_a + r) * H;
+        // TMEM -> registers -> padded staging tile (every lane owns one row: written straight to global memory that is one
+        // 16-byte piece of 32 different lines per instruction, which kept L1TEX 66 % busy and the loaders' gathers queued
+        // behind it — profiles/README.md r2 ws capture); the accumulator slot is released as soon as it is in registers
 #pragma unroll
         for (int c0 = 0; c0 < H; c0 += 16) {
           uint32_t rr[16];
           tc::ld16(tmem + lane_base + b * H + c0, rr);
           tc::ld_wait();
-          if (r < ns) {
+          if (r < RT) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]),
-                                                                     __uint_as_float(rr[j + 2]), __uint_as_float(rr[j + 3]));
+              *reinterpret_cast<uint4*>(Stage + r * kStagePitch + (c0 + j) * 4) = make_uint4(rr[j], rr[j + 1], rr[j + 2], rr[j + 3]);
           }
         }
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[b]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps: staging tile complete
+        // the item's rows are one contiguous block of PG: linear, fully coalesced copy-out (16 lanes per 256-byte row)
+        {
+          float4* dst = reinterpret_cast<float4*>(PG + (size_t)(x.tile * RT + x.seg_a) * H);
+          const int et = (warp - NLOAD - 1) * 32 + lane;       // 0 .. 127
+          for (int i = et; i < ns * H4; i += 128) {
+            const int rr_ = i >> 4, cc = i & 15;
+            dst[i] = *reinterpret_cast<const float4*>(Stage + rr_ * kStagePitch + cc * 16);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // staging tile free for the next item
         ++it;
       }
     }

@@ -151,6 +151,55 @@ class _FeatEmbMixin:
         save_emb(final_embs, os.path.join(save_path, "embedding.fbin"))
         save_emb(final_ids, os.path.join(save_path, "id.u64bin"))
 
+    def save_item_emb_resident(self, store, item_ids, retrieval_ids, save_path, chunk: int = 1 << 16) -> dict:
+        """The candidate-embedding sweep (model/BaseLine/model.py:402-433) as a STREAM: the item features
+        are resident in HBM (``resident.ResidentItemFeatures``), so a chunk of the sweep is its item ids alone — uploaded on
+        a copy stream one chunk ahead, expanded and embedded on the device (forward only), and copied back into a ring of
+        pinned buffers that a writer drains into ``embedding.fbin`` while the next chunks compute. No per-chunk host sync, no
+        dict walk, never more than three chunks of output on the host. Same files as ``save_item_emb``; returns timings."""
+        import os
+        import time
+
+        from .binfmt import EmbWriter, save_emb
+        from .resident import ResidentFeeder
+        ids = np.ascontiguousarray(item_ids, np.int64).reshape(-1)
+        N, H = ids.size, self._tgr_layout.H
+        dev = store.device
+        feeder = ResidentFeeder(store, slots=3)
+        ring = [torch.empty((chunk, H), dtype=torch.float32, pin_memory=True) for _ in range(3)]
+        done = [None, None, None]
+        pend = []                                     # (ring slot, rows) whose D2H copy is in flight, oldest first
+        t0 = time.perf_counter()
+        starts = list(range(0, N, chunk))
+        with EmbWriter(os.path.join(save_path, "embedding.fbin"), N, H) as out, torch.no_grad():
+            if starts:
+                feeder.submit([store.slim_items(ids[0:chunk])])
+            for ci, a in enumerate(starts):
+                n = min(chunk, N - a)
+                pb = feeder.take()[0]
+                if ci + 1 < len(starts):
+                    b = starts[ci + 1]
+                    feeder.submit([store.slim_items(ids[b:b + chunk])])      # next chunk's ids travel while this one computes
+                emb = self.feat2emb_packed(pb).reshape(n, H)
+                feeder.retire()
+                slot = ci % 3
+                if done[slot] is not None:                                    # the writer is two chunks behind the GPU
+                    s_, n_ = pend.pop(0)
+                    done[s_].synchronize()
+                    out.append(ring[s_][:n_].numpy())
+                ring[slot][:n].copy_(emb, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                done[slot] = ev
+                pend.append((slot, n))
+            for s_, n_ in pend:
+                done[s_].synchronize()
+                out.append(ring[s_][:n_].numpy())
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        save_emb(np.array(retrieval_ids, dtype=np.uint64).reshape(-1, 1), os.path.join(save_path, "id.u64bin"))
+        return {"items": N, "seconds": dt, "items_per_s": N / dt if dt > 0 else float("inf"), "chunk": chunk}
+
     def check_padding_rows(self):
         """Row 0 of every table must be all-zero (the reference keeps it so: main.py:106-111, padding_idx
         gradient masking, AdamW fixed point). Array pooling drops padding ids on that basis."""

@@ -94,19 +94,26 @@ def test_install_parity_mode_reproduces_the_reference_model(path):
     lr_.backward()
     lm_.backward()
     gm = dict(mine.named_parameters())
+    # a gradient that is zero in exact arithmetic (the key bias under a softmax: every score of a row shifts by the same
+    # amount) is pure rounding noise on both sides, so each tensor's scale is floored at 1e-3 of the largest gradient
+    gscale = max(p.grad.abs().max().item() for p in ref.parameters() if p.grad is not None)
     for k, p in ref.named_parameters():
         if p.grad is None:
             assert gm[k].grad is None or not bool(gm[k].grad.any()), k
             continue
         assert gm[k].grad is not None, k
         err = (gm[k].grad - p.grad).abs().max().item()
-        assert err <= E2E_RTOL * max(p.grad.abs().max().item(), 1e-30), f"grad {k}: {err:.3e}"
+        assert err <= E2E_RTOL * max(p.grad.abs().max().item(), 1e-3 * gscale), f"grad {k}: {err:.3e}"
     opt_r.step()
     opt_m.step()
     for k, p in ref.named_parameters():
         if _hot(k):
             g = p.grad.cpu().numpy()
-            assert_rows_updated(gm[k].detach().cpu().numpy(), p.detach().cpu().numpy(), g, LR, rtol=E2E_RTOL, what=f"{path} {k}")
+            rows = np.nonzero(np.any(g != 0, axis=1))[0]
+            got, want = gm[k].detach().cpu().numpy(), p.detach().cpu().numpy()
+            assert_rows_updated(got[rows], want[rows], g[rows], LR, rtol=E2E_RTOL, what=f"{path} {k}")
+            rest = np.setdiff1d(np.arange(got.shape[0]), rows)
+            np.testing.assert_allclose(got[rest], want[rest], rtol=0, atol=E2E_RTOL * max(np.abs(want).max(), 1e-30))
     assert set(mine.state_dict()) == set(ref.state_dict()), "state_dict keys must stay the reference's"
 
 
