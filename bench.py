@@ -251,7 +251,12 @@ def run_gpu(args):
     worldgen = synth.SynthWorld(cfg, 0)
     lay = worldgen.layout
     m = init_module(cfg, dev, "fused", args.path)
-    dense_opt = torch.optim.AdamW(m.dense_parameters(), lr=1e-3, betas=(0.9, 0.98), fused=True)
+    # factored path: the engine also owns the path's Linear layers (itemdnn / userdnn / emb_transform): one AdamW launch next
+    # to the row update instead of torch's multi-tensor AdamW (37 us of device time + 0.14 ms of host time per step)
+    own_dense = args.path == "factored" and not args.torch_dense_opt
+    if own_dense:
+        m.own_dense_parameters()
+    dense_opt = None if own_dense else torch.optim.AdamW(m.dense_parameters(), lr=1e-3, betas=(0.9, 0.98), fused=True)
     eng = m.engine
     n_batches = max(1, min(args.batches, args.steps + args.warmup))
     steps_np = [worldgen.make_step(s) for s in range(n_batches)]
@@ -265,13 +270,23 @@ def run_gpu(args):
     lookups = [st.n_lookups() for st in steps_np]   # host-side row counting stays out of the timed regions
 
     def one_step(pbs, ups):
-        dense_opt.zero_grad(set_to_none=True)
+        if dense_opt is not None:
+            dense_opt.zero_grad(set_to_none=True)
         m.prefetch(pbs)                          # factored path: one key sort / row projection per step
         outs = [m.feat2emb_packed(pb) for pb in pbs]
         torch.autograd.backward(outs, ups)
-        dense_opt.step()
-        m.fused_step(**hyper)
+        if dense_opt is not None:
+            dense_opt.step()
+            m.fused_step(**hyper)
+        else:
+            m.fused_step(**hyper, dense=True)
         return outs
+
+    def step_result(outs):
+        """The scalar read back every step in the e2e legs: a checksum of the step's outputs (the last position of the first
+        sequence of every call). The real loss comes from the trunk, which is not on this path."""
+        with torch.no_grad():
+            return torch.stack([o.detach()[0, -1] for o in outs]).sum()
 
     # ---- device-resident timing (value) -------------------------------------------------------
     clocks = ClockSampler(local_rank, period_ms=args.clock_period_ms)
@@ -378,8 +393,7 @@ def run_gpu(args):
             feeder.submit(host_steps[(i + 1) % n_batches])             # next step's copies overlap this step's kernels
             outs = one_step(pbs, dev_steps[k][1])
             feeder.retire()
-            with torch.no_grad():
-                loss = sum(o.detach().sum() for o in outs)
+            loss = step_result(outs)
             slot = i & 1
             if loss_ev[slot] is not None:                              # step i-2's loss has long arrived: read it
                 loss_ev[slot].synchronize()
@@ -426,10 +440,115 @@ def run_gpu(args):
                 "the device (ResidentItemFeatures / ResidentFeeder); H2D on a copy stream one step ahead, loss read back every "
                 "step; wall clock")
             e2e = e2e_resident
-            del store
         except Exception as exc:   # e.g. not enough host memory for the table build: keep the packed-feed number
             e2e_resident = {"error": repr(exc)}
+            store = None
+    else:
+        store = None
     e2e_steps = 1
+
+    # ---- the step as ONE CUDA graph (graphed.GraphedStep): the eager loop above is host-bound (tools/host_profile.py:
+    #      0.99 ms of Python/torch enqueue per 1.03 ms step), a replay costs the host one launch. Fixed-shape slim calls, lookup
+    #      count and AdamW bias corrections in device memory; bit-identical to the eager step (tests/test_gpu_graphed.py) -----
+    eager = {"value": value, "ms_per_step": ms / args.steps, "gpu_launches": launches, "clocks": clk, "e2e": e2e,
+             "how": "the same step issued eagerly from Python (one C-ABI call per phase)"}
+    graph_leg = None
+    if store is not None and args.graph != "off" and args.path == "factored":
+        try:
+            from tencent_recommendation_2025_b200.graphed import GraphedStep
+            from tencent_recommendation_2025_b200.resident import CallShape
+            shapes = [CallShape.covering([st.calls[i] for st in steps_np]) for i in range(len(steps_np[0].calls))]
+            fixed = [store.slim_step(st.calls, shapes) for st in steps_np]        # pinned, one buffer per step
+            dev_fixed = [f.ints.to(dev) for f in fixed]
+            cap_opt = None if own_dense else torch.optim.AdamW(m.dense_parameters(), lr=1e-3, betas=(0.9, 0.98), fused=True,
+                                                               capturable=True)
+            ups0 = dev_steps[0][1]     # upstream gradients are the trunk's stand-in: a static buffer inside the graph
+
+            def body(pbs):
+                if cap_opt is not None:
+                    cap_opt.zero_grad(set_to_none=True)
+                m.prefetch(pbs)
+                outs = [m.feat2emb_packed(pb) for pb in pbs]
+                torch.autograd.backward(outs, ups0)
+                if cap_opt is not None:
+                    cap_opt.step()
+                    m.fused_step(**hyper)
+                else:
+                    m.fused_step(**hyper, dense=True)
+                return step_result(outs)
+
+            g_warm = 3
+            l0 = _lib.launch_count()
+            runner = GraphedStep(m, store, fixed[0], body, hyper=hyper, warmup=g_warm)
+            per_replay = (_lib.launch_count() - l0) // (g_warm + 1)     # warm-ups and the capture issue the same launches
+            clocks2 = ClockSampler(local_rank, period_ms=args.clock_period_ms)
+            if not args.no_clocks:
+                clocks2.start()
+            for i in range(max(args.warmup, 3)):
+                runner.load(dev_fixed[i % n_batches])
+                runner.run()
+            torch.cuda.synchronize()
+            clocks2.mark()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            g_rows = 0
+            for i in range(args.steps):
+                k = (args.warmup + i) % n_batches
+                runner.load(dev_fixed[k])          # inputs resident in HBM: one 3 MB device-to-device copy into the static buffer
+                runner.run()
+                g_rows += lookups[k]
+            g1.record()
+            torch.cuda.synchronize()
+            g_clk = clocks2.stop()
+            g_ms = g0.elapsed_time(g1)
+            # e2e: pinned host slim buffers -> staging (copy stream, one step ahead) -> replay -> loss read back every step
+            e2e_n = max(3, min(args.steps, 20))
+            e2e_warm = n_batches + 1
+            loss_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+            loss_ev = [None, None]
+            losses, h2d, rows_e2e, t0 = [], 0, 0, None
+            runner.submit(fixed[0])
+            for i in range(e2e_warm + e2e_n):
+                k = i % n_batches
+                if i == e2e_warm:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                runner.submit(fixed[(i + 1) % n_batches])      # next step's H2D overlaps this step's replay
+                loss = runner.run()
+                slot = i & 1
+                if loss_ev[slot] is not None:
+                    loss_ev[slot].synchronize()
+                    losses.append(float(loss_host[slot]))
+                loss_host[slot:slot + 1].copy_(loss.reshape(1), non_blocking=True)
+                loss_ev[slot] = torch.cuda.Event()
+                loss_ev[slot].record()
+                if i >= e2e_warm:
+                    rows_e2e += lookups[k]
+                    h2d += fixed[k].ints.numel() * 4 + 48
+            for ev in loss_ev:
+                if ev is not None:
+                    ev.synchronize()
+            torch.cuda.synchronize()
+            t_g = time.perf_counter() - t0
+            runner.run()                                        # drain the look-ahead submission
+            torch.cuda.synchronize()
+            graph_leg = {"value": g_rows / (g_ms * 1e-3), "ms_per_step": g_ms / args.steps,
+                         "kernels_per_replay": int(per_replay), "clocks": g_clk,
+                         "e2e": {"value": rows_e2e / t_g, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_n, "d2h_bytes_per_step": 4,
+                                 "ms_per_step": round(t_g / e2e_n * 1e3, 3),
+                                 "entry": "GraphedStep.submit (pinned slim buffer: ids + user tokens, one H2D copy on a copy stream, "
+                                          "one step ahead) + GraphedStep.run (48-byte AdamW block + one graph replay: expansion from "
+                                          "the HBM-resident item tables, prefetch, feat2emb x3, backward, dense AdamW, row update) + "
+                                          "the step's loss copied back and read on the host every step; wall clock",
+                                 "loss_finite": bool(np.all(np.isfinite(losses)))}}
+            runner.close()
+            runner = dev_fixed = None
+            value, ms, launches, clk = graph_leg["value"], g_ms, int(per_replay) * args.steps, g_clk
+            e2e, t_e2e_step = graph_leg["e2e"], t_g / e2e_n
+        except Exception as exc:   # the eager numbers stand
+            import traceback
+            graph_leg = {"error": repr(exc), "trace": traceback.format_exc()[-1500:]}
+    store = None
 
     # ---- the reference itself, beside the number: on the box's host cores and as torch eager on this GPU -----------
     cpu = None
@@ -462,9 +581,11 @@ def run_gpu(args):
                             "dnn": ("itemdnn/userdnn folded into the deduplicated rows (factored kernels; 3xTF32 tensor-core "
                                     "row GEMMs, fp32 accumulate)" if args.path == "factored"
                                     else f"torch F.linear (caller side, unchanged), {args.dnn_matmul} as reference run.sh --use_tf32"),
-                            "rows_per_step": rows // args.steps, "distinct_batches": n_batches},
+                            "rows_per_step": rows // args.steps, "distinct_batches": n_batches,
+                            "launch": ("one CUDA graph replay per step (graphed.GraphedStep)" if graph_leg and "error" not in graph_leg
+                                       else "eager: one C-ABI call per phase from Python")},
             "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "e2e": e2e,
-            "e2e_host_packed_feed": e2e_packed,
+            "e2e_host_packed_feed": e2e_packed, "eager": eager, "graph": graph_leg,
             "gpu_launches": launches, "clocks": clk,
             "dict_tensorizer": None if args.no_cpu_baseline else tensorizer_timing(cfg)}
     print(json.dumps(line))
@@ -685,6 +806,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-items", default="auto", choices=["auto", "on", "off"],
                     help="e2e leg with the item feature / mm tables resident in HBM (auto: c1 and c2)")
+    ap.add_argument("--torch-dense-opt", action="store_true",
+                    help="factored path: update itemdnn/userdnn/emb_transform with torch.optim.AdamW instead of the engine's "
+                         "own dense AdamW launch")
+    ap.add_argument("--graph", default="auto", choices=["auto", "off"],
+                    help="N=1: the step replayed from a CUDA graph (needs the resident item tables); off = eager numbers only")
     ap.add_argument("--mm-dtype", default=None, choices=["f32", "bf16"],
                     help="storage dtype of the frozen mm features (default: bf16 for c3, f32 otherwise)")
     ap.add_argument("--no-prefetch", action="store_true", help="sharded path: per-call exchange instead of step prefetch")

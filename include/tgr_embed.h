@@ -209,6 +209,26 @@ int tgr_bwd_reduce_rows(const tgr_table_t* tables, int n_tables, int H, const fl
 int tgr_adam_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
                   const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam, void* stream);
 
+/* The same update with the hyper-parameter block in DEVICE memory (read when the kernel runs): a captured CUDA graph
+ * replays it while the host refreshes the bias corrections of the step with a 48-byte copy. */
+int tgr_adam_rows_dev(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
+                      const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam_dev, void* stream);
+
+/* AdamW on up to TGR_MAX_DENSE small dense tensors in ONE launch (the path's own Linear layers — itemdnn, userdnn,
+ * emb_transform, model/BaseLine/model.py:150-151,166-167 — ~0.1 M parameters; torch's multi-tensor AdamW spends 37 us
+ * of device time on them). Same arithmetic as the row update. Exactly one of adam / adam_dev is non-NULL. */
+#define TGR_MAX_DENSE 16
+typedef struct tgr_dense_list {
+  float* w[TGR_MAX_DENSE];
+  const float* g[TGR_MAX_DENSE];
+  float* m[TGR_MAX_DENSE];
+  float* v[TGR_MAX_DENSE];
+  int64_t numel[TGR_MAX_DENSE];
+  int32_t n;
+  int32_t reserved;
+} tgr_dense_list_t;
+int tgr_adam_dense(const tgr_dense_list_t* list, const tgr_adam_t* adam, const tgr_adam_t* adam_dev, void* stream);
+
 /* Parity mode: add reduced rows into dense per-table gradients tables[].grad (each key once => plain store-add). */
 int tgr_scatter_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
                      const int32_t* n_unique_dev, int64_t max_unique, void* stream);
@@ -390,10 +410,13 @@ typedef struct tgr_fact_grads { /* zero-initialised accumulators (+=), NULL = no
 typedef struct tgr_fact_group {
   /* ---- filled by the caller before tgr_fact_group_bytes / tgr_fact_prepare ---- */
   int32_t n_calls, H, key_bits, n_mm;
-  int64_t n;                           /* exact count of non-padding in-range ids over the calls (host-known) */
+  int64_t n;                           /* count of non-padding in-range ids over the calls: exact (host-known), or an
+                                          upper bound when n_is_capacity != 0 */
   int32_t mm_dim[TGR_MAX_MM];
   int32_t mm_x_dtype;                  /* TGR_DTYPE_* of the mm inputs */
-  int32_t reserved;
+  int32_t n_is_capacity;               /* != 0: the kernels take the count from device memory (what build_keys emitted),
+                                          n only sizes buffers and grids — the launch sequence is then a function of
+                                          the calls' shapes alone and can be captured in a CUDA graph */
   tgr_call_t calls[TGR_MAX_CALLS];     /* ids / arrays of every call; item_cat / user_cat unused */
   const void* mm_x[TGR_MAX_CALLS][TGR_MAX_MM]; /* [T, mm_dim] inputs of every call */
   tgr_row_source_t src;                /* row-sharded tables: set BEFORE the first forward (fetched rows or peer
@@ -418,6 +441,7 @@ typedef struct tgr_fact_group {
   void* ws;
   size_t ws_bytes;
   int32_t projected, n_backward;       /* progress */
+  int32_t mm_done, mm_joined;          /* tgr_fact_mm_branch ran / the caller's stream has waited for it */
 } tgr_fact_group_t;
 
 /* Arena bytes tgr_fact_prepare needs for this group (depends on n, the calls' T / n_single / arr_nnz, H, mm dims). */
@@ -425,6 +449,11 @@ size_t tgr_fact_group_bytes(const tgr_fact_group_t* g, int n_tables);
 /* keys -> sort -> dedup -> ids remapped to 1 + unique index, for all calls of the group. Value independent. */
 int tgr_fact_prepare(const tgr_table_t* tables, int n_tables, tgr_fact_group_t* g, void* arena, size_t arena_bytes,
                      void* stream);
+/* Optional, right after tgr_fact_prepare on the same stream, when the forwards follow immediately (the weights the mm
+ * projection reads are already final): fold + mm projection of EVERY call of the group on an internal side stream that
+ * forks from the point where tgr_fact_prepare started, so the small value-dependent mm kernels run next to the issue-bound
+ * key processing (sort / dedup) instead of after it. The first tgr_fact_call_forward joins. Capturable in a CUDA graph. */
+int tgr_fact_mm_branch(const tgr_fact_params_t* prm, tgr_fact_group_t* g, void* stream);
 /* feat2emb forward of call c into out [T, H]; the first forward of a group projects the unique rows. */
 int tgr_fact_call_forward(const tgr_table_t* tables, int n_tables, const tgr_fact_params_t* prm, tgr_fact_group_t* g,
                           int c, float* out, void* stream);

@@ -71,7 +71,7 @@ class FactGrads(C.Structure):
 
 class FactGroup(C.Structure):
     _fields_ = [("n_calls", C.c_int32), ("H", C.c_int32), ("key_bits", C.c_int32), ("n_mm", C.c_int32),
-                ("n", C.c_int64), ("mm_dim", C.c_int32 * MAX_MM), ("mm_x_dtype", C.c_int32), ("reserved", C.c_int32),
+                ("n", C.c_int64), ("mm_dim", C.c_int32 * MAX_MM), ("mm_x_dtype", C.c_int32), ("n_is_capacity", C.c_int32),
                 ("calls", Call * MAX_CALLS), ("mm_x", (C.c_void_p * MAX_MM) * MAX_CALLS),
                 ("src", RowSource),
                 ("cap", C.c_int64),
@@ -85,7 +85,15 @@ class FactGroup(C.Structure):
                 ("fold_M", C.c_void_p * MAX_MM), ("fold_c", C.c_void_p * MAX_MM), ("mm_A", C.c_void_p * MAX_MM),
                 ("mm_s", C.c_void_p * MAX_MM), ("fold_Mb", C.c_void_p * MAX_MM), ("dzb", C.c_void_p),
                 ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
-                ("projected", C.c_int32), ("n_backward", C.c_int32)]
+                ("projected", C.c_int32), ("n_backward", C.c_int32), ("mm_done", C.c_int32), ("mm_joined", C.c_int32)]
+
+
+MAX_DENSE = 16
+
+
+class DenseList(C.Structure):
+    _fields_ = [("w", C.c_void_p * MAX_DENSE), ("g", C.c_void_p * MAX_DENSE), ("m", C.c_void_p * MAX_DENSE),
+                ("v", C.c_void_p * MAX_DENSE), ("numel", C.c_int64 * MAX_DENSE), ("n", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Adam(C.Structure):
@@ -144,6 +152,9 @@ SIGNATURES = {
                                       C.c_void_p, C.c_int64, C.POINTER(Adam), C.c_void_p, C.c_size_t, C.c_void_p]),
     "tgr_adam_rows": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                 C.POINTER(Adam), C.c_void_p]),
+    "tgr_adam_dense": (C.c_int, [C.POINTER(DenseList), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tgr_adam_rows_dev": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_void_p]),
     "tgr_scatter_rows": (C.c_int, [C.POINTER(Table), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p]),
     "tgr_route_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
@@ -183,6 +194,7 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p]),
     "tgr_fact_group_bytes": (C.c_size_t, [C.POINTER(FactGroup), C.c_int]),
     "tgr_fact_prepare": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(FactGroup), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tgr_fact_mm_branch": (C.c_int, [C.POINTER(FactParams), C.POINTER(FactGroup), C.c_void_p]),
     "tgr_fact_call_forward": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(FactParams), C.POINTER(FactGroup), C.c_int,
                                         C.c_void_p, C.c_void_p]),
     "tgr_fact_call_backward": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(FactParams), C.POINTER(FactGroup), C.c_int,

@@ -28,7 +28,9 @@ namespace tgr {
 constexpr int kScanBlock = 1024;
 
 template <class F>
-__global__ void __launch_bounds__(kScanBlock) flag_count_kernel(const __grid_constant__ F f, int64_t n, int32_t* __restrict__ block_count) {
+__global__ void __launch_bounds__(kScanBlock) flag_count_kernel(const __grid_constant__ F f, int64_t n, int32_t* __restrict__ block_count,
+                                                                const int32_t* __restrict__ n_dev) {
+  if (n_dev) n = min(n, (int64_t)__ldg(n_dev));
   const int64_t e = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
   const int v = (e < n) && f.valid(e);
   const int c = __syncthreads_count(v);
@@ -96,7 +98,9 @@ __device__ __forceinline__ int block_rank(int v, int32_t* warp_cnt /*[32] shared
 }
 
 template <class F>
-__global__ void __launch_bounds__(kScanBlock) flag_emit_kernel(const __grid_constant__ F f, int64_t n, const int32_t* __restrict__ block_off) {
+__global__ void __launch_bounds__(kScanBlock) flag_emit_kernel(const __grid_constant__ F f, int64_t n, const int32_t* __restrict__ block_off,
+                                                               const int32_t* __restrict__ n_dev) {
+  if (n_dev) n = min(n, (int64_t)__ldg(n_dev));
   __shared__ int32_t warp_cnt[32];
   const int64_t e = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
   const int v = (e < n) && f.valid(e);
@@ -247,7 +251,133 @@ struct HeadFunctor {
   }
 };
 
-__global__ void dedup_finish_kernel(int32_t* seg_off, const int32_t* n_unique_dev, int64_t n) {
+// ---- dedup of the sorted keys: 8 keys per thread, 2048 per CTA (the generic one-entry-per-thread compaction above spent
+//      17 + 26 us on 2.85 M keys; profiles/README.md r2 graph timeline). The emit pass optionally does the id remap of the
+//      SINGLE slots as well (what tgr_remap_scatter does from seg_of_entry): one read of the sorted payloads instead of two
+//      passes over the entry list. ----
+constexpr int kDdThreads = 256, kDdItems = 8, kDdTile = kDdThreads * kDdItems;
+struct DedupScatter {
+  int32_t* out[TGR_MAX_CALLS];                          // NULL table => no remap
+  int32_t n_cols[TGR_MAX_CALLS];
+  int8_t col_of_slot[TGR_MAX_CALLS][TGR_MAX_SLOTS];
+  const uint32_t* srcs;
+};
+
+__device__ __forceinline__ void dd_load(const uint32_t* __restrict__ k, int64_t base, int64_t n, bool vec, uint32_t (&key)[kDdItems],
+                                        uint32_t& prev) {
+  if (vec && base + kDdItems <= n) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(k + base)), b = __ldg(reinterpret_cast<const uint4*>(k + base) + 1);
+    key[0] = a.x; key[1] = a.y; key[2] = a.z; key[3] = a.w; key[4] = b.x; key[5] = b.y; key[6] = b.z; key[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kDdItems; ++j) key[j] = base + j < n ? __ldg(k + base + j) : 0u;
+  }
+  prev = (base > 0 && base < n) ? __ldg(k + base - 1) : ~key[0];   // entry 0 always opens a run
+}
+
+__global__ void __launch_bounds__(kDdThreads) dedup_count_kernel(const uint32_t* __restrict__ k, int64_t n, int32_t* __restrict__ block_count,
+                                                                 const int32_t* __restrict__ n_dev, int vec) {
+  __shared__ int32_t ws[kDdThreads / 32];
+  if (n_dev) n = min(n, (int64_t)__ldg(n_dev));
+  const int64_t base = (int64_t)blockIdx.x * kDdTile + threadIdx.x * kDdItems;
+  int c = 0;
+  if (base < n) {
+    uint32_t key[kDdItems], prev;
+    dd_load(k, base, n, vec != 0, key, prev);
+#pragma unroll
+    for (int j = 0; j < kDdItems; ++j) {
+      if (base + j < n) c += key[j] != prev;
+      prev = key[j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kDdThreads / 32; ++w) t += ws[w];
+    block_count[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kDdThreads) dedup_emit_kernel(const uint32_t* __restrict__ k, int64_t n, const int32_t* __restrict__ block_off,
+                                                                uint32_t* __restrict__ uniq, int32_t* __restrict__ seg_off,
+                                                                int32_t* __restrict__ seg_of_entry, const __grid_constant__ DedupScatter sc,
+                                                                const int32_t* __restrict__ n_dev, int vec) {
+  __shared__ int32_t ws[kDdThreads / 32];
+  if (n_dev) n = min(n, (int64_t)__ldg(n_dev));
+  const int64_t base = (int64_t)blockIdx.x * kDdTile + threadIdx.x * kDdItems;
+  uint32_t key[kDdItems], prev = 0;
+  int c = 0;
+  unsigned heads = 0;
+  if (base < n) {
+    dd_load(k, base, n, vec != 0, key, prev);
+#pragma unroll
+    for (int j = 0; j < kDdItems; ++j) {
+      if (base + j < n && key[j] != prev) { heads |= 1u << j; ++c; }
+      prev = key[j];
+    }
+  }
+  // exclusive scan of the per-thread head counts over the CTA, in thread order
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int x = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) ws[wid] = x;
+  __syncthreads();
+  int before = 0;
+#pragma unroll
+  for (int w = 0; w < kDdThreads / 32; ++w) before += w < wid ? ws[w] : 0;
+  if (base >= n) return;
+  int pos = __ldg(block_off + blockIdx.x) + before + x - c;   // heads before this thread's first entry
+  int32_t seg[kDdItems];
+#pragma unroll
+  for (int j = 0; j < kDdItems; ++j) {
+    if (heads & (1u << j)) {
+      uniq[pos] = key[j];
+      seg_off[pos] = (int32_t)(base + j);
+      ++pos;
+    }
+    seg[j] = pos - 1;                                          // index of the last head at or before the entry
+  }
+  const bool full = vec && base + kDdItems <= n;
+  if (seg_of_entry) {
+    if (full) {
+      reinterpret_cast<int4*>(seg_of_entry + base)[0] = make_int4(seg[0], seg[1], seg[2], seg[3]);
+      reinterpret_cast<int4*>(seg_of_entry + base)[1] = make_int4(seg[4], seg[5], seg[6], seg[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kDdItems; ++j) if (base + j < n) seg_of_entry[base + j] = seg[j];
+    }
+  }
+  if (sc.srcs) {   // ids of the SINGLE slots -> 1 + unique index, scattered to (call, token, column)
+    uint32_t src[kDdItems];
+    if (full) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(sc.srcs + base)), b = __ldg(reinterpret_cast<const uint4*>(sc.srcs + base) + 1);
+      src[0] = a.x; src[1] = a.y; src[2] = a.z; src[3] = a.w; src[4] = b.x; src[5] = b.y; src[6] = b.z; src[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kDdItems; ++j) src[j] = base + j < n ? __ldg(sc.srcs + base + j) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kDdItems; ++j) {
+      if (base + j >= n) continue;
+      const int call = src[j] >> TGR_SRC_CALL_SHIFT;
+      const int col = sc.col_of_slot[call][(src[j] >> TGR_SRC_SLOT_SHIFT) & 31];
+      if (col < 0) continue;    // array values are remapped by tgr_remap_arrays (a token may hold several)
+      sc.out[call][(size_t)(src[j] & TGR_SRC_TOKEN_MASK) * sc.n_cols[call] + col] = 1 + seg[j];
+    }
+  }
+}
+
+__global__ void dedup_finish_kernel(int32_t* seg_off, int32_t* n_unique_dev, int64_t n, const int32_t* n_dev) {
+  if (n_dev) n = min(n, (int64_t)*n_dev);
+  if (n == 0) *n_unique_dev = 0;   // (entry 0 always opens a run: an empty list must not report one)
   seg_off[*n_unique_dev] = (int32_t)n;
 }
 
@@ -259,6 +389,7 @@ __global__ void __launch_bounds__(256) rows_kernel(const __grid_constant__ RowPa
                                                    const float* __restrict__ grads, const int32_t* __restrict__ n_dev) {
   const int n = *n_dev;
   const int H4 = p.H4;
+  const tgr_adam_t ad = (MODE == 0 && p.adam_dev) ? *p.adam_dev : p.adam;
   const int64_t total = (int64_t)n * H4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int u = (int)(i / H4), c = (int)(i - (int64_t)u * H4);
@@ -268,7 +399,7 @@ __global__ void __launch_bounds__(256) rows_kernel(const __grid_constant__ RowPa
     const float4 g = __ldg(reinterpret_cast<const float4*>(grads) + i);
     if (MODE == 0) {
       adam_row4(reinterpret_cast<float4*>(p.w[t] + row) + c, reinterpret_cast<float4*>(p.m[t] + row) + c,
-                reinterpret_cast<float4*>(p.v[t] + row) + c, g, p.adam);
+                reinterpret_cast<float4*>(p.v[t] + row) + c, g, ad);
     } else if (p.grad[t] != nullptr) {  // tables without a dense gradient target are skipped
       float4* d = reinterpret_cast<float4*>(p.grad[t] + row) + c;
       float4 o = *d;
@@ -381,15 +512,30 @@ extern "C" int tgr_bwd_build_keys(const tgr_table_t* tables, int n_tables, const
 }
 
 extern "C" size_t tgr_dedup_workspace_bytes(int64_t n) {
-  return align_up((size_t)((n + kScanBlock - 1) / kScanBlock + 1) * sizeof(int32_t));
+  return align_up((size_t)((n + kDdTile - 1) / kDdTile + 1) * sizeof(int32_t));
 }
 
 extern "C" int tgr_dedup(const uint32_t* keys_sorted, int64_t n, uint32_t* uniq, int32_t* seg_off, int32_t* seg_of_entry,
                          int32_t* n_unique_dev, void* workspace, size_t workspace_bytes, void* stream) {
+  return tgr::dedup_dn(keys_sorted, n, uniq, seg_off, seg_of_entry, n_unique_dev, workspace, workspace_bytes, nullptr, stream);
+}
+
+int tgr::dedup_dn(const uint32_t* keys_sorted, int64_t n, uint32_t* uniq, int32_t* seg_off, int32_t* seg_of_entry,
+                  int32_t* n_unique_dev, void* workspace, size_t workspace_bytes, const int32_t* n_dev, void* stream) {
+  return dedup_remap_dn(keys_sorted, nullptr, n, uniq, seg_off, seg_of_entry, n_unique_dev, workspace, workspace_bytes, nullptr, 0,
+                        nullptr, n_dev, stream);
+}
+
+// srcs_sorted / calls / ids_out != NULL: the emit pass also writes ids_out[call][token, column] = 1 + unique index for every
+// SINGLE-slot entry (the caller has zeroed ids_out: padding ids stay 0)
+int tgr::dedup_remap_dn(const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n, uint32_t* uniq, int32_t* seg_off,
+                        int32_t* seg_of_entry, int32_t* n_unique_dev, void* workspace, size_t workspace_bytes,
+                        const tgr_call_t* calls, int n_calls, int32_t* const* ids_out, const int32_t* n_dev, void* stream) {
   tgr::TimedScope tgr_timed_("dedup", stream);
   TGR_REQUIRE(uniq && seg_off && n_unique_dev && workspace, "null argument");
   TGR_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
   TGR_REQUIRE(workspace_bytes >= tgr_dedup_workspace_bytes(n), "workspace too small");
+  const int vec = (((uintptr_t)keys_sorted | (uintptr_t)seg_of_entry | (uintptr_t)srcs_sorted) & 15) == 0;   // 128-bit accesses
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
     cudaMemsetAsync(n_unique_dev, 0, sizeof(int32_t), st);
@@ -397,29 +543,107 @@ extern "C" int tgr_dedup(const uint32_t* keys_sorted, int64_t n, uint32_t* uniq,
     return check_launch("dedup(empty)");
   }
   TGR_REQUIRE(keys_sorted, "null keys");
+  DedupScatter sc{};
+  if (srcs_sorted != nullptr) {
+    TGR_REQUIRE(calls && ids_out && n_calls > 0 && n_calls <= TGR_MAX_CALLS, "dedup+remap: bad calls");
+    sc.srcs = srcs_sorted;
+    for (int c = 0; c < n_calls; ++c) {
+      TGR_REQUIRE(ids_out[c] != nullptr, "ids_out[%d] is NULL", c);
+      sc.out[c] = ids_out[c];
+      sc.n_cols[c] = calls[c].n_single;
+      for (int i = 0; i < TGR_MAX_SLOTS; ++i) sc.col_of_slot[c][i] = -1;
+      for (int i = 0; i < calls[c].n_slots; ++i)
+        if (calls[c].slots[i].kind == TGR_KIND_SINGLE) sc.col_of_slot[c][i] = (int8_t)calls[c].slots[i].src;
+    }
+  }
   int32_t* block_cnt = (int32_t*)workspace;
-  const int nb = (int)((n + kScanBlock - 1) / kScanBlock);
-  HeadFunctor f{keys_sorted, uniq, seg_off, seg_of_entry};
-  TGR_K(flag_count_kernel)<<<nb, kScanBlock, 0, st>>>(f, n, block_cnt);
+  const int nb = (int)((n + kDdTile - 1) / kDdTile);
+  TGR_K(dedup_count_kernel)<<<nb, kDdThreads, 0, st>>>(keys_sorted, n, block_cnt, n_dev, vec);
   TGR_K(block_scan_kernel)<<<1, kScanBlock, 0, st>>>(block_cnt, nb, n_unique_dev);
-  TGR_K(flag_emit_kernel)<<<nb, kScanBlock, 0, st>>>(f, n, block_cnt);
-  TGR_K(dedup_finish_kernel)<<<1, 1, 0, st>>>(seg_off, n_unique_dev, n);
+  TGR_K(dedup_emit_kernel)<<<nb, kDdThreads, 0, st>>>(keys_sorted, n, block_cnt, uniq, seg_off, seg_of_entry, sc, n_dev, vec);
+  TGR_K(dedup_finish_kernel)<<<1, 1, 0, st>>>(seg_off, n_unique_dev, n, n_dev);
   return check_launch("dedup");
 }
 
+static int adam_rows_impl(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
+                          const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam, const tgr_adam_t* adam_dev,
+                          void* stream);
+
 extern "C" int tgr_adam_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
                              const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam, void* stream) {
+  TGR_REQUIRE(adam, "null argument");
+  return adam_rows_impl(tables, n_tables, H, uniq, grads, n_unique_dev, max_unique, adam, nullptr, stream);
+}
+
+extern "C" int tgr_adam_rows_dev(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
+                                 const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam_dev, void* stream) {
+  TGR_REQUIRE(adam_dev, "null argument");
+  return adam_rows_impl(tables, n_tables, H, uniq, grads, n_unique_dev, max_unique, nullptr, adam_dev, stream);
+}
+
+static int adam_rows_impl(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
+                          const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam, const tgr_adam_t* adam_dev,
+                          void* stream) {
   tgr::TimedScope tgr_timed_("adam_rows", stream);
-  TGR_REQUIRE(uniq && grads && n_unique_dev && adam, "null argument");
+  TGR_REQUIRE(uniq && grads && n_unique_dev, "null argument");
   RowParams rp{};
   if (int rc = fill_row_params(rp, tables, n_tables, H)) return rc;
   for (int t = 0; t < n_tables; ++t) TGR_REQUIRE(rp.w[t] && rp.m[t] && rp.v[t], "table %d: weight/exp_avg/exp_avg_sq NULL", t);
-  rp.adam = *adam;
+  if (adam) rp.adam = *adam;
+  rp.adam_dev = adam_dev;
   if (max_unique <= 0) return 0;
   int64_t blocks = (max_unique * rp.H4 + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   TGR_K(rows_kernel<0>)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rp, uniq, grads, n_unique_dev);
   return check_launch("adam_rows");
+}
+
+namespace tgr {
+struct DenseParams {
+  tgr_dense_list_t l;
+  int32_t first_block[TGR_MAX_DENSE + 1];
+  tgr_adam_t adam;
+  const tgr_adam_t* adam_dev;
+};
+constexpr int kDenseChunk = 1024;   // elements per CTA (256 threads x 4)
+__global__ void __launch_bounds__(256) adam_dense_kernel(const __grid_constant__ DenseParams p) {
+  int t = 0;
+  while (t + 1 < p.l.n && (int)blockIdx.x >= p.first_block[t + 1]) ++t;
+  const tgr_adam_t ad = p.adam_dev ? *p.adam_dev : p.adam;
+  const int64_t i0 = (int64_t)(blockIdx.x - p.first_block[t]) * kDenseChunk;
+  float* w = p.l.w[t];
+  float* m = p.l.m[t];
+  float* v = p.l.v[t];
+  const float* g = p.l.g[t];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = i0 + k * 256 + threadIdx.x;
+    if (i < p.l.numel[t]) {
+      float ww = w[i], mm = m[i], vv = v[i];
+      adam_elem(ww, mm, vv, __ldg(g + i) * ad.grad_scale, ad);
+      w[i] = ww; m[i] = mm; v[i] = vv;
+    }
+  }
+}
+}  // namespace tgr
+
+extern "C" int tgr_adam_dense(const tgr_dense_list_t* list, const tgr_adam_t* adam, const tgr_adam_t* adam_dev, void* stream) {
+  tgr::TimedScope tgr_timed_("adam_dense", stream);
+  TGR_REQUIRE(list && list->n > 0 && list->n <= TGR_MAX_DENSE, "bad dense list");
+  TGR_REQUIRE((adam != nullptr) != (adam_dev != nullptr), "exactly one of adam / adam_dev");
+  DenseParams p{};
+  p.l = *list;
+  int blocks = 0;
+  for (int t = 0; t < list->n; ++t) {
+    TGR_REQUIRE(list->w[t] && list->g[t] && list->m[t] && list->v[t] && list->numel[t] > 0, "dense tensor %d: null / empty", t);
+    p.first_block[t] = blocks;
+    blocks += (int)((list->numel[t] + kDenseChunk - 1) / kDenseChunk);
+  }
+  p.first_block[list->n] = blocks;
+  if (adam) p.adam = *adam;
+  p.adam_dev = adam_dev;
+  TGR_K(adam_dense_kernel)<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("adam_dense");
 }
 
 extern "C" int tgr_scatter_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,

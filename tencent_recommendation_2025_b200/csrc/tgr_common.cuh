@@ -36,6 +36,21 @@ class TimedScope {
 // Every kernel launch of the library goes through TGR_K(kernel)<<<...>>>(...): a comma expression bumps a process-wide
 // counter ahead of the launch, so tgr_launch_count() is a COUNT of launches, not an estimate (bench.py gpu_launches).
 void count_launch();
+// variants whose entry count lives in device memory (n = capacity, *n_dev <= n the count when the kernels run): the
+// launch sequence is then a function of the call SHAPES only and can be captured in a CUDA graph (tgr_fact_group_t.n_is_capacity)
+int sort_pairs_dn(const uint32_t* keys_in, const uint32_t* srcs_in, uint32_t* keys_out, uint32_t* srcs_out, int64_t n,
+                  int key_bits, void* workspace, size_t workspace_bytes, const int32_t* n_dev, void* stream);
+int dedup_dn(const uint32_t* keys_sorted, int64_t n, uint32_t* uniq, int32_t* seg_off, int32_t* seg_of_entry,
+             int32_t* n_unique_dev, void* workspace, size_t workspace_bytes, const int32_t* n_dev, void* stream);
+int dedup_remap_dn(const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n, uint32_t* uniq, int32_t* seg_off,
+                   int32_t* seg_of_entry, int32_t* n_unique_dev, void* workspace, size_t workspace_bytes, const tgr_call_t* calls,
+                   int n_calls, int32_t* const* ids_out, const int32_t* n_dev, void* stream);
+int remap_scatter_dn(const uint32_t* srcs_sorted, const int32_t* seg_of_entry, int64_t n, const int32_t* perm,
+                     const tgr_call_t* calls, int n_calls, int32_t* const* ids_out, const int32_t* n_dev, void* stream);
+int bwd_reduce_dn(const tgr_table_t* tables, int n_tables, int H, const tgr_call_t* calls, int n_calls,
+                  const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n, int mode, const int32_t* seg_of_entry,
+                  float* grads_out, const tgr_adam_t* adam, void* workspace, size_t workspace_bytes, const int32_t* n_dev,
+                  void* stream);
 #define TGR_K(...) ::tgr::count_launch(), __VA_ARGS__
 
 constexpr int kNumSMs = 148;  // B200

@@ -107,6 +107,24 @@ static size_t carve(tgr_fact_group_t* g, void* arena, int n_tables) {
   return cv.off;
 }
 
+// side stream + fork / join events of the mm branch, one set per device (created on first use, i.e. in a warm-up step and
+// never during a graph capture)
+struct Branch {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static Branch* branch_of_device() {
+  static Branch b[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (b[dev].side == nullptr) {
+    if (cudaStreamCreateWithFlags(&b[dev].side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&b[dev].fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&b[dev].join, cudaEventDisableTiming);
+  }
+  return &b[dev];
+}
+
 }  // namespace tgr
 
 using namespace tgr;
@@ -135,27 +153,81 @@ extern "C" int tgr_fact_prepare(const tgr_table_t* tables, int n_tables, tgr_fac
   TGR_REQUIRE(arena_bytes >= need, "arena too small (%zu < %zu)", arena_bytes, need);
   g->projected = 0;
   g->n_backward = 0;
+  g->mm_done = g->mm_joined = 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g->n_mm > 0)
+    if (Branch* br = branch_of_device()) cudaEventRecord(br->fork, st);   // where tgr_fact_mm_branch (if called) forks from
   for (int f = 0; f < g->n_mm; ++f) {   // A = dz^T x and s = colsum(dz) accumulate over the group's calls
     cudaMemsetAsync(g->mm_A[f], 0, (size_t)g->H * g->mm_dim[f] * sizeof(float), st);
     cudaMemsetAsync(g->mm_s[f], 0, (size_t)g->H * sizeof(float), st);
   }
   if (int rc = tgr_bwd_build_keys(tables, n_tables, g->calls, g->n_calls, g->keys_in, g->srcs_in, g->n_valid, g->ws,
                                   g->ws_bytes, stream)) return rc;
-  if (int rc = tgr_sort_pairs(g->keys_in, g->srcs_in, g->keys, g->srcs, g->n, g->key_bits, g->ws, g->ws_bytes, stream))
+  // n_is_capacity: g->n only bounds the count; the kernels read the count build_keys left in g->n_valid, so the launch
+  // sequence depends on the calls' shapes alone (CUDA-graph capture, graphed.py)
+  const int32_t* nd = g->n_is_capacity ? g->n_valid : nullptr;
+  if (int rc = sort_pairs_dn(g->keys_in, g->srcs_in, g->keys, g->srcs, g->n, g->key_bits, g->ws, g->ws_bytes, nd, stream))
     return rc;
-  if (int rc = tgr_dedup(g->keys, g->n, g->uniq, g->seg_off, g->seg_of, g->n_unique, g->ws, g->ws_bytes, stream)) return rc;
+  // dedup + id remap of the SINGLE slots in one pass over the sorted pairs (ids_u zeroed first: padding ids stay 0)
   int32_t* outs[TGR_MAX_CALLS];
   for (int c = 0; c < g->n_calls; ++c) {
     const tgr_call_t& cl = g->calls[c];
     outs[c] = g->ids_u[c];
     cudaMemsetAsync(g->ids_u[c], 0, (size_t)cl.T * cl.n_single * sizeof(int32_t), st);
   }
-  if (int rc = tgr_remap_scatter(g->srcs, g->seg_of, g->n, nullptr, g->calls, g->n_calls, outs, stream)) return rc;
+  if (int rc = dedup_remap_dn(g->keys, g->srcs, g->n, g->uniq, g->seg_off, g->seg_of, g->n_unique, g->ws, g->ws_bytes, g->calls,
+                              g->n_calls, outs, nd, stream)) return rc;
   // array values (a token may hold several): searching remap, they are few — one launch for all of them
   if (int rc = tgr_remap_arrays(tables, n_tables, g->calls, g->n_calls, g->uniq, g->n_unique, nullptr, g->arr_u, stream))
     return rc;
   return check_launch("fact_prepare");
+}
+
+static int mm_fold_all(const tgr_fact_params_t* prm, tgr_fact_group_t* g, void* stream) {
+  const int H = g->H;
+  for (int f = 0; f < g->n_mm; ++f) {
+    const tgr_mm_feat_t& m = prm->mm[f];
+    TGR_REQUIRE(m.mm_dim == g->mm_dim[f], "mm_dim mismatch");
+    if (int rc = tgr_fact_mm_fold(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, H, m.mm_dim, g->fold_M[f],
+                                  g->fold_c[f], stream)) return rc;
+    if (tgr_mm_proj_fwd_tc_supported(g->mm_x_dtype, m.mm_dim, H))   // wide bf16 feature: tcgen05 path wants a bf16 M
+      if (int rc = tgr_split_bf16(g->fold_M[f], (int64_t)H * m.mm_dim, g->fold_Mb[f],
+                                  (uint16_t*)g->fold_Mb[f] + (size_t)H * m.mm_dim, stream)) return rc;
+  }
+  return 0;
+}
+
+static int mm_project_call(tgr_fact_group_t* g, int c, void* stream) {
+  const int H = g->H;
+  const tgr_call_t& cl = g->calls[c];
+  for (int f = 0; f < g->n_mm; ++f) {
+    TGR_REQUIRE(g->mm_x[c][f] != nullptr, "mm input %d of call %d is NULL", f, c);
+    if (tgr_mm_proj_fwd_tc_supported(g->mm_x_dtype, g->mm_dim[f], H)) {
+      if (int rc = tgr_mm_proj_fwd_tc(g->mm_x[c][f], cl.T, g->mm_dim[f], g->fold_Mb[f], 2, g->fold_c[f], H, g->mmz[c][f], H,
+                                      TGR_DTYPE_F32, stream)) return rc;
+      continue;
+    }
+    if (int rc = tgr_mm_proj_fwd(g->mm_x[c][f], g->mm_x_dtype, cl.T, g->mm_dim[f], g->fold_M[f], g->fold_c[f], H,
+                                 g->mmz[c][f], H, TGR_DTYPE_F32, stream)) return rc;
+  }
+  return 0;
+}
+
+extern "C" int tgr_fact_mm_branch(const tgr_fact_params_t* prm, tgr_fact_group_t* g, void* stream) {
+  if (int rc = check_group(g)) return rc;
+  TGR_REQUIRE(prm != nullptr && prm->n_mm == g->n_mm, "bad params");
+  if (g->n_mm == 0 || g->mm_done) return 0;
+  TGR_REQUIRE(!g->projected, "tgr_fact_mm_branch must precede the group's first forward");
+  Branch* br = branch_of_device();
+  TGR_REQUIRE(br != nullptr, "could not create the side stream");
+  cudaStreamWaitEvent(br->side, br->fork, 0);          // recorded by tgr_fact_prepare on the caller's stream
+  if (int rc = mm_fold_all(prm, g, br->side)) return rc;
+  for (int c = 0; c < g->n_calls; ++c)
+    if (int rc = mm_project_call(g, c, br->side)) return rc;
+  cudaEventRecord(br->join, br->side);
+  (void)stream;
+  g->mm_done = 1;
+  return check_launch("fact_mm_branch");
 }
 
 extern "C" int tgr_fact_call_forward(const tgr_table_t* tables, int n_tables, const tgr_fact_params_t* prm,
@@ -169,27 +241,20 @@ extern "C" int tgr_fact_call_forward(const tgr_table_t* tables, int n_tables, co
     tgr_row_source_t src = g->src;
     if (src.n_peers > 0) src.save_rows = g->rows_local;   // read the owners' shards once; the backward uses the copy
     if (int rc = tgr_fact_project_rows(tables, n_tables, H, &prm->dnn, g->uniq, g->n_unique, g->n, &src, g->P, stream)) return rc;
-    for (int f = 0; f < g->n_mm; ++f) {
-      const tgr_mm_feat_t& m = prm->mm[f];
-      TGR_REQUIRE(m.mm_dim == g->mm_dim[f], "mm_dim mismatch");
-      if (int rc = tgr_fact_mm_fold(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, H, m.mm_dim, g->fold_M[f],
-                                    g->fold_c[f], stream)) return rc;
-      if (tgr_mm_proj_fwd_tc_supported(g->mm_x_dtype, m.mm_dim, H))   // wide bf16 feature: tcgen05 path wants a bf16 M
-        if (int rc = tgr_split_bf16(g->fold_M[f], (int64_t)H * m.mm_dim, g->fold_Mb[f],
-                                    (uint16_t*)g->fold_Mb[f] + (size_t)H * m.mm_dim, stream)) return rc;
-    }
+    if (!g->mm_done)
+      if (int rc = mm_fold_all(prm, g, stream)) return rc;
     g->projected = 1;
   }
   tgr_call_t& cl = g->calls[c];
-  for (int f = 0; f < g->n_mm; ++f) {
-    TGR_REQUIRE(g->mm_x[c][f] != nullptr, "mm input %d of call %d is NULL", f, c);
-    if (tgr_mm_proj_fwd_tc_supported(g->mm_x_dtype, g->mm_dim[f], H)) {
-      if (int rc = tgr_mm_proj_fwd_tc(g->mm_x[c][f], cl.T, g->mm_dim[f], g->fold_Mb[f], 2, g->fold_c[f], H, g->mmz[c][f], H,
-                                      TGR_DTYPE_F32, stream)) return rc;
-      continue;
+  if (g->mm_done) {
+    if (!g->mm_joined) {
+      Branch* br = branch_of_device();
+      TGR_REQUIRE(br != nullptr, "side stream missing");
+      cudaStreamWaitEvent((cudaStream_t)stream, br->join, 0);
+      g->mm_joined = 1;
     }
-    if (int rc = tgr_mm_proj_fwd(g->mm_x[c][f], g->mm_x_dtype, cl.T, g->mm_dim[f], g->fold_M[f], g->fold_c[f], H,
-                                 g->mmz[c][f], H, TGR_DTYPE_F32, stream)) return rc;
+  } else if (int rc = mm_project_call(g, c, stream)) {
+    return rc;
   }
   return tgr_fact_forward(&cl, H, g->ids_u[c], call_arr_extent(cl) ? g->arr_u[c] : nullptr, g->P, (const float* const*)g->mmz[c], g->n_mm, prm->b_item,
                           call_has_user(cl) ? prm->b_user : nullptr, out, g->mask[c], stream);
@@ -261,8 +326,8 @@ extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, c
     calls[i].user_ld = H;
     calls[i].cat_dtype = TGR_DTYPE_F32;
   }
-  if (int rc = tgr_bwd_reduce(tables, n_tables, H, calls, g->n_calls, g->keys, g->srcs, g->n, 0, g->seg_of, g->G, nullptr,
-                              g->ws, g->ws_bytes, stream)) return rc;
+  if (int rc = bwd_reduce_dn(tables, n_tables, H, calls, g->n_calls, g->keys, g->srcs, g->n, 0, g->seg_of, g->G, nullptr,
+                             g->ws, g->ws_bytes, g->n_is_capacity ? g->n_valid : nullptr, stream)) return rc;
   tgr_row_source_t src = g->src;
   if (src.n_peers > 0) {   // the rows were copied out of the peers' shards by the forward projection
     src = tgr_row_source_t{};

@@ -39,8 +39,10 @@ struct RedParams {
   float* cta_head;              // [n_cta, H]
   float* cta_tail;              // [n_cta, H]
   int64_t n;
+  const int32_t* n_dev;         // != NULL: n is a capacity, the entry count is *n_dev when the kernels run
   int32_t H4;
   int32_t mode;
+  __device__ __forceinline__ int64_t count() const { return n_dev ? min(n, (int64_t)__ldg(n_dev)) : n; }
 };
 
 template <int LANES>
@@ -94,8 +96,12 @@ __global__ void __launch_bounds__(kRedThreads, 4) reduce_tiles_kernel(const __gr
 
   const int tid = threadIdx.x, lane = tid % LANES, grp = tid / LANES;
   const int H4 = p.H4;
-  const int64_t n = p.n;
+  const int64_t n = p.count();
   const int64_t cta_a = (int64_t)blockIdx.x * TILE;
+  if (cta_a >= n) {            // tile past the data (capacity-sized grid)
+    if (p.mode == 1 && tid == 0) p.row_cnt[blockIdx.x] = 0;
+    return;
+  }
   const int cnt_cta = (int)(min(n, cta_a + TILE) - cta_a);
 
   for (int i = tid; i < cnt_cta + 2; i += kRedThreads) {
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(kRedThreads) reduce_fixup_kernel(const __grid_
   __shared__ float4 s_part[G][NJ * LANES];
   const int lane = threadIdx.x % LANES, grp = threadIdx.x / LANES;
   const int c0 = blockIdx.x;
-  const int64_t n = p.n;
+  const int64_t n = p.count();
   const int H4 = p.H4;
   const int64_t a = (int64_t)c0 * TILE, b = min(n, a + TILE);
   if (b >= n) return;
@@ -359,6 +365,14 @@ extern "C" int tgr_bwd_reduce(const tgr_table_t* tables, int n_tables, int H, co
                               const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n, int mode,
                               const int32_t* seg_of_entry, float* grads_out, const tgr_adam_t* adam, void* workspace,
                               size_t workspace_bytes, void* stream) {
+  return tgr::bwd_reduce_dn(tables, n_tables, H, calls, n_calls, keys_sorted, srcs_sorted, n, mode, seg_of_entry, grads_out, adam,
+                            workspace, workspace_bytes, nullptr, stream);
+}
+
+int tgr::bwd_reduce_dn(const tgr_table_t* tables, int n_tables, int H, const tgr_call_t* calls, int n_calls,
+                       const uint32_t* keys_sorted, const uint32_t* srcs_sorted, int64_t n, int mode,
+                       const int32_t* seg_of_entry, float* grads_out, const tgr_adam_t* adam, void* workspace,
+                       size_t workspace_bytes, const int32_t* n_dev, void* stream) {
   tgr::TimedScope tgr_timed_("bwd_reduce", stream);
   TGR_REQUIRE(calls && n_calls > 0 && n_calls <= TGR_MAX_CALLS, "bad calls");
   TGR_REQUIRE(H > 0 && H % 4 == 0 && H <= 512, "H=%d unsupported (multiple of 4, <= 512)", H);
@@ -389,6 +403,7 @@ extern "C" int tgr_bwd_reduce(const tgr_table_t* tables, int n_tables, int H, co
   p.keys = keys_sorted;
   p.srcs = srcs_sorted;
   p.n = n;
+  p.n_dev = n_dev;
   p.H4 = H / 4;
   p.mode = mode;
   const int tile = red_tile(p.H4);

@@ -31,7 +31,9 @@ __global__ void __launch_bounds__(256) scatter_user_kernel(const int32_t* __rest
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n_tok * n_cols) return;
   const int u = i / n_cols, j = i - u * n_cols;
-  ids[(size_t)__ldg(tok + u) * n_single + col0 + j] = __ldg(vals + i);
+  const int t = __ldg(tok + u);
+  if (t < 0) return;                       // padding entry of a fixed-shape call
+  ids[(size_t)t * n_single + col0 + j] = __ldg(vals + i);
 }
 
 // out[t, :] = table[item_ids[t], :] (16-byte pieces; rows are mm_dim * esz bytes, a multiple of 16)

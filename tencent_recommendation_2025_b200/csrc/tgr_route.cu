@@ -223,7 +223,9 @@ struct ScatterParams {
 __global__ void __launch_bounds__(256) remap_scatter_kernel(const uint32_t* __restrict__ srcs,
                                                             const int32_t* __restrict__ seg_of_entry, int64_t n,
                                                             const int32_t* __restrict__ perm,
-                                                            const __grid_constant__ ScatterParams p) {
+                                                            const __grid_constant__ ScatterParams p,
+                                                            const int32_t* __restrict__ n_dev) {
+  if (n_dev) n = min(n, (int64_t)__ldg(n_dev));
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t src = __ldg(srcs + e);
     const int call = src >> TGR_SRC_CALL_SHIFT;
@@ -239,6 +241,11 @@ __global__ void __launch_bounds__(256) remap_scatter_kernel(const uint32_t* __re
 
 extern "C" int tgr_remap_scatter(const uint32_t* srcs_sorted, const int32_t* seg_of_entry, int64_t n, const int32_t* perm,
                                  const tgr_call_t* calls, int n_calls, int32_t* const* ids_out, void* stream) {
+  return tgr::remap_scatter_dn(srcs_sorted, seg_of_entry, n, perm, calls, n_calls, ids_out, nullptr, stream);
+}
+
+int tgr::remap_scatter_dn(const uint32_t* srcs_sorted, const int32_t* seg_of_entry, int64_t n, const int32_t* perm,
+                          const tgr_call_t* calls, int n_calls, int32_t* const* ids_out, const int32_t* n_dev, void* stream) {
   tgr::TimedScope tgr_timed_("remap_scatter", stream);
   TGR_REQUIRE(n >= 0 && n_calls > 0 && n_calls <= TGR_MAX_CALLS, "bad n / n_calls");
   if (n == 0) return 0;
@@ -254,7 +261,7 @@ extern "C" int tgr_remap_scatter(const uint32_t* srcs_sorted, const int32_t* seg
   }
   int64_t blocks = (n + 255) / 256;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  TGR_K(remap_scatter_kernel)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(srcs_sorted, seg_of_entry, n, perm, p);
+  TGR_K(remap_scatter_kernel)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(srcs_sorted, seg_of_entry, n, perm, p, n_dev);
   return check_launch("remap_scatter");
 }
 

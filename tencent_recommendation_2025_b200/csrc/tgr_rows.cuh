@@ -13,6 +13,7 @@ struct RowParams {
   int32_t n_tables;
   int32_t H4;
   tgr_adam_t adam;
+  const tgr_adam_t* adam_dev;   // != NULL: the hyper-parameters are read from device memory when the kernel runs (graph replay)
 };
 
 __device__ __forceinline__ float adam_elem(float& w, float& m, float& v, float g, const tgr_adam_t& a) {

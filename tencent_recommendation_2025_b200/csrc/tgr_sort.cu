@@ -33,22 +33,35 @@ struct SortGeom {
   int n_blocks;
 };
 
-static SortGeom sort_geom(int64_t n) {
+__host__ __device__ inline int sort_tile_of(int64_t n) {
   int64_t tile = (n + kNumSMs - 1) / kNumSMs;
   tile = (tile + kSortThreads - 1) / kSortThreads * kSortThreads;
   if (tile < kSortThreads) tile = kSortThreads;
   if (tile > kSortMaxTile) tile = kSortMaxTile;
+  return (int)tile;
+}
+
+// n_blocks is the LAUNCHED grid and the row pitch of the block histograms. It covers every n' <= n: when the entry count
+// is only known on the device (n = capacity, the kernels read n' and derive the tile from it) a smaller n' can need MORE
+// blocks than n does (tile(n') shrinks in steps of 512), but never more than min(SMs, ceil(n / 512)) while one wave
+// suffices. Blocks past the data see an empty range and write zero histograms.
+static SortGeom sort_geom(int64_t n) {
   SortGeom g;
-  g.tile = (int)tile;
-  g.n_blocks = (int)((n + tile - 1) / tile);
-  if (g.n_blocks < 1) g.n_blocks = 1;
+  g.tile = sort_tile_of(n);
+  int64_t nb = (n + g.tile - 1) / g.tile;
+  const int64_t wave = (n + kSortThreads - 1) / kSortThreads < kNumSMs ? (n + kSortThreads - 1) / kSortThreads : kNumSMs;
+  if (nb < wave) nb = wave;
+  if (nb < 1) nb = 1;
+  g.n_blocks = (int)nb;
   return g;
 }
 
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int tile,
                                                                   int shift, int bits, int nb,
-                                                                  int32_t* __restrict__ block_hist /*[R][nb]*/) {
+                                                                  int32_t* __restrict__ block_hist /*[R][nb]*/,
+                                                                  const int32_t* __restrict__ n_dev) {
   extern __shared__ int32_t sh[];   // [R]
+  if (n_dev) { n = min(n, __ldg(n_dev)); tile = sort_tile_of(n); }   // count known on the device only (n = capacity)
   const int R = 1 << bits;
   const uint32_t mask = (uint32_t)R - 1u;
   for (int i = threadIdx.x; i < R; i += kSortThreads) sh[i] = 0;
@@ -134,8 +147,10 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
                                                                      uint32_t* __restrict__ vals_out, int n, int tile,
                                                                      int shift, int bits, int nb,
                                                                      const int32_t* __restrict__ block_off /*[R][nb]*/,
-                                                                     const int32_t* __restrict__ bin_base /*[R]*/) {
+                                                                     const int32_t* __restrict__ bin_base /*[R]*/,
+                                                                     const int32_t* __restrict__ n_dev) {
   extern __shared__ __align__(16) unsigned char sort_smem[];
+  if (n_dev) { n = min(n, __ldg(n_dev)); tile = sort_tile_of(n); }
   const int R = 1 << bits;
   int32_t* base = reinterpret_cast<int32_t*>(sort_smem);                  // [R] first output position of (block, digit)
   uint16_t* wh = reinterpret_cast<uint16_t*>(sort_smem + (size_t)R * 4);  // [kSortWarps][R] counts, then running offsets
@@ -216,6 +231,12 @@ extern "C" size_t tgr_sort_workspace_bytes(int64_t n) {
 
 extern "C" int tgr_sort_pairs(const uint32_t* keys_in, const uint32_t* srcs_in, uint32_t* keys_out, uint32_t* srcs_out,
                               int64_t n, int key_bits, void* workspace, size_t workspace_bytes, void* stream) {
+  return tgr::sort_pairs_dn(keys_in, srcs_in, keys_out, srcs_out, n, key_bits, workspace, workspace_bytes, nullptr, stream);
+}
+
+// n_dev != NULL: n is a capacity, the entry count is *n_dev (<= n) when the kernels run (CUDA-graph replay)
+int tgr::sort_pairs_dn(const uint32_t* keys_in, const uint32_t* srcs_in, uint32_t* keys_out, uint32_t* srcs_out,
+                       int64_t n, int key_bits, void* workspace, size_t workspace_bytes, const int32_t* n_dev, void* stream) {
   tgr::TimedScope tgr_timed_("sort_pairs", stream);
   TGR_REQUIRE(n >= 0 && n < (1ll << 31), "n out of range");
   TGR_REQUIRE(key_bits > 0 && key_bits <= 32, "key_bits=%d out of range", key_bits);
@@ -245,11 +266,11 @@ extern "C" int tgr_sort_pairs(const uint32_t* keys_in, const uint32_t* srcs_in, 
     const bool to_out = ((P - 1 - p) % 2) == 0;   // the last pass lands in the caller's output
     uint32_t* kdst = to_out ? keys_out : keys_tmp;
     uint32_t* vdst = to_out ? srcs_out : srcs_tmp;
-    TGR_K(radix_hist_kernel)<<<g.n_blocks, kSortThreads, (size_t)R * 4, st>>>(ksrc, (int)n, g.tile, shift, bits, g.n_blocks, block_hist);
+    TGR_K(radix_hist_kernel)<<<g.n_blocks, kSortThreads, (size_t)R * 4, st>>>(ksrc, (int)n, g.tile, shift, bits, g.n_blocks, block_hist, n_dev);
     TGR_K(radix_binscan_kernel)<<<(R * 32 + kSortThreads - 1) / kSortThreads, kSortThreads, 0, st>>>(block_hist, g.n_blocks, R, bin_total);
     TGR_K(radix_totals_kernel)<<<1, 1024, 0, st>>>(bin_total, R, bin_base);
     TGR_K(radix_scatter_kernel)<<<g.n_blocks, kSortThreads, (size_t)R * 4 + (size_t)kSortWarps * R * 2, st>>>(ksrc, vsrc, kdst, vdst, (int)n, g.tile, shift,
-                                                                                    bits, g.n_blocks, block_hist, bin_base);
+                                                                                    bits, g.n_blocks, block_hist, bin_base, n_dev);
     if (int rc = check_launch("sort_pairs")) return rc;
     ksrc = kdst;
     vsrc = vdst;

@@ -114,6 +114,12 @@ class FactoredEngine(EmbeddingEngine):
         self._prm_fresh = False
         self._tab_memo: Dict[bool, object] = {}
         self._arena_pool: List[torch.Tensor] = []
+        self.adam_dev: Optional[torch.Tensor] = None   # device copy of the tgr_adam_t block (set by graphed.GraphedStep)
+        # fused mode may also own the path's Linear layers (itemdnn / userdnn / emb_transform): their gradients then stay in
+        # the group's accumulators (no autograd AccumulateGrad copies) and fused_step(dense=True) updates them in one launch
+        self.own_dense = False
+        self.overlap_mm = True      # prefetch(): mm branch on a side stream (tgr_fact_mm_branch)
+        self._dense_state: Dict[int, tuple] = {}
 
     # ------------------------------------------------------------------ structs: pointers are re-read once per group
     def _table_array(self, state: bool = False, grads=None):
@@ -165,7 +171,13 @@ class FactoredEngine(EmbeddingEngine):
             raise ValueError(f"at most {_lib.MAX_CALLS} calls per group")
         c = g.c
         c.n_calls, c.H, c.key_bits, c.n_mm = len(g.pbs), lay.H, lay.key_bits, len(self._mm_slots)
-        g.n = c.n = sum(pb.n_valid for pb in g.pbs)
+        if all(pb.n_cap is not None for pb in g.pbs):
+            # fixed-shape calls: nothing the launch sequence depends on may come from the buffers' CONTENT
+            g.n = c.n = sum(pb.n_cap for pb in g.pbs)
+            c.n_is_capacity = 1
+        else:
+            g.n = c.n = sum(pb.n_valid for pb in g.pbs)
+            c.n_is_capacity = 0
         x_dt = None
         for f, s in enumerate(self._mm_slots):
             c.mm_dim[f] = s.mm_dim
@@ -196,7 +208,7 @@ class FactoredEngine(EmbeddingEngine):
               "tgr_fact_prepare")
         self._t1("fact_prepare", e0)
         self.launches += 13 + 2 * len(g.pbs) + sum(1 for pb in g.pbs for z in pb.arr_nnz if z)
-        if _DEBUG:
+        if _DEBUG and not c.n_is_capacity:
             got = int(g._view(c.n_valid, (1,), torch.int32).item())
             if got != g.n:
                 raise _lib.TgrError(f"PackedBatch.n_valid mismatch: host {g.n}, device {got}")
@@ -221,8 +233,12 @@ class FactoredEngine(EmbeddingEngine):
         return _dtype_code(dt)
 
     def prefetch(self, pbs: Sequence[PackedBatch]) -> FactGroup:
-        self.current = self.prepare(pbs)
-        return self.current
+        self.current = g = self.prepare(pbs)
+        if self._mm_slots and self.overlap_mm:
+            # the forwards follow at once: fold + mm projection of every call on a side stream next to the key processing
+            check(self.lib.tgr_fact_mm_branch(C.byref(self._params()), C.byref(g.c), _stream()), "tgr_fact_mm_branch")
+            self.launches += len(self._mm_slots) * (1 + len(g.pbs))
+        return g
 
     def _group_of(self, pb: PackedBatch) -> FactGroup:
         g = self.current
@@ -324,11 +340,44 @@ class FactoredEngine(EmbeddingEngine):
         return len(groups) + super().discard_pending()
 
     # ------------------------------------------------------------------ row update
+    def _dense_update(self, g: FactGroup, adam):
+        """AdamW on itemdnn / userdnn / emb_transform from the group's gradient accumulators (tgr_adam_dense)."""
+        a = g.acc
+        pairs = [(self.dnn["item"].weight, a["dW_item"]), (self.dnn["item"].bias, a["db_item"])]
+        if a.get("dW_user") is not None:
+            pairs += [(self.dnn["user"].weight, a["dW_user"]), (self.dnn["user"].bias, a["db_user"])]
+        for s in self._mm_slots:
+            lin = self.mm[s.name]
+            pairs.append((lin.weight, a[f"dWmm/{s.name}"]))
+            if lin.bias is not None:
+                pairs.append((lin.bias, a[f"dbmm/{s.name}"]))
+        if len(pairs) > _lib.MAX_DENSE:
+            raise ValueError(f"more than {_lib.MAX_DENSE} dense tensors")
+        dl = _lib.DenseList()
+        dl.n = len(pairs)
+        for i, (p, gr) in enumerate(pairs):
+            st = self._dense_state.get(id(p))
+            if st is None or st[0].shape != p.shape or st[0].device != p.device:
+                st = self._dense_state[id(p)] = (torch.zeros_like(p.data), torch.zeros_like(p.data))
+            if p.dtype != torch.float32 or not p.data.is_contiguous():
+                raise TypeError("dense parameters must be contiguous float32")
+            dl.w[i], dl.g[i], dl.m[i], dl.v[i], dl.numel[i] = p.data.data_ptr(), gr.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), p.numel()
+        e0 = self._t0()
+        if self.adam_dev is not None:
+            check(self.lib.tgr_adam_dense(C.byref(dl), None, self.adam_dev.data_ptr(), _stream()), "tgr_adam_dense")
+        else:
+            check(self.lib.tgr_adam_dense(C.byref(dl), C.addressof(adam), None, _stream()), "tgr_adam_dense")
+        self._t1("adam_dense", e0)
+        self.launches += 1
+
     def fused_step(self, lr: float = 1e-3, betas=(0.9, 0.98), eps: float = 1e-8, weight_decay: float = 1e-2,
-                   grad_scale: float = 1.0):
+                   grad_scale: float = 1.0, dense: bool = False):
+        """``dense=True`` (needs ``own_dense``): also AdamW-update the path's Linear layers with the same hyper-parameters."""
         groups, self.ready = self.ready, []
         if not groups:
             return 0
+        if dense and (not self.own_dense or len(groups) != 1):
+            raise RuntimeError("fused_step(dense=True) needs engine.own_dense and the prefetch protocol (one group per step)")
         self._require_cuda()
         self.ensure_state()
         self._tab_memo.pop(True, None)
@@ -340,10 +389,17 @@ class FactoredEngine(EmbeddingEngine):
             g = groups[0]
             if g.n:
                 e0 = self._t0()
-                check(self.lib.tgr_adam_rows(tabs, len(self.tables), H, g.c.uniq, g.c.G, g.c.n_unique, g.c.cap, C.byref(adam),
-                                             _stream()), "tgr_adam_rows")
+                if self.adam_dev is not None:
+                    # hyper-parameter block in device memory (graphed.GraphedStep refreshes it before every replay)
+                    check(self.lib.tgr_adam_rows_dev(tabs, len(self.tables), H, g.c.uniq, g.c.G, g.c.n_unique, g.c.cap,
+                                                     self.adam_dev.data_ptr(), _stream()), "tgr_adam_rows_dev")
+                else:
+                    check(self.lib.tgr_adam_rows(tabs, len(self.tables), H, g.c.uniq, g.c.G, g.c.n_unique, g.c.cap,
+                                                 C.byref(adam), _stream()), "tgr_adam_rows")
                 self._t1("adam_rows", e0)
                 self.launches += 1
+            if dense and g.acc is not None:
+                self._dense_update(g, adam)
             g.release()
             return g.n
         # several groups touched the step (per-call protocol): merge their (key, row gradient) lists in group order,
@@ -402,6 +458,8 @@ class FactoredFn(torch.autograd.Function):
         names = list(eng.layout.item_emb_feat)
         if eng.mode == "fused":
             eng.ready.append(g)
+            if eng.own_dense:       # the Linear gradients stay in g.acc for fused_step(dense=True)
+                return (None, None, None, *grads)
         else:
             dense = eng.dense_from_rows(g)
             for i in range(n_t):

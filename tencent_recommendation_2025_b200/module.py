@@ -128,8 +128,21 @@ class _FeatEmbMixin:
         if getattr(eng, "path", "concat") == "factored":
             eng.prefetch(list(pbs))
 
-    def fused_step(self, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
+    def fused_step(self, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2, grad_scale=1.0, dense=False):
+        """Row update of the step's touched rows. ``dense=True`` (factored path, after ``own_dense_parameters()``): the same
+        AdamW also updates itemdnn / userdnn / emb_transform from the gradients the kernels accumulated."""
+        if dense:
+            return self._tgr_engine.fused_step(lr, betas, eps, weight_decay, grad_scale, dense=True)
         return self._tgr_engine.fused_step(lr, betas, eps, weight_decay, grad_scale)
+
+    def own_dense_parameters(self, own: bool = True):
+        """Fused mode, factored path: the engine also owns the path's Linear layers (model.py:150-151,166-167). Their
+        gradients are no longer handed to autograd (``.grad`` stays None — leave them out of the outer optimizer) and
+        ``fused_step(dense=True)`` updates them in one launch next to the row update."""
+        eng = self._tgr_engine
+        if getattr(eng, "path", "concat") != "factored" or eng.mode != "fused":
+            raise ValueError("own_dense_parameters needs the factored path in fused mode")
+        eng.own_dense = bool(own)
 
     def save_item_emb(self, item_ids, retrieval_ids, feat_dict, save_path, batch_size=1024):
         """Candidate-embedding sweep with the reference's signature and outputs (model/BaseLine/model.py:402-433):

@@ -193,6 +193,8 @@ class PackedBatch:
     mm_x: List[torch.Tensor]          # [T, mm_dim] float32 / bfloat16
     n_valid: int
     h2d_bytes: int = 0
+    n_cap: Optional[int] = None       # fixed-shape calls (resident.StepShape): upper bound of n_valid for ANY content of the
+                                      # buffers; the kernels then take the count from device memory (CUDA-graph replay)
 
     @property
     def T(self) -> int:

@@ -45,6 +45,7 @@ class SlimCall:
     arr_begin: List[int]
     arr_nnz: List[int]
     n_valid: int
+    n_cap: Optional[int] = None   # fixed-shape calls: bound of n_valid for any content (see CallShape)
 
     @property
     def T(self) -> int:
@@ -53,6 +54,43 @@ class SlimCall:
     @property
     def nbytes(self) -> int:
         return self.ints.numel() * 4
+
+
+@dataclass(frozen=True)
+class CallShape:
+    """Everything about a slim call that may size a buffer or a launch: with these fixed, two calls differ in CONTENT only
+    (user tokens padded with token index -1, array values padded with id 0 behind each array's last token), which is what a
+    captured CUDA graph needs (graphed.GraphedStep)."""
+
+    B: int
+    L: int
+    include_user: bool
+    n_user_cap: int
+    arr_caps: tuple
+
+    @staticmethod
+    def covering(pcs: Sequence[PackedCall], slack: float = 1.5, round_to: int = 1024) -> "CallShape":
+        """Shape that fits every example call with ``slack`` head-room on the array lengths."""
+        p0 = pcs[0]
+        n_arr = p0.arr_off.shape[0]
+        caps = []
+        for a in range(n_arr):
+            m = max(int(pc.arr_off[a, -1] - pc.arr_off[a, 0]) for pc in pcs)
+            caps.append((int(m * slack) + round_to) // round_to * round_to)
+        return CallShape(p0.B, p0.L, bool(p0.include_user), p0.B if p0.include_user else 0, tuple(caps))
+
+
+@dataclass
+class SlimStep:
+    """The slim calls of one step in ONE pinned buffer (one H2D copy per step); ``calls[i].ints`` are views of ``ints``."""
+
+    ints: torch.Tensor
+    calls: List[SlimCall]
+    bases: List[int]
+
+    @property
+    def n_valid(self) -> int:
+        return sum(c.n_valid for c in self.calls)
 
 
 class ResidentItemFeatures:
@@ -108,10 +146,8 @@ class ResidentItemFeatures:
         return cls(lay, feat, mm, device, mm_dtype)
 
     # ------------------------------------------------------------------ host side
-    def slim(self, pc: PackedCall, pin: Optional[bool] = None) -> SlimCall:
-        """What the data pipeline hands over for one call: ids + user tokens + user arrays (here derived from a packed call)."""
+    def _slim_parts(self, pc: PackedCall, shape: Optional[CallShape]):
         lay = self.layout
-        n_single = pc.ids.shape[1]
         item_ids = np.ascontiguousarray(pc.ids[:, self.id_col[pc.include_user]])
         if pc.include_user:
             ucols = pc.ids[:, self.user_col0:self.user_col0 + self.n_ucols]
@@ -121,18 +157,44 @@ class ResidentItemFeatures:
             tok, uvals = np.zeros(0, np.int32), np.zeros((0, self.n_ucols), np.int32)
         arr_tok = _arr_tok(pc)
         n_arr = pc.arr_off.shape[0]
-        parts = [item_ids, tok, uvals.reshape(-1), pc.arr_off.reshape(-1), pc.arr_val, arr_tok]
+        begins = [int(pc.arr_off[a, 0]) for a in range(n_arr)]
+        nnzs = [int(pc.arr_off[a, -1] - pc.arr_off[a, 0]) for a in range(n_arr)]
+        arr_off, arr_val = pc.arr_off, pc.arr_val
+        n_cap = None
+        if shape is not None:
+            if (pc.B, pc.L, bool(pc.include_user)) != (shape.B, shape.L, shape.include_user) or n_arr != len(shape.arr_caps):
+                raise ValueError("call does not match its CallShape")
+            if tok.size > shape.n_user_cap:
+                raise ValueError(f"{tok.size} user tokens exceed the shape's capacity {shape.n_user_cap}")
+            pad = shape.n_user_cap - tok.size
+            tok_p = np.concatenate([tok, np.full(pad, -1, np.int32)])             # -1: skipped by the scatter kernel
+            uvals_p = np.concatenate([uvals, np.zeros((pad, self.n_ucols), np.int32)])
+            val_p = np.zeros(sum(shape.arr_caps), np.int32)                         # id 0 = padding: emits no key
+            tok_a = np.zeros(sum(shape.arr_caps), np.int32)
+            off_p = np.empty_like(pc.arr_off)
+            b = 0
+            src = 0
+            for a, cap in enumerate(shape.arr_caps):
+                if nnzs[a] > cap:
+                    raise ValueError(f"array {a}: {nnzs[a]} values exceed the shape's capacity {cap}")
+                val_p[b:b + nnzs[a]] = pc.arr_val[begins[a]:begins[a] + nnzs[a]]
+                tok_a[b:b + nnzs[a]] = arr_tok[src:src + nnzs[a]]
+                off_p[a] = pc.arr_off[a] - begins[a] + b
+                src += nnzs[a]
+                b += cap
+            cl = lay.calls[pc.include_user]
+            n_cap = pc.T * cl.n_single + sum(shape.arr_caps)
+            begins_s = [int(x) for x in np.concatenate([[0], np.cumsum(shape.arr_caps)[:-1]])] if n_arr else []
+            parts = [item_ids, tok_p, uvals_p.reshape(-1), off_p.reshape(-1), val_p, tok_a]
+            meta = (shape.n_user_cap, n_arr, begins_s, [int(c) for c in shape.arr_caps])
+        else:
+            parts = [item_ids, tok, uvals.reshape(-1), pc.arr_off.reshape(-1), pc.arr_val, arr_tok]
+            meta = (int(tok.size), n_arr, begins, nnzs)
         sizes = [int(p.size) for p in parts]
         offs, tot = [], 0
         for sz in sizes:
             offs.append(tot)
             tot += (sz + 3) // 4 * 4
-        if pin is None:
-            pin = torch.cuda.is_available()
-        ints = torch.empty(max(tot, 4), dtype=torch.int32, pin_memory=pin)
-        v = ints.numpy()
-        for p, o, sz in zip(parts, offs, sizes):
-            v[o:o + sz] = p
         # entries the key builder emits: host-known without touching the feature values of the items
         in_range = (item_ids >= 0) & (item_ids < self.n_items)
         n = int(self.nnz_item[np.where(in_range, item_ids, 0)].sum(dtype=np.int64))
@@ -140,12 +202,40 @@ class ResidentItemFeatures:
             if pc.include_user:
                 n += int(np.count_nonzero((uvals[:, j] > 0) & (uvals[:, j] < r)))
         for a in range(n_arr):
-            lo, hi = int(pc.arr_off[a, 0]), int(pc.arr_off[a, -1])
-            vv = pc.arr_val[lo:hi]
+            vv = arr_val[begins[a]:begins[a] + nnzs[a]]
             n += int(np.count_nonzero((vv > 0) & (vv < self.arr_rows[a])))
-        begins = [int(pc.arr_off[a, 0]) for a in range(n_arr)]
-        nnzs = [int(pc.arr_off[a, -1] - pc.arr_off[a, 0]) for a in range(n_arr)]
-        return SlimCall(pc.B, pc.L, pc.include_user, ints, offs, sizes, int(tok.size), n_arr, begins, nnzs, n)
+        return parts, sizes, offs, max(tot, 4), meta, n, n_cap
+
+    def slim(self, pc: PackedCall, pin: Optional[bool] = None, shape: Optional[CallShape] = None,
+             out: Optional[torch.Tensor] = None) -> SlimCall:
+        """What the data pipeline hands over for one call: ids + user tokens + user arrays (here derived from a packed call).
+        ``shape``: pad to a fixed CallShape. ``out``: write into this (pinned) int32 buffer instead of allocating one."""
+        parts, sizes, offs, tot, meta, n, n_cap = self._slim_parts(pc, shape)
+        if out is None:
+            if pin is None:
+                pin = torch.cuda.is_available()
+            out = torch.empty(tot, dtype=torch.int32, pin_memory=pin)
+        elif out.numel() != tot:
+            raise ValueError(f"slim: the output buffer holds {out.numel()} ints, the call needs {tot}")
+        v = out.numpy()
+        for p, o, sz in zip(parts, offs, sizes):
+            v[o:o + sz] = p
+        return SlimCall(pc.B, pc.L, pc.include_user, out, offs, sizes, meta[0], meta[1], meta[2], meta[3], n, n_cap)
+
+    def slim_step(self, pcs: Sequence[PackedCall], shapes: Optional[Sequence[CallShape]] = None,
+                  pin: Optional[bool] = None) -> SlimStep:
+        """All calls of a step in one pinned buffer."""
+        shapes = list(shapes) if shapes is not None else [None] * len(pcs)
+        tots = [self._slim_parts(pc, sh)[3] for pc, sh in zip(pcs, shapes)]
+        if pin is None:
+            pin = torch.cuda.is_available()
+        ints = torch.empty(sum(tots), dtype=torch.int32, pin_memory=pin)
+        calls, bases, b = [], [], 0
+        for pc, sh, t in zip(pcs, shapes, tots):
+            calls.append(self.slim(pc, shape=sh, out=ints[b:b + t]))
+            bases.append(b)
+            b += t
+        return SlimStep(ints, calls, bases)
 
     def slim_items(self, item_ids, pin: Optional[bool] = None) -> SlimCall:
         """Slim call of the candidate sweep's shape (model.py:418-425): one 'sequence' of n item ids, no user side. Only
@@ -190,7 +280,7 @@ class ResidentItemFeatures:
             mm.append(out)
         return PackedBatch(sc.B, sc.L, sc.include_user, ids, dev_ints[o[3]:o[3] + s[3]].view(sc.n_arr, T + 1),
                            dev_ints[o[4]:o[4] + s[4]], dev_ints[o[5]:o[5] + s[5]], sc.arr_begin, sc.arr_nnz, mm, sc.n_valid,
-                           sc.nbytes)
+                           sc.nbytes, sc.n_cap)
 
     def to_device(self, sc: SlimCall) -> PackedBatch:
         return self.expand(sc, sc.ints.to(self.device, non_blocking=True))

@@ -102,3 +102,38 @@ def test_streaming_item_sweep_writes_the_same_files(tmp_path):
     assert a.shape == b.shape == (item_ids.size, cfg.H)
     assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
     assert np.array_equal(binfmt.load_emb(d1 / "id.u64bin", np.uint64), binfmt.load_emb(d2 / "id.u64bin", np.uint64))
+
+
+def test_fixed_shape_slim_calls_pad_without_changing_content():
+    """CallShape padding (graphed.GraphedStep): user tokens padded with -1, array values with id 0 behind the last token of
+    each array; offsets rebased to the per-array capacity regions; host counts unchanged."""
+    from tencent_recommendation_2025_b200.resident import CallShape, ResidentItemFeatures
+    cfg = SynthConfig(B=5, L=9, H=32, item_num=200, user_num=40, alpha=1.1, mm_ids=("81",), min_len=2)
+    world = SynthWorld(cfg, 1)
+    steps = [world.make_step(s) for s in range(3)]
+    store = ResidentItemFeatures.from_world(world, "cpu")
+    shapes = [CallShape.covering([st.calls[i] for st in steps]) for i in range(3)]
+    sigs = set()
+    for st in steps:
+        exact = store.slim_step(st.calls, pin=False)
+        fixed = store.slim_step(st.calls, shapes, pin=False)
+        sigs.add(tuple((tuple(c.offs), tuple(c.sizes), c.n_cap) for c in fixed.calls) + (fixed.ints.numel(),))
+        for pc, e, f, sh in zip(st.calls, exact.calls, fixed.calls, shapes):
+            assert f.n_valid == e.n_valid and e.n_cap is None and f.n_cap >= f.n_valid
+            ev, fv = e.ints.numpy(), f.ints.numpy()
+            assert np.array_equal(fv[f.offs[0]:f.offs[0] + f.sizes[0]], ev[e.offs[0]:e.offs[0] + e.sizes[0]])   # item ids
+            tok = fv[f.offs[1]:f.offs[1] + f.sizes[1]]
+            assert f.sizes[1] == sh.n_user_cap and np.array_equal(tok[:e.sizes[1]], ev[e.offs[1]:e.offs[1] + e.sizes[1]])
+            assert (tok[e.sizes[1]:] == -1).all()
+            n_arr = pc.arr_off.shape[0]
+            off = fv[f.offs[3]:f.offs[3] + f.sizes[3]].reshape(n_arr, pc.T + 1)
+            val = fv[f.offs[4]:f.offs[4] + f.sizes[4]]
+            atok = fv[f.offs[5]:f.offs[5] + f.sizes[5]]
+            for a in range(n_arr):
+                assert off[a, 0] == f.arr_begin[a] and f.arr_nnz[a] == sh.arr_caps[a]
+                for t in range(pc.T):
+                    want = pc.arr_val[pc.arr_off[a, t]:pc.arr_off[a, t + 1]]
+                    assert np.array_equal(val[off[a, t]:off[a, t + 1]], want)
+                    assert (atok[off[a, t]:off[a, t + 1]] == t).all()
+                assert (val[off[a, -1]:f.arr_begin[a] + f.arr_nnz[a]] == 0).all()
+    assert len(sigs) == 1, "every step must have the same buffer layout"
