@@ -661,14 +661,28 @@ __global__ void __launch_bounds__(kFT) fact_dw_reduce_kernel(const __grid_consta
                                                              const float* __restrict__ dw_part, int rows_grid,
                                                              float* dW_item, float* dW_user) {
   __shared__ float s_p[4][64];
+  __shared__ int s_ab[2];
   const int t = blockIdx.x;
   const int U = *n_unique_dev;
-  int lo = 0, hi = U;   // unique-row range [a, b) of table t by binary search on the sorted keys
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(uniq + mid) < p.key_base[t]) lo = mid + 1; else hi = mid; }
-  const int a = lo;
-  hi = U;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(uniq + mid) < p.key_base[t + 1]) lo = mid + 1; else hi = mid; }
-  const int b = lo;
+  // unique-row range [a, b) of table t: two 32-ary searches on the sorted keys, one warp each (a thread-serial binary
+  // search was 2 x 18 dependent L2 round trips = most of this kernel's 21 us, profiles/README.md r2 graph timeline)
+  if (threadIdx.x < 64) {
+    const int which = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t key = p.key_base[t + which];
+    int lo = 0, hi = U;
+    while (lo < hi) {
+      const int step = (hi - lo + 31) / 32;
+      const int i = lo + lane * step;
+      const bool lt = i < hi && __ldg(uniq + i) < key;
+      const int c = __popc(__ballot_sync(0xffffffffu, lt));
+      if (c == 0) break;
+      hi = min(hi, lo + c * step);
+      lo = lo + (c - 1) * step + 1;
+    }
+    if (lane == 0) s_ab[which] = lo;
+  }
+  __syncthreads();
+  const int a = s_ab[0], b = s_ab[1];
   if (b <= a) return;
   float* dW = p.side[t] == 0 ? dW_item : dW_user;
   if (dW == nullptr) return;

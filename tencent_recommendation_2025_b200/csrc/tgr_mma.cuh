@@ -15,11 +15,12 @@
 
 namespace tgr {
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// Round-to-nearest (ties away from zero) to 10 explicit mantissa bits: what cvt.rna.tf32.f32 returns for every finite
+// value, as two integer instructions. On sm_100a ptxas expands the cvt into an ~8-instruction FSETP/IMAD/LOP3/SEL
+// sequence; with two conversions per split and a split per fragment element that was 75 % of fact_dz_kernel's issue
+// slots (profiles/README.md r2, ncu source page). A mantissa carry runs into the exponent exactly as rounding up to the
+// next binade must; inf stays inf (the mask clears the added bits), NaN stays NaN.
+__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = to_tf32(x);

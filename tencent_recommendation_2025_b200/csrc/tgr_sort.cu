@@ -56,6 +56,7 @@ static SortGeom sort_geom(int64_t n) {
   return g;
 }
 
+template <bool IN_PAIRS>   // keys[i] or the .x of interleaved (key, payload) pairs
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int tile,
                                                                   int shift, int bits, int nb,
                                                                   int32_t* __restrict__ block_hist /*[R][nb]*/,
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t
   for (int i0 = a + threadIdx.x; i0 < b; i0 += kSortAhead * kSortThreads) {
     uint32_t k[kSortAhead];
 #pragma unroll
-    for (int j = 0; j < kSortAhead; ++j) k[j] = i0 + j * kSortThreads < b ? __ldg(keys + i0 + j * kSortThreads) : 0u;
+    for (int j = 0; j < kSortAhead; ++j)
+      k[j] = i0 + j * kSortThreads < b ? __ldg(keys + (size_t)(i0 + j * kSortThreads) * (IN_PAIRS ? 2 : 1)) : 0u;
 #pragma unroll
     for (int j = 0; j < kSortAhead; ++j)
       if (i0 + j * kSortThreads < b) atomicAdd(&sh[(k[j] >> shift) & mask], 1);
@@ -141,6 +143,11 @@ __global__ void __launch_bounds__(1024) radix_totals_kernel(const int32_t* __res
   }
 }
 
+// IN_PAIRS / OUT_PAIRS: the pass reads / writes interleaved (key, payload) pairs (keys_in / keys_out point at uint2[n],
+// vals_* unused). The intermediate buffer of a two-pass sort is interleaved: the first pass scatters its entries to 4096 bins
+// in effectively random order, so every entry is its own partial-sector write — one 8-byte write per entry instead of two
+// 4-byte ones halves the L2 write transactions of that pass.
+template <bool IN_PAIRS, bool OUT_PAIRS>
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                      const uint32_t* __restrict__ vals_in,
                                                                      uint32_t* __restrict__ keys_out,
@@ -168,7 +175,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
     for (int i0 = a; i0 < b; i0 += 32 * kSortAhead) {
       uint32_t k[kSortAhead];
 #pragma unroll
-      for (int j = 0; j < kSortAhead; ++j) k[j] = i0 + 32 * j + lane < b ? __ldg(keys_in + i0 + 32 * j + lane) : 0u;
+      for (int j = 0; j < kSortAhead; ++j)
+        k[j] = i0 + 32 * j + lane < b ? __ldg(keys_in + (size_t)(i0 + 32 * j + lane) * (IN_PAIRS ? 2 : 1)) : 0u;
 #pragma unroll
       for (int j = 0; j < kSortAhead; ++j) {
         if (i0 + 32 * j + lane < b) {
@@ -197,8 +205,14 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
 #pragma unroll
     for (int j = 0; j < kSortAhead; ++j) {
       const int i = i0 + 32 * j + lane;
-      k[j] = i < b ? __ldg(keys_in + i) : 0u;
-      v[j] = i < b ? __ldg(vals_in + i) : 0u;
+      if constexpr (IN_PAIRS) {
+        const uint2 kv = i < b ? __ldg(reinterpret_cast<const uint2*>(keys_in) + i) : make_uint2(0u, 0u);
+        k[j] = kv.x;
+        v[j] = kv.y;
+      } else {
+        k[j] = i < b ? __ldg(keys_in + i) : 0u;
+        v[j] = i < b ? __ldg(vals_in + i) : 0u;
+      }
     }
 #pragma unroll
     for (int j = 0; j < kSortAhead; ++j) {
@@ -210,7 +224,10 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
       __syncwarp();
       if (ok && lane == __ffs(m) - 1) mine[d] = (uint16_t)(mine[d] + __popc(m));
       __syncwarp();
-      if (ok) { keys_out[pos] = k[j]; vals_out[pos] = v[j]; }
+      if (ok) {
+        if constexpr (OUT_PAIRS) reinterpret_cast<uint2*>(keys_out)[pos] = make_uint2(k[j], v[j]);
+        else { keys_out[pos] = k[j]; vals_out[pos] = v[j]; }
+      }
     }
   }
 }
@@ -254,23 +271,35 @@ int tgr::sort_pairs_dn(const uint32_t* keys_in, const uint32_t* srcs_in, uint32_
   int32_t* bin_base = (int32_t*)((char*)bin_total + align_up((size_t)(1 << kSortMaxBits) * 4));
   const int P = sort_passes(key_bits);
   const int bits0 = (key_bits + P - 1) / P;
+  const int kScatterSmem = (1 << kSortMaxBits) * 4 + kSortWarps * (1 << kSortMaxBits) * 2;
   { static bool once = false;
-    if (!once) { cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (1 << kSortMaxBits) * 4 + kSortWarps * (1 << kSortMaxBits) * 2); once = true; } }
+    if (!once) {
+      cudaFuncSetAttribute(radix_scatter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem);
+      cudaFuncSetAttribute(radix_scatter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem);
+      cudaFuncSetAttribute(radix_scatter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterSmem);
+      once = true; } }
   const uint32_t* ksrc = keys_in;
   const uint32_t* vsrc = srcs_in;
   int shift = 0;
+  const bool pairs = P == 2;   // the intermediate buffer holds interleaved pairs (keys_tmp | srcs_tmp are contiguous: uint2[n])
   for (int p = 0; p < P; ++p) {
     const int bits = min(bits0, key_bits - shift);
     const int R = 1 << bits;
     const bool to_out = ((P - 1 - p) % 2) == 0;   // the last pass lands in the caller's output
     uint32_t* kdst = to_out ? keys_out : keys_tmp;
     uint32_t* vdst = to_out ? srcs_out : srcs_tmp;
-    TGR_K(radix_hist_kernel)<<<g.n_blocks, kSortThreads, (size_t)R * 4, st>>>(ksrc, (int)n, g.tile, shift, bits, g.n_blocks, block_hist, n_dev);
+    const bool in_pairs = pairs && p == 1, out_pairs = pairs && p == 0;
+    if (in_pairs) TGR_K(radix_hist_kernel<true>)<<<g.n_blocks, kSortThreads, (size_t)R * 4, st>>>(ksrc, (int)n, g.tile, shift, bits, g.n_blocks, block_hist, n_dev);
+    else TGR_K(radix_hist_kernel<false>)<<<g.n_blocks, kSortThreads, (size_t)R * 4, st>>>(ksrc, (int)n, g.tile, shift, bits, g.n_blocks, block_hist, n_dev);
     TGR_K(radix_binscan_kernel)<<<(R * 32 + kSortThreads - 1) / kSortThreads, kSortThreads, 0, st>>>(block_hist, g.n_blocks, R, bin_total);
     TGR_K(radix_totals_kernel)<<<1, 1024, 0, st>>>(bin_total, R, bin_base);
-    TGR_K(radix_scatter_kernel)<<<g.n_blocks, kSortThreads, (size_t)R * 4 + (size_t)kSortWarps * R * 2, st>>>(ksrc, vsrc, kdst, vdst, (int)n, g.tile, shift,
-                                                                                    bits, g.n_blocks, block_hist, bin_base, n_dev);
+    const size_t smem = (size_t)R * 4 + (size_t)kSortWarps * R * 2;
+    if (in_pairs)
+      TGR_K(radix_scatter_kernel<true, false>)<<<g.n_blocks, kSortThreads, smem, st>>>(ksrc, vsrc, kdst, vdst, (int)n, g.tile, shift, bits, g.n_blocks, block_hist, bin_base, n_dev);
+    else if (out_pairs)
+      TGR_K(radix_scatter_kernel<false, true>)<<<g.n_blocks, kSortThreads, smem, st>>>(ksrc, vsrc, kdst, vdst, (int)n, g.tile, shift, bits, g.n_blocks, block_hist, bin_base, n_dev);
+    else
+      TGR_K(radix_scatter_kernel<false, false>)<<<g.n_blocks, kSortThreads, smem, st>>>(ksrc, vsrc, kdst, vdst, (int)n, g.tile, shift, bits, g.n_blocks, block_hist, bin_base, n_dev);
     if (int rc = check_launch("sort_pairs")) return rc;
     ksrc = kdst;
     vsrc = vdst;
