@@ -300,7 +300,16 @@ extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, c
     g->n_backward++;
   }
   if (!finish) return 0;
-  // the chain rule through emb_transform / the item-DNN block is linear in (A, s): ONCE per group on the sums
+  // the chain rule through emb_transform / the item-DNN block is linear in (A, s): ONCE per group on the sums. Nothing in
+  // the reduce / row-gradient kernels below depends on it (it adds into the mm features' own columns of dW_item), so it
+  // runs on the side stream next to them and is joined at the end of this call.
+  Branch* br = (g->n_mm > 0 && g->n > 0) ? branch_of_device() : nullptr;
+  void* chain_stream = stream;
+  if (br != nullptr) {
+    cudaEventRecord(br->fork, (cudaStream_t)stream);
+    cudaStreamWaitEvent(br->side, br->fork, 0);
+    chain_stream = br->side;
+  }
   for (int f = 0; f < g->n_mm; ++f) {
     const tgr_mm_feat_t& m = prm->mm[f];
     if (gr->dW_mm[f] == nullptr) continue;
@@ -312,8 +321,9 @@ extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, c
     TGR_REQUIRE(!tcb || gr->db_item != nullptr, "the tensor-core mm backward reads colsum(dz) from db_item: it must not be NULL");
     if (int rc = tgr_fact_mm_chain_bwd(prm->dnn.w_item + m.col, prm->dnn.item_ld, m.w, m.b, g->mm_A[f], tcb ? gr->db_item : g->mm_s[f], H,
                                        m.mm_dim, gr->dW_mm[f], gr->db_mm[f], gr->dW_item + m.col, prm->dnn.item_ld,
-                                       stream)) return rc;
+                                       chain_stream)) return rc;
   }
+  if (br != nullptr) cudaEventRecord(br->join, br->side);
   if (g->n == 0) return 0;
   // "concat gradient" of the reduction = dZ [T, H]: every slot at column 0 of its side, row pitch H
   tgr_call_t calls[TGR_MAX_CALLS];
@@ -333,6 +343,8 @@ extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, c
     src = tgr_row_source_t{};
     src.fetched_rows = g->rows_local;
   }
-  return tgr_fact_unique_backward(tables, n_tables, H, &prm->dnn, g->uniq, g->n_unique, g->n, &src, g->G, gr->dW_item,
-                                  gr->dW_user, g->ws, g->ws_bytes, stream);
+  const int rc = tgr_fact_unique_backward(tables, n_tables, H, &prm->dnn, g->uniq, g->n_unique, g->n, &src, g->G, gr->dW_item,
+                                          gr->dW_user, g->ws, g->ws_bytes, stream);
+  if (br != nullptr) cudaStreamWaitEvent((cudaStream_t)stream, br->join, 0);
+  return rc;
 }

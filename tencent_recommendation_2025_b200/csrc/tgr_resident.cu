@@ -8,21 +8,43 @@
 
 namespace tgr {
 
-// ids[t, :] = 0 except ids[t, id_col] = item_ids[t] and ids[t, col0 + j] = feat[item_ids[t], j]; one thread per (t, 4 cols)
-__global__ void __launch_bounds__(256) expand_items_kernel(const int32_t* __restrict__ item_ids, int64_t T, int n_single, int id_col,
-                                                           int col0, const int32_t* __restrict__ feat, int n_feat, int64_t n_items,
-                                                           int32_t* __restrict__ ids) {
-  const int64_t total = T * n_single;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    const int64_t t = i / n_single;
-    const int c = (int)(i - t * n_single);
-    int id = __ldg(item_ids + t);
-    if (id < 0 || id >= n_items) id = 0;          // out-of-range ids read the padding row here; the range check proper is the kernels'
-    int v = 0;
-    if (c == id_col) v = __ldg(item_ids + t);
-    else if (c >= col0 && c < col0 + n_feat) v = __ldg(feat + (size_t)id * n_feat + (c - col0));
-    ids[i] = v;
+// ids[t, :] = 0 except ids[t, id_col] = item_ids[t] and ids[t, col0 + j] = feat[item_ids[t], j].
+// CTA = 256 tokens: thread t reads its id and the item's feature row (all loads of a thread independent, 8-byte pieces when
+// the row allows), stages the packed row in shared memory, and the CTA copies the [256, n_single] block out linearly (it is
+// contiguous in `ids`), 16 bytes per lane. The first version (one thread per element: id load -> dependent feature load ->
+// store) took 10 us per call at T = 103 k.
+constexpr int kExpTok = 256;
+__global__ void __launch_bounds__(kExpTok) expand_items_kernel(const int32_t* __restrict__ item_ids, int64_t T, int n_single, int id_col,
+                                                               int col0, const int32_t* __restrict__ feat, int n_feat, int64_t n_items,
+                                                               int32_t* __restrict__ ids) {
+  extern __shared__ __align__(16) int32_t s_rows[];   // [kExpTok][n_single]
+  const int64_t t0 = (int64_t)blockIdx.x * kExpTok;
+  const int nt = (int)min((int64_t)kExpTok, T - t0);
+  const int tid = threadIdx.x;
+  if (tid < nt) {
+    const int raw = __ldg(item_ids + t0 + tid);
+    const int id = (raw < 0 || raw >= n_items) ? 0 : raw;   // out-of-range ids read the padding row here; the range check proper is the kernels'
+    int32_t* row = s_rows + tid * n_single;
+    for (int c = 0; c < col0; ++c) row[c] = 0;
+    for (int c = col0 + n_feat; c < n_single; ++c) row[c] = 0;
+    const int32_t* src = feat + (size_t)id * n_feat;
+    if ((n_feat & 1) == 0) {                                  // rows are 8-byte aligned
+      for (int j = 0; j < n_feat; j += 2) {
+        const int2 v = __ldg(reinterpret_cast<const int2*>(src + j));
+        row[col0 + j] = v.x;
+        row[col0 + j + 1] = v.y;
+      }
+    } else {
+      for (int j = 0; j < n_feat; ++j) row[col0 + j] = __ldg(src + j);
+    }
+    row[id_col] = raw;
   }
+  __syncthreads();
+  const int total = nt * n_single;
+  int32_t* dst = ids + t0 * n_single;                         // 256 * n_single * 4 bytes per CTA: 16-byte aligned
+  const int total4 = total >> 2;
+  for (int i = tid; i < total4; i += kExpTok) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(s_rows)[i];
+  for (int i = (total4 << 2) + tid; i < total; i += kExpTok) dst[i] = s_rows[i];
 }
 
 // ids[tok[u], col0 + j] = vals[u, j] for the few user tokens of a call (one per sequence, dataset.py:119)
@@ -36,16 +58,30 @@ __global__ void __launch_bounds__(256) scatter_user_kernel(const int32_t* __rest
   ids[(size_t)t * n_single + col0 + j] = __ldg(vals + i);
 }
 
-// out[t, :] = table[item_ids[t], :] (16-byte pieces; rows are mm_dim * esz bytes, a multiple of 16)
+// out[t, :] = table[item_ids[t], :] (16-byte pieces; rows are mm_dim * esz bytes, a multiple of 16); four pieces in flight
+// per thread
 __global__ void __launch_bounds__(256) gather_mm_kernel(const int32_t* __restrict__ item_ids, int64_t T, const uint4* __restrict__ table,
                                                         int row16, int64_t n_items, uint4* __restrict__ out) {
   const int64_t total = T * row16;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    const int64_t t = i / row16;
-    const int c = (int)(i - t * row16);
-    int id = __ldg(item_ids + t);
-    if (id < 0 || id >= n_items) id = 0;
-    out[i] = __ldg(table + (size_t)id * row16 + c);
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) {
+        const int64_t t = i / row16;
+        const int c = (int)(i - t * row16);
+        int id = __ldg(item_ids + t);
+        if (id < 0 || id >= n_items) id = 0;
+        v[u] = __ldg(table + (size_t)id * row16 + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) out[i] = v[u];
+    }
   }
 }
 
@@ -60,10 +96,11 @@ extern "C" int tgr_expand_item_features(const int32_t* item_ids, int64_t T, int 
               "bad column layout");
   if (T == 0) return 0;
   TGR_REQUIRE(item_ids && ids_out && (n_feat == 0 || feat_table) && n_items > 0, "null argument");
-  int64_t blocks = (T * n_single + 255) / 256;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  TGR_K(expand_items_kernel)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(item_ids, T, n_single, id_col, col0, feat_table, n_feat,
-                                                                             n_items, ids_out);
+  TGR_REQUIRE(((uintptr_t)ids_out & 15) == 0 && ((uintptr_t)feat_table & 7) == 0, "misaligned buffers");
+  TGR_REQUIRE(n_single <= 48, "n_single too large for the staging tile");
+  const int64_t blocks = (T + kExpTok - 1) / kExpTok;
+  TGR_K(expand_items_kernel)<<<(unsigned)blocks, kExpTok, (size_t)kExpTok * n_single * sizeof(int32_t), (cudaStream_t)stream>>>(
+      item_ids, T, n_single, id_col, col0, feat_table, n_feat, n_items, ids_out);
   return check_launch("expand_item_features");
 }
 
@@ -86,7 +123,7 @@ extern "C" int tgr_gather_mm_rows(const int32_t* item_ids, int64_t T, const void
   TGR_REQUIRE(item_ids && table && out && n_items > 0, "null argument");
   TGR_REQUIRE(((uintptr_t)table & 15) == 0 && ((uintptr_t)out & 15) == 0, "misaligned buffers");
   const int row16 = mm_dim * esz / 16;
-  int64_t blocks = (T * row16 + 255) / 256;
+  int64_t blocks = (T * row16 + 1023) / 1024;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   TGR_K(gather_mm_kernel)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(item_ids, T, (const uint4*)table, row16, n_items, (uint4*)out);
   return check_launch("gather_mm_rows");
