@@ -24,7 +24,7 @@ namespace tgr {
 
 constexpr int kRedThreads = 256;
 constexpr int kC = 64;  // sorted entries per group tile
-constexpr int kU = 4;   // gradient rows in flight per thread
+constexpr int kU = 8;   // gradient rows in flight per thread
 
 struct RedParams {
   const char* chunk_base[TGR_MAX_CALLS][TGR_MAX_SLOTS];  // d(concat) base of (call, slot), offset to the slot's column

@@ -47,6 +47,7 @@ class GraphedStep:
         n = example.ints.numel()
         self.static_ints = torch.empty(n, dtype=torch.int32, device=self.device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._gather_stream = torch.cuda.Stream(device=self.device)
         self.staging = [{"buf": torch.empty(n, dtype=torch.int32, device=self.device), "filled": None, "free": None}
                         for _ in range(staging_slots)]
         self._next_slot = 0
@@ -100,10 +101,17 @@ class GraphedStep:
                       c.n_cap) for c in st.calls) + (tuple(st.bases),)
 
     def _expand(self) -> List[PackedBatch]:
+        """Static slim buffer -> the step's PackedBatches; the mm row gathers run on a forked stream next to the id expansion."""
+        cur = torch.cuda.current_stream(self.device)
+        side = self._gather_stream if self.store.mm_dev else None
+        if side is not None:
+            side.wait_stream(cur)
         pbs = []
         for i, (sc, b) in enumerate(zip(self.template.calls, self.template.bases)):
             dev = self.static_ints[b:b + sc.ints.numel()]
-            pbs.append(self.store.expand(sc, dev, self._ids[i], self._mm[i]))
+            pbs.append(self.store.expand(sc, dev, self._ids[i], self._mm[i], mm_stream=side))
+        if side is not None:
+            cur.wait_stream(side)
         return pbs
 
     def _refresh_adam(self):

@@ -255,8 +255,10 @@ class ResidentItemFeatures:
 
     # ------------------------------------------------------------------ device side
     def expand(self, sc: SlimCall, dev_ints: torch.Tensor, ids_out: Optional[torch.Tensor] = None,
-               mm_out: Optional[List[torch.Tensor]] = None) -> PackedBatch:
-        """Slim call (its int buffer already on the device) -> the packed call, on the current stream."""
+               mm_out: Optional[List[torch.Tensor]] = None, mm_stream: Optional["torch.cuda.Stream"] = None) -> PackedBatch:
+        """Slim call (its int buffer already on the device) -> the packed call, on the current stream. ``mm_stream``: the mm
+        row gathers go to that stream instead (the caller forks it from / joins it into the current stream): they only feed
+        the mm projection, so they can run next to the id expansion and the key processing."""
         lay = self.layout
         cl = lay.calls[sc.include_user]
         T, o, s = sc.T, sc.offs, sc.sizes
@@ -275,7 +277,8 @@ class ResidentItemFeatures:
         for j, tab in enumerate(self.mm_dev):
             out = mm_out[j] if mm_out is not None else torch.empty((T, tab.shape[1]), dtype=tab.dtype, device=self.device)
             check(self.lib.tgr_gather_mm_rows(item_ids.data_ptr(), T, tab.data_ptr(), _lib.DTYPE_BF16 if tab.dtype == torch.bfloat16
-                                              else _lib.DTYPE_F32, tab.shape[1], self.n_items, out.data_ptr(), _stream()),
+                                              else _lib.DTYPE_F32, tab.shape[1], self.n_items, out.data_ptr(),
+                                              mm_stream.cuda_stream if mm_stream is not None else _stream()),
                   "tgr_gather_mm_rows")
             mm.append(out)
         return PackedBatch(sc.B, sc.L, sc.include_user, ids, dev_ints[o[3]:o[3] + s[3]].view(sc.n_arr, T + 1),
