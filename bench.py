@@ -455,7 +455,8 @@ def run_gpu(args):
     graph_leg = None
     if store is not None and args.graph != "off" and args.path == "factored":
         try:
-            from tencent_recommendation_2025_b200.graphed import GraphedStep
+            from tencent_recommendation_2025_b200.graphed import GraphedStep, PipelinedStep
+            piped = args.graph == "auto"       # the next batch's key processing on a forked branch of the same graph
             from tencent_recommendation_2025_b200.resident import CallShape
             shapes = [CallShape.covering([st.calls[i] for st in steps_np]) for i in range(len(steps_np[0].calls))]
             fixed = [store.slim_step(st.calls, shapes) for st in steps_np]        # pinned, one buffer per step
@@ -478,14 +479,21 @@ def run_gpu(args):
                 return step_result(outs)
 
             g_warm = 3
-            l0 = _lib.launch_count()
-            runner = GraphedStep(m, store, fixed[0], body, hyper=hyper, warmup=g_warm)
-            per_replay = (_lib.launch_count() - l0) // (g_warm + 1)     # warm-ups and the capture issue the same launches
+            if piped:
+                runner = PipelinedStep(m, store, fixed[0], body, hyper=hyper, warmup=g_warm)
+            else:
+                runner = GraphedStep(m, store, fixed[0], body, hyper=hyper, warmup=g_warm)
+            per_replay = runner.launches_per_replay      # this library's launches inside one captured step
             clocks2 = ClockSampler(local_rank, period_ms=args.clock_period_ms)
             if not args.no_clocks:
                 clocks2.start()
-            for i in range(max(args.warmup, 3)):
-                runner.load(dev_fixed[i % n_batches])
+            # pipelined: run() computes the batch loaded one call EARLIER (its key processing ran inside the previous replay)
+            # and prepares the batch just loaded; every replay does one full step's work, rows are counted per computed batch
+            gw = max(args.warmup, 3)
+            if piped:
+                runner.prime(dev_fixed[0])
+            for i in range(gw):
+                runner.load(dev_fixed[(i + 1) % n_batches] if piped else dev_fixed[i % n_batches])
                 runner.run()
             torch.cuda.synchronize()
             clocks2.mark()
@@ -493,8 +501,8 @@ def run_gpu(args):
             g0.record()
             g_rows = 0
             for i in range(args.steps):
-                k = (args.warmup + i) % n_batches
-                runner.load(dev_fixed[k])          # inputs resident in HBM: one 3 MB device-to-device copy into the static buffer
+                k = (gw + i) % n_batches           # the batch this replay computes
+                runner.load(dev_fixed[(k + 1) % n_batches] if piped else dev_fixed[k])   # inputs resident in HBM: one 3 MB D2D copy
                 runner.run()
                 g_rows += lookups[k]
             g1.record()
@@ -507,13 +515,19 @@ def run_gpu(args):
             loss_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
             loss_ev = [None, None]
             losses, h2d, rows_e2e, t0 = [], 0, 0, None
-            runner.submit(fixed[0])
+            if piped:
+                torch.cuda.synchronize()
+                runner.prime(fixed[0])
+                runner.submit(fixed[1 % n_batches])
+            else:
+                runner.submit(fixed[0])
             for i in range(e2e_warm + e2e_n):
                 k = i % n_batches
                 if i == e2e_warm:
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                runner.submit(fixed[(i + 1) % n_batches])      # next step's H2D overlaps this step's replay
+                # the H2D copy of a later step overlaps this step's replay (pipelined: two ahead, the replay prepares step i + 1)
+                runner.submit(fixed[(i + 2) % n_batches] if piped else fixed[(i + 1) % n_batches])
                 loss = runner.run()
                 slot = i & 1
                 if loss_ev[slot] is not None:
@@ -530,13 +544,15 @@ def run_gpu(args):
                     ev.synchronize()
             torch.cuda.synchronize()
             t_g = time.perf_counter() - t0
-            runner.run()                                        # drain the look-ahead submission
+            runner.run()                                        # drain the look-ahead submission(s)
+            if piped:
+                runner.run()
             torch.cuda.synchronize()
             graph_leg = {"value": g_rows / (g_ms * 1e-3), "ms_per_step": g_ms / args.steps,
                          "kernels_per_replay": int(per_replay), "clocks": g_clk,
                          "e2e": {"value": rows_e2e / t_g, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_n, "d2h_bytes_per_step": 4,
                                  "ms_per_step": round(t_g / e2e_n * 1e3, 3),
-                                 "entry": "GraphedStep.submit (pinned slim buffer: ids + user tokens, one H2D copy on a copy stream, "
+                                 "entry": ("PipelinedStep" if piped else "GraphedStep") + ".submit (pinned slim buffer: ids + user tokens, one H2D copy on a copy stream, "
                                           "one step ahead) + GraphedStep.run (48-byte AdamW block + one graph replay: expansion from "
                                           "the HBM-resident item tables, prefetch, feat2emb x3, backward, dense AdamW, row update) + "
                                           "the step's loss copied back and read on the host every step; wall clock",
@@ -582,7 +598,7 @@ def run_gpu(args):
                                     "row GEMMs, fp32 accumulate)" if args.path == "factored"
                                     else f"torch F.linear (caller side, unchanged), {args.dnn_matmul} as reference run.sh --use_tf32"),
                             "rows_per_step": rows // args.steps, "distinct_batches": n_batches,
-                            "launch": ("one CUDA graph replay per step (graphed.GraphedStep)" if graph_leg and "error" not in graph_leg
+                            "launch": ("one CUDA graph replay per step (graphed.PipelinedStep / GraphedStep)" if graph_leg and "error" not in graph_leg
                                        else "eager: one C-ABI call per phase from Python")},
             "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "e2e": e2e,
             "e2e_host_packed_feed": e2e_packed, "eager": eager, "graph": graph_leg,
@@ -809,8 +825,9 @@ def main():
     ap.add_argument("--torch-dense-opt", action="store_true",
                     help="factored path: update itemdnn/userdnn/emb_transform with torch.optim.AdamW instead of the engine's "
                          "own dense AdamW launch")
-    ap.add_argument("--graph", default="auto", choices=["auto", "off"],
-                    help="N=1: the step replayed from a CUDA graph (needs the resident item tables); off = eager numbers only")
+    ap.add_argument("--graph", default="auto", choices=["auto", "plain", "off"],
+                    help="N=1: the step replayed from a CUDA graph (needs the resident item tables). auto = pipelined (the next "
+                         "batch's key processing on a forked branch of the same graph), plain = one step per graph, off = eager only")
     ap.add_argument("--mm-dtype", default=None, choices=["f32", "bf16"],
                     help="storage dtype of the frozen mm features (default: bf16 for c3, f32 otherwise)")
     ap.add_argument("--no-prefetch", action="store_true", help="sharded path: per-call exchange instead of step prefetch")

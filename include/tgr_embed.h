@@ -442,6 +442,10 @@ typedef struct tgr_fact_group {
   size_t ws_bytes;
   int32_t projected, n_backward;       /* progress */
   int32_t mm_done, mm_joined;          /* tgr_fact_mm_branch ran / the caller's stream has waited for it */
+  void* reduce_done_event;             /* optional cudaEvent_t (caller-owned): recorded on the stream right after the
+                                          segmented reduce of the finishing backward — the L2-sensitive gathers of the step
+                                          are over, what follows (row gradients, row update) is latency- / HBM-bound and
+                                          a good neighbour for the NEXT step's key processing (graphed.PipelinedStep) */
 } tgr_fact_group_t;
 
 /* Arena bytes tgr_fact_prepare needs for this group (depends on n, the calls' T / n_single / arr_nnz, H, mm dims). */
@@ -452,8 +456,10 @@ int tgr_fact_prepare(const tgr_table_t* tables, int n_tables, tgr_fact_group_t* 
 /* Optional, right after tgr_fact_prepare on the same stream, when the forwards follow immediately (the weights the mm
  * projection reads are already final): fold + mm projection of EVERY call of the group on an internal side stream that
  * forks from the point where tgr_fact_prepare started, so the small value-dependent mm kernels run next to the issue-bound
- * key processing (sort / dedup) instead of after it. The first tgr_fact_call_forward joins. Capturable in a CUDA graph. */
-int tgr_fact_mm_branch(const tgr_fact_params_t* prm, tgr_fact_group_t* g, void* stream);
+ * key processing (sort / dedup) instead of after it. The first tgr_fact_call_forward joins. Capturable in a CUDA graph.
+ * fork_now != 0: the group was prepared EARLIER (one step ahead, possibly on another stream): the side stream forks from
+ * `stream` at this call instead. */
+int tgr_fact_mm_branch(const tgr_fact_params_t* prm, tgr_fact_group_t* g, int fork_now, void* stream);
 /* feat2emb forward of call c into out [T, H]; the first forward of a group projects the unique rows. */
 int tgr_fact_call_forward(const tgr_table_t* tables, int n_tables, const tgr_fact_params_t* prm, tgr_fact_group_t* g,
                           int c, float* out, void* stream);

@@ -85,7 +85,8 @@ class FactGroup(C.Structure):
                 ("fold_M", C.c_void_p * MAX_MM), ("fold_c", C.c_void_p * MAX_MM), ("mm_A", C.c_void_p * MAX_MM),
                 ("mm_s", C.c_void_p * MAX_MM), ("fold_Mb", C.c_void_p * MAX_MM), ("dzb", C.c_void_p),
                 ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
-                ("projected", C.c_int32), ("n_backward", C.c_int32), ("mm_done", C.c_int32), ("mm_joined", C.c_int32)]
+                ("projected", C.c_int32), ("n_backward", C.c_int32), ("mm_done", C.c_int32), ("mm_joined", C.c_int32),
+                ("reduce_done_event", C.c_void_p)]
 
 
 MAX_DENSE = 16
@@ -194,7 +195,7 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p]),
     "tgr_fact_group_bytes": (C.c_size_t, [C.POINTER(FactGroup), C.c_int]),
     "tgr_fact_prepare": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(FactGroup), C.c_void_p, C.c_size_t, C.c_void_p]),
-    "tgr_fact_mm_branch": (C.c_int, [C.POINTER(FactParams), C.POINTER(FactGroup), C.c_void_p]),
+    "tgr_fact_mm_branch": (C.c_int, [C.POINTER(FactParams), C.POINTER(FactGroup), C.c_int, C.c_void_p]),
     "tgr_fact_call_forward": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(FactParams), C.POINTER(FactGroup), C.c_int,
                                         C.c_void_p, C.c_void_p]),
     "tgr_fact_call_backward": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(FactParams), C.POINTER(FactGroup), C.c_int,

@@ -213,19 +213,19 @@ static int mm_project_call(tgr_fact_group_t* g, int c, void* stream) {
   return 0;
 }
 
-extern "C" int tgr_fact_mm_branch(const tgr_fact_params_t* prm, tgr_fact_group_t* g, void* stream) {
+extern "C" int tgr_fact_mm_branch(const tgr_fact_params_t* prm, tgr_fact_group_t* g, int fork_now, void* stream) {
   if (int rc = check_group(g)) return rc;
   TGR_REQUIRE(prm != nullptr && prm->n_mm == g->n_mm, "bad params");
   if (g->n_mm == 0 || g->mm_done) return 0;
   TGR_REQUIRE(!g->projected, "tgr_fact_mm_branch must precede the group's first forward");
   Branch* br = branch_of_device();
   TGR_REQUIRE(br != nullptr, "could not create the side stream");
-  cudaStreamWaitEvent(br->side, br->fork, 0);          // recorded by tgr_fact_prepare on the caller's stream
+  if (fork_now) cudaEventRecord(br->fork, (cudaStream_t)stream);
+  cudaStreamWaitEvent(br->side, br->fork, 0);          // (else) recorded by tgr_fact_prepare on the caller's stream
   if (int rc = mm_fold_all(prm, g, br->side)) return rc;
   for (int c = 0; c < g->n_calls; ++c)
     if (int rc = mm_project_call(g, c, br->side)) return rc;
   cudaEventRecord(br->join, br->side);
-  (void)stream;
   g->mm_done = 1;
   return check_launch("fact_mm_branch");
 }
@@ -338,6 +338,7 @@ extern "C" int tgr_fact_call_backward(const tgr_table_t* tables, int n_tables, c
   }
   if (int rc = bwd_reduce_dn(tables, n_tables, H, calls, g->n_calls, g->keys, g->srcs, g->n, 0, g->seg_of, g->G, nullptr,
                              g->ws, g->ws_bytes, g->n_is_capacity ? g->n_valid : nullptr, stream)) return rc;
+  if (g->reduce_done_event != nullptr) cudaEventRecord((cudaEvent_t)g->reduce_done_event, (cudaStream_t)stream);
   tgr_row_source_t src = g->src;
   if (src.n_peers > 0) {   // the rows were copied out of the peers' shards by the forward projection
     src = tgr_row_source_t{};

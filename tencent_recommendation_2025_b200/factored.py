@@ -118,6 +118,8 @@ class FactoredEngine(EmbeddingEngine):
         # fused mode may also own the path's Linear layers (itemdnn / userdnn / emb_transform): their gradients then stay in
         # the group's accumulators (no autograd AccumulateGrad copies) and fused_step(dense=True) updates them in one launch
         self.own_dense = False
+        self._staged: Dict[tuple, FactGroup] = {}
+        self.reduce_done_event = None   # torch.cuda.Event recorded after the finishing backward's segmented reduce
         self.overlap_mm = True      # prefetch(): mm branch on a side stream (tgr_fact_mm_branch)
         self._dense_state: Dict[int, tuple] = {}
 
@@ -160,12 +162,9 @@ class FactoredEngine(EmbeddingEngine):
         return p
 
     # ------------------------------------------------------------------ group preparation (value independent)
-    def prepare(self, pbs: Sequence[PackedBatch]) -> FactGroup:
-        """keys -> sort -> dedup -> id remap for the calls of one group (ONE C call). Independent of table VALUES."""
-        self._require_cuda()
-        self._tab_memo.clear()       # re-read the parameter pointers for this group
-        self._prm_fresh = False
-        lay, dev = self.layout, self._device()
+    def _describe(self, pbs: Sequence[PackedBatch]):
+        """-> (group with its C descriptor filled from the calls, arena bytes it needs)."""
+        lay = self.layout
         g = FactGroup(pbs)
         if len(g.pbs) > _lib.MAX_CALLS:
             raise ValueError(f"at most {_lib.MAX_CALLS} calls per group")
@@ -197,12 +196,27 @@ class FactoredEngine(EmbeddingEngine):
                     raise TypeError("all mm inputs of a group must share one dtype")
                 c.mm_x[i][f] = x.data_ptr()
         c.mm_x_dtype = _lib.DTYPE_F32 if x_dt is None else self._dt_code(x_dt)
-        nt = len(self.tables)
-        nbytes = self.lib.tgr_fact_group_bytes(C.byref(c), nt)
+        nbytes = self.lib.tgr_fact_group_bytes(C.byref(c), len(self.tables))
         if nbytes == 0:
             check(-1, "tgr_fact_group_bytes")
-        g.arena = self._take_arena(nbytes, dev)
-        g.pool = self._arena_pool
+        return g, int(nbytes)
+
+    def prepare(self, pbs: Sequence[PackedBatch], arena: Optional[torch.Tensor] = None) -> FactGroup:
+        """keys -> sort -> dedup -> id remap for the calls of one group (ONE C call). Independent of table VALUES.
+        ``arena``: carve the group from this uint8 buffer (kept by the caller) instead of the engine's recycling pool."""
+        self._require_cuda()
+        self._tab_memo.clear()       # re-read the parameter pointers for this group
+        self._prm_fresh = False
+        dev = self._device()
+        g, nbytes = self._describe(pbs)
+        c, nt = g.c, len(self.tables)
+        if arena is not None:
+            if arena.numel() < nbytes or arena.dtype != torch.uint8 or arena.device != dev:
+                raise ValueError(f"prepare: the arena must be a uint8 tensor of >= {nbytes} bytes on {dev}")
+            g.arena, g.pool = arena, None
+        else:
+            g.arena = self._take_arena(nbytes, dev)
+            g.pool = self._arena_pool
         e0 = self._t0()
         check(self.lib.tgr_fact_prepare(self._table_array(), nt, C.byref(c), g.arena.data_ptr(), nbytes, _stream()),
               "tgr_fact_prepare")
@@ -232,11 +246,28 @@ class FactoredEngine(EmbeddingEngine):
         from .engine import _dtype_code
         return _dtype_code(dt)
 
+    def group_bytes(self, pbs: Sequence[PackedBatch]) -> int:
+        """Arena bytes a group of these calls needs (for callers that keep their own arenas)."""
+        return self._describe(pbs)[1]
+
+    def stage(self, g: FactGroup):
+        """Hand over a group prepared ahead of time (its key processing already enqueued, e.g. next to the previous step's
+        backward): the ``prefetch`` of the same calls picks it up instead of preparing them again."""
+        self._staged[tuple(id(pb) for pb in g.pbs)] = g
+
     def prefetch(self, pbs: Sequence[PackedBatch]) -> FactGroup:
-        self.current = g = self.prepare(pbs)
+        g = self._staged.pop(tuple(id(pb) for pb in pbs), None)
+        early = g is not None
+        if g is None:
+            g = self.prepare(pbs)
+        else:
+            self._tab_memo.clear()       # parameter pointers are re-read for the step that consumes the group
+            self._prm_fresh = False
+        self.current = g
         if self._mm_slots and self.overlap_mm:
             # the forwards follow at once: fold + mm projection of every call on a side stream next to the key processing
-            check(self.lib.tgr_fact_mm_branch(C.byref(self._params()), C.byref(g.c), _stream()), "tgr_fact_mm_branch")
+            check(self.lib.tgr_fact_mm_branch(C.byref(self._params()), C.byref(g.c), 1 if early else 0, _stream()),
+                  "tgr_fact_mm_branch")
             self.launches += len(self._mm_slots) * (1 + len(g.pbs))
         return g
 
@@ -306,6 +337,8 @@ class FactoredEngine(EmbeddingEngine):
             raise RuntimeError("a prefetched group needs the gradient of every one of its calls "
                                f"({g.n_bwd} of {len(g.pbs)} arrived); prefetch only the calls that reach the loss")
         n_mm = len(self._mm_slots)
+        ev = self.reduce_done_event
+        g.c.reduce_done_event = ev.cuda_event if (finish and ev is not None) else None
         e0 = self._t0()
         check(self.lib.tgr_fact_call_backward(self._table_array(), len(self.tables), C.byref(self._params()), C.byref(g.c),
                                               g.index[id(pb)], d_out.data_ptr(), C.byref(a["c"]), 1 if finish else 0,

@@ -185,3 +185,53 @@ def test_engine_owned_dense_adamw_matches_torch_and_is_graphable():
     for p in own.dense_parameters():
         assert p.grad is None, "own_dense: the Linear gradients stay inside the engine"
     runner.close()
+
+
+def test_pipelined_step_equals_eager_step_bitwise():
+    """PipelinedStep: replay r computes batch r and, on a forked branch of the same graph, runs the expansion / key
+    processing of batch r + 1. Outputs and every parameter after 8 replays == the eager steps, bit for bit."""
+    from tencent_recommendation_2025_b200.graphed import PipelinedStep
+    dev, cfg, world, steps, store, shapes = _setup()
+    eager, piped = _module(cfg, dev), _module(cfg, dev)
+    eager.own_dense_parameters()
+    piped.own_dense_parameters()
+    ups = [torch.from_numpy(r).to(dev) for r in steps[0].upstream]
+    slims = [store.slim_step(st.calls, shapes) for st in steps]
+
+    def body_of(m):
+        def body(pbs):
+            m.prefetch(pbs)
+            outs = [m.feat2emb_packed(pb) for pb in pbs]
+            torch.autograd.backward(outs, ups)
+            m.fused_step(**HYPER, dense=True)
+            return [o.detach() for o in outs]
+        return body
+
+    n_warm = 2
+    runner = PipelinedStep(piped, store, slims[0], body_of(piped), hyper=HYPER, warmup=n_warm)
+    b_e = body_of(eager)
+
+    def eager_step(st):
+        dints = st.ints.to(dev)
+        return b_e([store.expand(sc, dints[b:b + sc.ints.numel()]) for sc, b in zip(st.calls, st.bases)])
+
+    for _ in range(n_warm):
+        eager_step(slims[0])
+    assert eager.engine.step == piped.engine.step == n_warm
+    seq = slims[1:] + slims + slims[:2]
+    runner.prime(seq[0])
+    for k, st in enumerate(seq):
+        if k + 1 < len(seq):
+            if k % 2 == 0:
+                runner.submit(seq[k + 1])
+            else:
+                runner.load(seq[k + 1].ints.to(dev))
+        got = runner.run()
+        want = eager_step(st)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), f"step {k}: outputs differ"
+    torch.cuda.synchronize()
+    assert eager.engine.step == piped.engine.step
+    for (k, p), (_, q) in zip(eager.named_parameters(), piped.named_parameters()):
+        assert torch.equal(p, q), f"{k} differs after {runner.replays} replays"
+    runner.close()

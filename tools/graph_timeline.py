@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from tencent_recommendation_2025_b200 import synth
-from tencent_recommendation_2025_b200.graphed import GraphedStep
+from tencent_recommendation_2025_b200.graphed import GraphedStep, PipelinedStep
 from tencent_recommendation_2025_b200.resident import CallShape, ResidentItemFeatures
 
 dev = torch.device("cuda", 0)
@@ -28,14 +28,17 @@ def body(pbs):
     with torch.no_grad():
         return torch.stack([o.detach()[0, -1] for o in outs]).sum()
 
-r = GraphedStep(m, store, fixed[0], body, hyper=hyper)
+PIPE = os.environ.get("PIPE", "1") == "1"
+r = (PipelinedStep if PIPE else GraphedStep)(m, store, fixed[0], body, hyper=hyper)
+if PIPE:
+    r.prime(dev_fixed[0])
 for i in range(8):
-    r.load(dev_fixed[i % 4]); r.run()
+    r.load(dev_fixed[(i + 1) % 4]); r.run()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for i in range(4):
-        r.load(dev_fixed[i % 4]); r.run()
+        r.load(dev_fixed[(i + 1) % 4]); r.run()
     torch.cuda.synchronize()
 os.makedirs("gpurun_out", exist_ok=True)
 prof.export_chrome_trace("gpurun_out/trace_graph.json")
@@ -49,7 +52,7 @@ last = None; busy = 0.0; gaps = 0.0
 for e in ev:
     if e["ts"] < lo: continue
     gap = 0 if last is None else e["ts"] - last
-    print(f"  +{e['ts']-lo:8.1f} us  dur {e['dur']:7.1f}  gap {gap:6.1f}  {e['name'][:70]}")
+    print(f"  +{e['ts']-lo:8.1f} us  dur {e['dur']:7.1f}  gap {gap:6.1f}  s{e['args'].get('stream','?')}  {e['name'][:70]}")
     busy += e["dur"]; gaps += max(gap, 0)
     last = max(last or 0, e["ts"] + e["dur"])
 print(f"last replay: busy {busy:.1f} us, gaps {gaps:.1f} us")
