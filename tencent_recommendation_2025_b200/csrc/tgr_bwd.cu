@@ -568,6 +568,9 @@ int tgr::dedup_remap_dn(const uint32_t* keys_sorted, const uint32_t* srcs_sorted
 static int adam_rows_impl(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
                           const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam, const tgr_adam_t* adam_dev,
                           void* stream);
+// resident CTAs of the row update per SM: HBM-bound at four already (32 warps x 4 independent 16-byte loads per thread);
+// the other half of the SM's thread slots stays free for the next step's key processing running beside it
+static const int kAdamRowsBlocksPerSM = [] { const char* e = getenv("TGR_ADAM_BPS"); return e ? atoi(e) : 4; }();
 
 extern "C" int tgr_adam_rows(const tgr_table_t* tables, int n_tables, int H, const uint32_t* uniq, const float* grads,
                              const int32_t* n_unique_dev, int64_t max_unique, const tgr_adam_t* adam, void* stream) {
@@ -593,7 +596,7 @@ static int adam_rows_impl(const tgr_table_t* tables, int n_tables, int H, const 
   rp.adam_dev = adam_dev;
   if (max_unique <= 0) return 0;
   int64_t blocks = (max_unique * rp.H4 + 255) / 256;
-  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (blocks > kNumSMs * kAdamRowsBlocksPerSM) blocks = kNumSMs * kAdamRowsBlocksPerSM;
   TGR_K(rows_kernel<0>)<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rp, uniq, grads, n_unique_dev);
   return check_launch("adam_rows");
 }

@@ -204,7 +204,7 @@ class PipelinedStep:
         self._sig = GraphedStep._signature(example)
         n = example.ints.numel()
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self._prep_stream = torch.cuda.Stream(device=dev)
+        self._prep_stream = torch.cuda.Stream(device=dev, priority=-1)   # its short kernels go first when block slots free up
         self._fork_ev = torch.cuda.Event()
         self._fork_ev.record(torch.cuda.current_stream(dev))     # creates the underlying cudaEvent_t
         self._gather_stream = torch.cuda.Stream(device=dev)
