@@ -374,7 +374,7 @@ def run_gpu(args):
 
     # ---- end to end from host buffers (e2e): pinned host batches -> copy stream -> step -> loss read back ----------
     def e2e_loop(feeder, host_steps, entry):
-        e2e_steps = max(3, min(args.steps, 20))
+        e2e_steps = max(3, min(args.steps, 100))
         e2e_warm = n_batches + 1
         loss_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
         loss_ev = [None, None]
@@ -510,7 +510,7 @@ def run_gpu(args):
             g_clk = clocks2.stop()
             g_ms = g0.elapsed_time(g1)
             # e2e: pinned host slim buffers -> staging (copy stream, one step ahead) -> replay -> loss read back every step
-            e2e_n = max(3, min(args.steps, 20))
+            e2e_n = max(3, min(args.steps, 100))
             e2e_warm = n_batches + 1
             loss_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
             loss_ev = [None, None]
@@ -794,8 +794,15 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = get_config(args.config, args.batch)
+    # a full-batch step of the reference costs ~2.1 s on 16 host cores (dict walk + dense AdamW over every row): the arm
+    # times at most `budget` seconds of them so that any --steps K finishes within a few minutes; the steps stay FULL
+    # batches (a smaller batch would charge the reference its per-step dense AdamW against fewer rows)
+    budget_s, est_step_s = 150.0, 2.2
+    steps_run = max(2, min(args.steps, int(budget_s / est_step_s)))
+    warm_run = max(1, min(args.warmup, 2))
     try:
-        cpu = cpu_reference(cfg, steps=args.steps, warmup=args.warmup, n_batches=2, prebuilt_steps=1)
+        cpu = cpu_reference(cfg, steps=steps_run, warmup=warm_run, n_batches=2, prebuilt_steps=1)
+        cpu["steps_timed"], cpu["warmup_run"] = steps_run, warm_run
     except FileNotFoundError as e:
         print(json.dumps({"impl": "reference", "unavailable": str(e)}))
         return
@@ -810,8 +817,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--path", default="factored", choices=["concat", "factored"],

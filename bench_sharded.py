@@ -233,7 +233,7 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     # ---- e2e from pinned host buffers: copy stream two steps ahead (the look-ahead key processing needs step k+1's
     #      ids on the device during step k), loss of every step copied back and read on the host ----
     host_steps = [[stage_pinned(lay, pc) for pc in st.calls] for st in steps_np]   # as a pin_memory DataLoader would
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 50))
     e2e_warm = n_batches + 1
     feeder = HostPrefetcher(dev, slots=5)
     m.rank_state.prep = None
