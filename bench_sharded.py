@@ -151,7 +151,8 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
             if t.key_base % world == rank:
                 m.local_table[t.key_base // world].zero_()
     dense = [p for p in m.parameters() if p is not m.local_table]
-    dense_opt = torch.optim.AdamW(dense, lr=1e-3, betas=(0.9, 0.98), fused=True)
+    # replicated dense parameters: one tgr_adam_dense launch (m.dense_adam_) unless --torch-dense-opt
+    dense_opt = torch.optim.AdamW(dense, lr=1e-3, betas=(0.9, 0.98), fused=True) if args.torch_dense_opt else None
     dev_steps = [([to_device(lay, pc, dev) for pc in st.calls], [torch.from_numpy(r).to(dev) for r in st.upstream])
                  for st in steps_np]
     hyper = dict(lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
@@ -176,7 +177,10 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
         torch.autograd.backward(outs, ups)
         m.fused_step(**hyper)                    # row gradients to their owners, owners' AdamW row update
         m.allreduce_dense_(flat_grad, pre_barrier=False)   # replicated dense parameters: mean over ranks (peer memory or NCCL)
-        dense_opt.step()
+        if dense_opt is not None:
+            dense_opt.step()
+        else:
+            m.dense_adam_(dense, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
         if next_pbs is not None and not args.no_lookahead:
             m.finish_prepare()
         return outs

@@ -1087,6 +1087,36 @@ class ShardedBaselineEmbedding(torch.nn.Module):
         flat.copy_(tmp)
         return flat
 
+    def dense_adam_(self, params, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2):
+        """AdamW on the replicated dense parameters (itemdnn / userdnn / emb_transform) from their (already all-reduced)
+        ``.grad`` tensors in ONE launch (tgr_adam_dense) — instead of torch's multi-tensor AdamW (37 us of device time and
+        0.14 ms of host time per step for ~0.1 M parameters). State is kept here; same arithmetic as the row update."""
+        from ._lib import DenseList, MAX_DENSE, make_adam
+        params = [p for p in params if p.grad is not None]
+        if not params:
+            return
+        if len(params) > MAX_DENSE:
+            raise ValueError(f"more than {MAX_DENSE} dense tensors")
+        st = getattr(self, "_dense_adam", None)
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
+        if st is None or st["key"] != key:
+            dl = DenseList()
+            dl.n = len(params)
+            keep = []
+            old = st["state"] if st is not None else {}
+            state = {}
+            for i, p in enumerate(params):
+                if p.dtype != torch.float32 or not p.data.is_contiguous() or not p.grad.is_contiguous():
+                    raise TypeError("dense parameters and gradients must be contiguous float32")
+                mv = old.get(id(p)) or (torch.zeros_like(p.data), torch.zeros_like(p.data))
+                state[id(p)] = mv
+                dl.w[i], dl.g[i], dl.m[i], dl.v[i], dl.numel[i] = p.data.data_ptr(), p.grad.data_ptr(), mv[0].data_ptr(), mv[1].data_ptr(), p.numel()
+                keep.append(p)
+            st = self._dense_adam = {"key": key, "dl": dl, "state": state, "step": st["step"] if st is not None else 0}
+        st["step"] += 1
+        adam = make_adam(lr, betas[0], betas[1], eps, weight_decay, st["step"], 1.0)
+        check(self.ops.lib.tgr_adam_dense(C.byref(st["dl"]), C.addressof(adam), None, _stream()), "tgr_adam_dense")
+
     @staticmethod
     def _alloc_shard(n_local: int, H: int, device, world_size: int, group, want_p2p: bool):
         """The rank's slice of the flat table. With p2p (factored path, W > 1, NCCL group up) it is allocated as torch
