@@ -292,7 +292,7 @@ def run_gpu(args):
     clocks = ClockSampler(local_rank, period_ms=args.clock_period_ms)
     if not args.no_clocks:
         clocks.start()
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3 * n_batches)):   # every distinct batch shape several times (allocator warm)
         one_step(*dev_steps[i % n_batches])
     torch.cuda.synchronize()
     clocks.mark()

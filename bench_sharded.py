@@ -190,7 +190,7 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     clocks = bench.ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
-    nw = max(args.warmup, 3)
+    nw = max(args.warmup, 3 * n_batches)     # every distinct batch shape several times: the caching allocator has seen every size
     for i in range(nw):
         one_step(*dev_steps[i % n_batches], next_pbs=dev_steps[(i + 1) % n_batches][0])
     torch.cuda.synchronize()

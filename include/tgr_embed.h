@@ -302,6 +302,10 @@ int tgr_peer_pull(const uint32_t* const* src_ptrs, const int64_t* counts, int n_
  * key of the concatenation (ties keep bucket order) — replaces the owner-side second radix sort. */
 int tgr_merge_buckets(const uint32_t* rows, const int64_t* counts, int n_buckets, int with_code, uint32_t* keys_out,
                       uint32_t* code_out, void* stream);
+/* Device-side barrier between the ranks of one node over symmetric memory: flags[r] = rank r's uint32 flag array
+ * (>= n_peers entries, zero-initialised, mapped into this process), epoch = 1, 2, 3, ... identical on every rank. Orders
+ * everything enqueued before it on `stream` (on every rank) before everything enqueued after it. */
+int tgr_peer_barrier(uint32_t* const* flags, int rank, int n_peers, uint32_t epoch, void* stream);
 /* out[i] = scale * sum over r (ascending) of peers[r][i]: one-shot pull all-reduce of a small replicated buffer. */
 int tgr_allreduce_peers(const float* const* peers, int n_peers, int64_t n, float scale, float* out, void* stream);
 

@@ -174,6 +174,7 @@ SIGNATURES = {
     "tgr_peer_put": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "tgr_peer_pull": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_void_p]),
     "tgr_merge_buckets": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tgr_peer_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p]),
     "tgr_allreduce_peers": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
     "tgr_remap_arrays": (C.c_int, [C.POINTER(Table), C.c_int, C.POINTER(Call), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_void_p), C.c_void_p]),

@@ -136,6 +136,45 @@ extern "C" int tgr_merge_buckets(const uint32_t* rows, const int64_t* counts, in
   return check_launch("merge_buckets");
 }
 
+// Device-side barrier between the W ranks over a symmetric flag array (uint32 [>= W] per rank, zero-initialised; every rank
+// passes the same monotonically increasing epoch): thread r publishes everything this rank's stream has written so far
+// (system-scope fence + release store of the epoch into slot [rank] of rank r's array) and waits until rank r's epoch has
+// arrived in its own array. torch's symmetric-memory barrier does the same on its signal pads but costs ~0.12 ms of HOST time
+// per call (three per sharded step, tools/profile_sharded.py CPROFILE=1). One CTA; the wait is bounded (~20 s) and traps.
+namespace tgr {
+struct PeerU32 { uint32_t* p[TGR_MAX_PEERS]; };
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerU32 flags, int rank, int W, uint32_t epoch) {
+  const int r = threadIdx.x;
+  if (r < W) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[r] + rank), "r"(epoch) : "memory");
+    const uint32_t* mine = flags.p[rank] + r;
+    const long long t0 = clock64();
+    uint32_t v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int32_t)(v - epoch) >= 0) break;
+      if (clock64() - t0 > 40000000000ll) __trap();   // a peer never arrived
+      __nanosleep(64);
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+}  // namespace tgr
+
+extern "C" int tgr_peer_barrier(uint32_t* const* flags, int rank, int n_peers, uint32_t epoch, void* stream) {
+  tgr::TimedScope tgr_timed_("peer_barrier", stream);
+  TGR_REQUIRE(flags && n_peers > 0 && n_peers <= TGR_MAX_PEERS && n_peers <= 32 && rank >= 0 && rank < n_peers, "bad argument");
+  PeerU32 f{};
+  for (int r = 0; r < n_peers; ++r) {
+    TGR_REQUIRE(flags[r] != nullptr, "peer %d: NULL flag array", r);
+    f.p[r] = flags[r];
+  }
+  TGR_K(peer_barrier_kernel)<<<1, 32, 0, (cudaStream_t)stream>>>(f, rank, n_peers, epoch);
+  return check_launch("peer_barrier");
+}
+
 extern "C" int tgr_allreduce_peers(const float* const* peers, int n_peers, int64_t n, float scale, float* out, void* stream) {
   tgr::TimedScope tgr_timed_("allreduce_peers", stream);
   TGR_REQUIRE(peers && out && n_peers > 0 && n_peers <= TGR_MAX_PEERS && n >= 0 && n % 4 == 0, "bad argument (n must be a multiple of 4)");

@@ -1033,8 +1033,23 @@ class ShardedBaselineEmbedding(torch.nn.Module):
                              [[b + 4 * (2 * n_g + q * n_r) for b in base] for q in range(2)])
 
     def _symm_barrier(self):
-        """Device-side barrier over the signal pads of the mailbox allocation (blocks the current stream, not the host)."""
-        self._io_hdl.barrier(channel=0)
+        """Device-side barrier between the ranks (blocks the current stream, not the host): tgr_peer_barrier over a symmetric
+        flag array; falls back to the signal pads of the mailbox allocation."""
+        b = getattr(self, "_bar_state", None)
+        if b is None:
+            buf, hdl = self._alloc_symm((64,), torch.int32, self.dev, self.W, self.group)
+            if hdl is None or self.W > 32:
+                b = self._bar_state = False
+            else:
+                views = [hdl.get_buffer(r, (64,), torch.int32) for r in range(self.W)]
+                hdl.barrier(channel=0)          # every rank has zeroed its flags before anybody signals
+                b = self._bar_state = {"buf": buf, "hdl": hdl, "views": views, "epoch": 0,
+                                       "ptrs": (C.c_void_p * self.W)(*[v.data_ptr() for v in views])}
+        if b is False:
+            self._io_hdl.barrier(channel=0)
+            return
+        b["epoch"] += 1
+        check(self.ops.lib.tgr_peer_barrier(b["ptrs"], self.rank, self.W, b["epoch"], _stream()), "tgr_peer_barrier")
 
     @staticmethod
     def _alloc_symm(shape, dtype, device, world_size: int, group):
@@ -1079,11 +1094,11 @@ class ShardedBaselineEmbedding(torch.nn.Module):
             return flat
         t, hdl, views, tmp = d
         if pre_barrier:
-            hdl.barrier(channel=0)
+            self._symm_barrier()
         ptrs = (C.c_void_p * self.W)(*[v.data_ptr() for v in views])
         check(self.ops.lib.tgr_allreduce_peers(ptrs, self.W, t.numel(), 1.0 / self.W if average else 1.0, tmp.data_ptr(), _stream()),
               "tgr_allreduce_peers")
-        hdl.barrier(channel=0)          # every rank has read every buffer before anybody overwrites its own
+        self._symm_barrier()            # every rank has read every buffer before anybody overwrites its own
         flat.copy_(tmp)
         return flat
 

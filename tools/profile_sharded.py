@@ -19,9 +19,13 @@ m = ShardedBaselineEmbedding(cfg.user_num, cfg.item_num, cfg.statistics(), cfg.f
 with torch.no_grad():
     m.local_table.normal_(0, 0.05)
 dense = [p for p in m.parameters() if p is not m.local_table]
-opt = torch.optim.AdamW(dense, lr=1e-3, betas=(0.9, 0.98), fused=True)
-st = w.make_step(1000 * rank)
-pbs = [to_device(lay, pc, dev) for pc in st.calls]; ups = [torch.from_numpy(r).to(dev) for r in st.upstream]
+opt = None
+NB = int(os.environ.get("BATCHES", "1"))          # distinct batches cycled (bench.py cycles 4)
+sts = [w.make_step(1000 * rank + s) for s in range(NB)]
+all_pbs = [[to_device(lay, pc, dev) for pc in st.calls] for st in sts]
+all_ups = [[torch.from_numpy(r).to(dev) for r in st.upstream] for st in sts]
+pbs, ups = all_pbs[0], all_ups[0]
+step_i = [0]
 
 flat_grad = m.symm_empty(sum(p.numel() for p in dense))
 o = 0
@@ -30,14 +34,16 @@ for p in dense:
 LOOK = os.environ.get("LOOKAHEAD", "1") == "1"
 
 def step():
+    k = step_i[0] % NB; step_i[0] += 1
+    pbs, ups, nxt = all_pbs[k], all_ups[k], all_pbs[(k + 1) % NB]
     flat_grad.zero_()
     m.prefetch(pbs)
-    if LOOK: m.prepare_next(pbs)
+    if LOOK: m.prepare_next(nxt)
     outs = [m.feat2emb_packed(pb) for pb in pbs]
     torch.autograd.backward(outs, ups)
     m.fused_step(lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
     m.allreduce_dense_(flat_grad)
-    opt.step()
+    m.dense_adam_(dense, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
     if LOOK: m.finish_prepare()
 
 for _ in range(4): step()
@@ -46,6 +52,25 @@ t0 = time.perf_counter()
 for _ in range(10): step()
 torch.cuda.synchronize(); t1 = time.perf_counter()
 if rank == 0: print(f"wall {1e3*(t1-t0)/10:.3f} ms/step at W={world}")
+if os.environ.get("CPROFILE") == "1":
+    import cProfile, pstats, io
+    def timed(n):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n): step()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        return 1e3 * (t1 - t0) / n, 1e3 * (time.perf_counter() - t0) / n
+    e, w = timed(20)
+    if rank == 0: print(f"enqueue {e:.3f} ms/step, wall {w:.3f} ms/step")
+    pr = cProfile.Profile(); pr.enable()
+    for _ in range(20): step()
+    pr.disable(); torch.cuda.synchronize()
+    if rank == 0:
+        for key in ("cumulative", "tottime"):
+            sio = io.StringIO(); pstats.Stats(pr, stream=sio).sort_stats(key).print_stats(45)
+            print("==== cProfile by", key); print(sio.getvalue()[:7000])
+    dist.barrier(); dist.destroy_process_group(); sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3): step()
