@@ -203,6 +203,12 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
 
     l0 = n_launch()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the sharded step is issued eagerly and every rank waits for the slowest at four barriers per step: keep the Python
+    # garbage collector's pauses (thousands of short-lived ctypes / tensor objects per step) out of the loop
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     torch.cuda.synchronize()
     ev0.record()
     rows = 0
@@ -212,6 +218,7 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
         rows += lookups[k]
     ev1.record()
     torch.cuda.synchronize()
+    gc.enable()
     dist.barrier()
     clk = clocks.stop() if clocks else None
     ms_local = ev0.elapsed_time(ev1)
