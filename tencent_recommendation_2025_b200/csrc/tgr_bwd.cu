@@ -9,33 +9,25 @@
 //                calls, compacted in (call, token, slot) order (count -> scan -> emit, no atomics)
 //   sort_pairs   (tgr_sort.cu) stable LSD radix sort on the key bits only (stability keeps each row's contributions
 //                in ascending (call, token) order = embedding_dense_backward's per-row order, F16)
-//   dedup        run-length encode -> unique keys / segment offsets / per-entry segment index
+//   dedup        run-length encode -> unique keys / segment offsets / per-entry segment index (8 keys per thread; the
+//                emit pass can also write the remapped ids of the SINGLE slots)
 //   reduce       fixed-tile segmented sum of the concat-gradient rows the sources point at; short runs
 //                are summed sequentially in order, runs crossing tile borders are stitched from
 //                per-tile partials in a fixed order (bitwise reproducible, no float atomics);
 //                mode 1 applies the AdamW row update in the same pass (w, m, v read+written once)
 //
 // All kernels are HBM/L2-bound integer/byte movers: 128-bit row accesses, one LANES=H/4 thread
-// group per gradient row, grids sized by the (host-known) entry count.
+// group per gradient row, grids sized by the entry count — host-known, or an upper bound with the count read from device
+// memory (the *_dn variants: what makes the step capturable in a CUDA graph).
 #include "tgr_common.cuh"
 #include "tgr_rows.cuh"
 
 namespace tgr {
 
 // =================================================================================================
-// generic ordered compaction: count -> single-CTA scan -> emit           (1024 entries per block)
+// single-CTA exclusive scan of per-block counts (shared by build_keys and dedup)
 // =================================================================================================
 constexpr int kScanBlock = 1024;
-
-template <class F>
-__global__ void __launch_bounds__(kScanBlock) flag_count_kernel(const __grid_constant__ F f, int64_t n, int32_t* __restrict__ block_count,
-                                                                const int32_t* __restrict__ n_dev) {
-  if (n_dev) n = min(n, (int64_t)__ldg(n_dev));
-  const int64_t e = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-  const int v = (e < n) && f.valid(e);
-  const int c = __syncthreads_count(v);
-  if (threadIdx.x == 0) block_count[blockIdx.x] = c;
-}
 
 // exclusive scan of block counts in place; total -> *total_out (and optional second copy)
 __global__ void __launch_bounds__(kScanBlock) block_scan_kernel(int32_t* __restrict__ block_count, int n_blocks,
@@ -74,40 +66,6 @@ __global__ void __launch_bounds__(kScanBlock) block_scan_kernel(int32_t* __restr
     __syncthreads();
   }
   if (threadIdx.x == 0 && total_out) *total_out = carry_s;
-}
-
-// position of this thread's entry among the block's valid entries (exclusive), ordered by thread index
-__device__ __forceinline__ int block_rank(int v, int32_t* warp_cnt /*[32] shared*/) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned b = __ballot_sync(0xffffffffu, v);
-  const int r = __popc(b & ((1u << lane) - 1u));
-  if (lane == 0) warp_cnt[wid] = __popc(b);
-  __syncthreads();
-  if (wid == 0) {
-    int w = warp_cnt[lane];
-    const int orig = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += y;
-    }
-    warp_cnt[lane] = w - orig;  // exclusive
-  }
-  __syncthreads();
-  return r + warp_cnt[wid];
-}
-
-template <class F>
-__global__ void __launch_bounds__(kScanBlock) flag_emit_kernel(const __grid_constant__ F f, int64_t n, const int32_t* __restrict__ block_off,
-                                                               const int32_t* __restrict__ n_dev) {
-  if (n_dev) n = min(n, (int64_t)__ldg(n_dev));
-  __shared__ int32_t warp_cnt[32];
-  const int64_t e = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
-  const int v = (e < n) && f.valid(e);
-  const int r = block_rank(v, warp_cnt);
-  const int64_t pos = (int64_t)block_off[blockIdx.x] + r;
-  if (v) f.emit(e, pos);
-  if (e < n) f.every(e, pos + v - 1);  // index of the last valid entry at or before e
 }
 
 // =================================================================================================
@@ -236,21 +194,6 @@ __global__ void __launch_bounds__(kKT) keys_block_kernel(const __grid_constant__
 // =================================================================================================
 // dedup (run-length encode of sorted keys)
 // =================================================================================================
-struct HeadFunctor {
-  const uint32_t* __restrict__ k;
-  uint32_t* uniq;
-  int32_t* seg_off;
-  int32_t* seg_of_entry;  // optional
-  __device__ __forceinline__ bool valid(int64_t e) const { return e == 0 || k[e] != k[e - 1]; }
-  __device__ __forceinline__ void emit(int64_t e, int64_t pos) const {
-    uniq[pos] = k[e];
-    seg_off[pos] = (int32_t)e;
-  }
-  __device__ __forceinline__ void every(int64_t e, int64_t seg) const {
-    if (seg_of_entry) seg_of_entry[e] = (int32_t)seg;
-  }
-};
-
 // ---- dedup of the sorted keys: 8 keys per thread, 2048 per CTA (the generic one-entry-per-thread compaction above spent
 //      17 + 26 us on 2.85 M keys; profiles/README.md r2 graph timeline). The emit pass optionally does the id remap of the
 //      SINGLE slots as well (what tgr_remap_scatter does from seg_of_entry): one read of the sorted payloads instead of two

@@ -5,9 +5,13 @@
 // packed calls are known. Driving them one ctypes call at a time left the GPU idle behind the Python interpreter
 // (1.85 ms of host time per 1.4 ms of kernels, profiles/README.md), so the sequencing lives here:
 //
-//   tgr_fact_prepare        carve the group's arena, keys -> sort -> dedup -> id remap                (value independent)
+//   tgr_fact_prepare        carve the group's arena, keys -> sort -> dedup + id remap                 (value independent)
+//   tgr_fact_mm_branch      (optional) mm fold + projection of every call on an internal side stream
 //   tgr_fact_call_forward   [first call: project unique rows, fold mm weights] mm projection, gather-sum forward
-//   tgr_fact_call_backward  relu mask + bias grads + mm chain; with `finish`: segmented reduce, row grads, dW
+//   tgr_fact_call_backward  relu mask + bias grads; with `finish`: mm chain rule (side stream), segmented reduce, row grads, dW
+//
+// With tgr_fact_group_t.n_is_capacity the sequence depends on the calls' SHAPES only (the lookup count is read from device
+// memory), so a whole step can be captured in a CUDA graph (graphed.py).
 //
 // Every buffer is carved from ONE caller-provided arena (torch-allocated); nothing is allocated here and all work is
 // enqueued on the caller's stream in a fixed order, so results are identical to the per-kernel entry points.
