@@ -1,17 +1,25 @@
 """bench.py — embedding fwd+bwd rows/sec of the TencentGR sparse-feature path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c3|c5|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c1|c2|c3|c4|c5]
+                    [--path factored|concat] [--graph auto|plain|off]
 
 One "step" = one training step's worth of the hot path on one synthetic batch:
-  3 x feat2emb forward (seq with users, pos, neg: model.py:324,376-377)  — fused gather/pool/concat kernels,
-      mm projection, then the reference's own itemdnn/userdnn torch calls
-  + backward from injected upstream gradients            — torch Linear backward, mm dW/db,
-      key build, radix sort, fixed-tile segmented reduction
-  + fused sparse AdamW row update of every touched table row.
-"row" = one non-padding table-row lookup in a forward call. `value` = rows/s with inputs resident in HBM;
-`e2e` = the same step driven from HOST packed buffers (pinned H2D inside the timed region, loss read back).
-`roofline` describes the dominant kernel, timed live with CUDA events on the launching stream.
-`--impl reference` times the CPU oracle port (the reference's torch op sequence + dense AdamW, all host threads).
+  3 x feat2emb forward (seq with users, pos, neg: model.py:324,376-377)
+  + backward from injected upstream gradients
+  + AdamW on the path's Linear layers + fused sparse AdamW row update of every touched table row.
+"row" = one non-padding table-row lookup in a forward call.
+
+N = 1 (default path `factored`: itemdnn / userdnn folded into the step's deduplicated rows):
+  `value`  rows/s of the step replayed from a CUDA graph with the NEXT batch's key processing on a branch of the same graph
+           (graphed.PipelinedStep), slim inputs resident in HBM, CUDA events around K replays; `eager` in the line = the same
+           step issued from Python (host-bound), `--graph plain` = one step per graph, `--graph off` = eager only.
+  `e2e`    the same replays fed from pinned HOST buffers (ids + user tokens, one H2D copy per step on a copy stream; the item
+           feature / mm tables are resident in HBM) with the step's result copied back and read on the host every step.
+  `roofline`  the C-ABI entry with the largest CUDA-event time (events recorded inside the library on the launching stream,
+           an eager pass over the same steps); `roofline.kernels` lists every entry.
+  `cpu_baseline` / `gpu_eager_baseline`  the UNMODIFIED reference (baseline/_ref) on the host cores / as torch eager on the GPU.
+N > 1 (torchrun): bench_sharded.py — tables row-sharded over the ranks, peer-memory exchange, value = all ranks' rows / max time.
+`--impl reference` times the unmodified reference's CPU implementation of the same step (full batches, all host threads).
 """
 from __future__ import annotations
 
@@ -825,7 +833,6 @@ def main():
                     help="concat: gather/pool/concat kernels + torch itemdnn/userdnn; factored: DNN folded into unique rows")
     ap.add_argument("--batch", type=int, default=1024, help="sequences per GPU")
     ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches to cycle")
-    ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-items", default="auto", choices=["auto", "on", "off"],
                     help="e2e leg with the item feature / mm tables resident in HBM (auto: c1 and c2)")
