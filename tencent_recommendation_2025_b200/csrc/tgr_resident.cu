@@ -9,11 +9,11 @@
 namespace tgr {
 
 // ids[t, :] = 0 except ids[t, id_col] = item_ids[t] and ids[t, col0 + j] = feat[item_ids[t], j].
-// CTA = 256 tokens: thread t reads its id and the item's feature row (all loads of a thread independent, 8-byte pieces when
+// CTA = kExpTok tokens: thread t reads its id and the item's feature row (all loads of a thread independent, 8-byte pieces when
 // the row allows), stages the packed row in shared memory, and the CTA copies the [256, n_single] block out linearly (it is
 // contiguous in `ids`), 16 bytes per lane. The first version (one thread per element: id load -> dependent feature load ->
 // store) took 10 us per call at T = 103 k.
-constexpr int kExpTok = 256;
+constexpr int kExpTok = 64;    // 5 KB of staging per CTA: small enough to run beside the 218 KB row-gradient kernel (PipelinedStep branch)
 __global__ void __launch_bounds__(kExpTok) expand_items_kernel(const int32_t* __restrict__ item_ids, int64_t T, int n_single, int id_col,
                                                                int col0, const int32_t* __restrict__ feat, int n_feat, int64_t n_items,
                                                                int32_t* __restrict__ ids) {
