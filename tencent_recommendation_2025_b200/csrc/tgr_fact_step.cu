@@ -165,6 +165,10 @@ extern "C" int tgr_fact_prepare(const tgr_table_t* tables, int n_tables, tgr_fac
     cudaMemsetAsync(g->mm_A[f], 0, (size_t)g->H * g->mm_dim[f] * sizeof(float), st);
     cudaMemsetAsync(g->mm_s[f], 0, (size_t)g->H * sizeof(float), st);
   }
+  // remapped ids start from zero (padding): cleared FIRST — when the group is prepared on a branch next to the previous
+  // step's row-gradient kernel these copy-engine nodes run at once instead of sitting on the tail of the key chain
+  for (int c = 0; c < g->n_calls; ++c)
+    cudaMemsetAsync(g->ids_u[c], 0, (size_t)g->calls[c].T * g->calls[c].n_single * sizeof(int32_t), st);
   if (int rc = tgr_bwd_build_keys(tables, n_tables, g->calls, g->n_calls, g->keys_in, g->srcs_in, g->n_valid, g->ws,
                                   g->ws_bytes, stream)) return rc;
   // n_is_capacity: g->n only bounds the count; the kernels read the count build_keys left in g->n_valid, so the launch
@@ -172,13 +176,9 @@ extern "C" int tgr_fact_prepare(const tgr_table_t* tables, int n_tables, tgr_fac
   const int32_t* nd = g->n_is_capacity ? g->n_valid : nullptr;
   if (int rc = sort_pairs_dn(g->keys_in, g->srcs_in, g->keys, g->srcs, g->n, g->key_bits, g->ws, g->ws_bytes, nd, stream))
     return rc;
-  // dedup + id remap of the SINGLE slots in one pass over the sorted pairs (ids_u zeroed first: padding ids stay 0)
+  // dedup + id remap of the SINGLE slots in one pass over the sorted pairs (ids_u were zeroed above: padding ids stay 0)
   int32_t* outs[TGR_MAX_CALLS];
-  for (int c = 0; c < g->n_calls; ++c) {
-    const tgr_call_t& cl = g->calls[c];
-    outs[c] = g->ids_u[c];
-    cudaMemsetAsync(g->ids_u[c], 0, (size_t)cl.T * cl.n_single * sizeof(int32_t), st);
-  }
+  for (int c = 0; c < g->n_calls; ++c) outs[c] = g->ids_u[c];
   if (int rc = dedup_remap_dn(g->keys, g->srcs, g->n, g->uniq, g->seg_off, g->seg_of, g->n_unique, g->ws, g->ws_bytes, g->calls,
                               g->n_calls, outs, nd, stream)) return rc;
   // array values (a token may hold several): searching remap, they are few — one launch for all of them
