@@ -14,7 +14,8 @@ What has to hold for a replay to be the step of a NEW batch:
   the body must be ``capturable=True``.
 
 ``body(pbs)`` is the user's step on the static ``PackedBatch``es — prefetch, ``feat2emb_packed`` x3, trunk + loss (or injected
-upstream gradients), ``backward()``, the dense optimizer step, ``fused_step`` — run eagerly a few times, then captured.
+upstream gradients), ``backward()``, the dense optimizer step, ``fused_step`` — run eagerly ``warmup`` times on the example
+batch (REAL steps: they update the model), then captured.
 Results are identical to the eager step (same kernels, same order; tests/test_gpu_graphed.py compares bit for bit).
 """
 from __future__ import annotations
@@ -175,9 +176,13 @@ class PipelinedStep:
     """``GraphedStep`` with the value-independent half of the NEXT step inside the same graph, on a forked branch.
 
     Expansion, key building, sort, dedup and id remap of a batch (~170 us of issue-bound kernels at the C2 benchmark) depend on
-    the batch alone, not on the tables, so replay r runs them for batch r+1 NEXT TO the forward / backward / row update of
-    batch r (L2- and HBM-bound kernels) instead of in front of its own step. Two slots (static inputs, expansion targets,
-    group arena) alternate roles, hence two graphs: graph[s] computes the batch prepared in slot s and prepares slot 1-s.
+    the batch alone, not on the tables, so replay r runs them for batch r+1 NEXT TO the row-gradient GEMMs and the row update
+    of batch r (latency- / HBM-bound kernels; the branch forks after the segmented reduce, see ``_step``) instead of in front
+    of its own step. Two slots (static inputs, expansion targets, group arena) alternate roles, hence two graphs: graph[s]
+    computes the batch prepared in slot s and prepares slot 1-s.
+
+    Construction runs ``max(2, warmup)`` REAL steps on ``example`` (they update the model, like the warm-up of
+    ``GraphedStep``) before capturing.
 
         runner.prime(b0)            # batch 0 into the slot the first replay computes; its key processing runs eagerly
         runner.submit(b1)           # (or load(dev_ints)): the batch the next run() PREPARES
